@@ -1,0 +1,208 @@
+/* luxrays_b200.h -- C ABI of the B200 (sm_100a) closest-hit intersection device.
+ *
+ * This is the drop-in boundary: a thin, torch-free, exception-free C
+ * interface that replaces what the reference reaches through cuew/NVRTC inside
+ *   - luxrays::CUDADevice          (src/luxrays/devices/cudadevice.cpp:205-211,407-540:
+ *                                   Push/Pop current, Alloc/Free, Read/Write, Flush/Finish)
+ *   - luxrays::BVHKernel           (src/luxrays/accelerators/bvhaccelhw.cpp:38-268: vertex + node
+ *                                   upload, kernel launch)
+ *   - luxrays::MBVHKernel          (src/luxrays/accelerators/mbvhaccelhw.cpp:41-306 upload,
+ *                                   :308-466 UpdateBVHNodes/Update, :468-507 launch)
+ *   - bvh.cl / mbvh.cl             (include/luxrays/accelerators/bvh.cl:228-260, mbvh.cl:351-383:
+ *                                   Accelerator_Intersect_RayBuffer)
+ *
+ * The C++ host layer in luxcore_b200/host (namespace luxrays, same class names as the reference)
+ * sits on top of this ABI; INTEGRATION.md shows the binding a LuxCore maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = LRB_OK, anything else is an error whose text is
+ *     available (per calling thread) from lrb_last_error_string(); no C++ exception crosses the ABI;
+ *   - all device work (copies, re-layout kernels, traces) is enqueued IN ORDER on the device's
+ *     stream; lrb_sync() is the only implicit synchronisation point besides `blocking` copies --
+ *     the same contract as the reference's single in-order queue (cudadevice.cpp:407-442);
+ *   - the structs below are bit-identical to the reference wire types, so the reference's own
+ *     arrays are handed over unchanged.
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with
+ *     LRB_ERR_NO_DEVICE.
+ */
+#ifndef LUXRAYS_B200_H
+#define LUXRAYS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRB_API __attribute__((visibility("default")))
+
+/* status codes */
+#define LRB_OK 0
+#define LRB_ERR_INVALID 1      /* bad argument */
+#define LRB_ERR_CUDA 2         /* a CUDA runtime call failed */
+#define LRB_ERR_NO_DEVICE 3    /* no usable CUDA device */
+#define LRB_ERR_OOM 4
+#define LRB_ERR_INTERNAL 5
+
+#define LRB_NULL_INDEX 0xffffffffu
+#define LRB_RAY_FLAGS_NONE 0u
+#define LRB_RAY_FLAGS_MASKED 1u   /* include/luxrays/core/geometry/ray_types.cl:21-22 */
+
+/* luxrays::Ray / ocl::Ray -- include/luxrays/core/geometry/ray.h:35-88, ray_types.cl:24-31. 48 B. */
+typedef struct {
+	float o[3];
+	float d[3];
+	float mint, maxt, time;
+	uint32_t flags;
+	float pad[2];
+} lrb_ray;
+
+/* luxrays::RayHit -- ray.h:95-103, ray_types.cl:33-36. 20 B. Miss <=> meshIndex == LRB_NULL_INDEX. */
+typedef struct {
+	float t, b1, b2;
+	uint32_t meshIndex, triangleIndex;
+} lrb_rayhit;
+
+/* ocl::BVHArrayNode -- include/luxrays/core/bvh/bvhbuild_types.cl:21-42. 32 B.
+ * nodeData: bit 31 = leaf flag, bits 0-30 = skip index (bvhbuild.h:40-41). */
+typedef struct {
+	union {
+		struct { float bboxMin[3], bboxMax[3]; } bvhNode;
+		struct { uint32_t v[3], meshIndex, triangleIndex; } triangleLeaf;
+		struct { uint32_t leafIndex, transformIndex, motionIndex, meshOffsetIndex; } bvhLeaf;
+	};
+	uint32_t nodeData;
+	int32_t pad0;
+} lrb_bvh_node;
+
+/* ocl::MotionSystem -- include/luxrays/core/geometry/motionsystem_types.cl:49-55. 16 B.
+ * Indices into the flat interpolated-transform array; the inverse range is ignored. */
+typedef struct {
+	uint32_t interpolatedTransformFirstIndex;
+	uint32_t interpolatedTransformLastIndex;
+	uint32_t interpolatedInverseTransformFirstIndex;
+	uint32_t interpolatedInverseTransformLastIndex;
+} lrb_motion_system;
+
+/* Size of one ocl::InterpolatedTransform record (motionsystem_types.cl:21-47); the device reads
+ * the reference layout directly from the host array and re-packs what traversal needs. */
+#define LRB_INTERPOLATED_TRANSFORM_SIZE 576
+
+typedef struct lrb_device lrb_device;
+typedef struct lrb_scene lrb_scene;
+
+typedef struct {
+	int cuda_ordinal;
+	int cc_major, cc_minor;
+	int sm_count;
+	int l2_bytes;
+	uint64_t total_mem_bytes;
+	char name[128];
+} lrb_device_props;
+
+/* What lrb_mbvh_upload consumes: exactly the arrays MBVHKernel walks (mbvhaccelhw.cpp:63-175,308-440)
+ * BEFORE its index rewriting -- i.e. the accelerator's own, tree-relative arrays. */
+typedef struct {
+	const lrb_bvh_node *root_nodes;        /* MBVHAccel::bvhRootTree */
+	uint32_t n_root_nodes;                 /* MBVHAccel::nRootNodes */
+	uint32_t n_leaves;                     /* uniqueLeafs.size() */
+	const lrb_bvh_node *const *leaf_nodes; /* uniqueLeafs[i]->bvhTree */
+	const uint32_t *leaf_n_nodes;          /* uniqueLeafs[i]->nNodes */
+	const float *const *leaf_vertices;     /* uniqueLeafs[i]->meshes[0]->GetVertices(): local xyz, 12-B stride */
+	const uint32_t *leaf_n_vertices;
+	const float *transforms_minv;          /* uniqueLeafsTransform[i]->mInv, 16 floats row-major each */
+	uint32_t n_transforms;
+	const lrb_motion_system *motion_systems;
+	uint32_t n_motion_systems;
+	const void *interpolated_transforms;   /* n * LRB_INTERPOLATED_TRANSFORM_SIZE bytes */
+	uint32_t n_interpolated_transforms;
+} lrb_mbvh_desc;
+
+typedef struct {
+	uint32_t n_ref_nodes;          /* BVHArrayNode count received */
+	uint32_t n_wide_nodes;         /* 128-B wide nodes after re-layout */
+	uint32_t n_triangles;          /* 48-B pre-gathered triangle records */
+	uint32_t n_instances;          /* 32-B instance records (MBVH) */
+	uint32_t stack_need;           /* worst-case traversal stack entries */
+	uint32_t two_level;            /* 0 = BVH, 1 = MBVH */
+	uint64_t device_bytes;         /* bytes of device memory owned by the scene */
+} lrb_scene_info;
+
+typedef struct {
+	uint64_t rays_traced;          /* rays submitted (masked included, like cudaintersectiondevice.cpp:85) */
+	uint64_t trace_launches;       /* traversal kernel launches */
+	uint64_t kernel_launches;      /* every kernel launched by this library (trace + re-layout) */
+	uint64_t h2d_bytes, d2h_bytes;
+	uint64_t device_bytes_in_use;
+} lrb_counters;
+
+/* per-batch traversal statistics from the instrumented kernel (lrb_trace_stats) */
+typedef struct {
+	uint64_t rays;                 /* non-masked rays */
+	uint64_t wide_nodes;           /* 128-B node fetches */
+	uint64_t triangles;            /* 48-B triangle record fetches */
+	uint64_t instances;            /* instance entries (32-B record + 64-B matrix) */
+	uint64_t motion_samples;       /* motion leaves entered */
+	uint64_t max_stack;            /* deepest stack seen */
+} lrb_trace_stats_t;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+LRB_API int lrb_device_count(int *count);
+LRB_API int lrb_device_create(int cuda_ordinal, lrb_device **out);       /* replaces CUDADevice ctor + Start */
+LRB_API int lrb_device_destroy(lrb_device *dev);
+LRB_API int lrb_device_get_props(lrb_device *dev, lrb_device_props *out);
+/* Adopt a caller-owned cudaStream_t (e.g. the application's render stream) as the in-order queue;
+ * NULL restores the device's own stream. */
+LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
+LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
+/* Tunables: "block_threads", "blocks_per_sm", "kernel" = "persistent"|"simple", "l2_persist" = 0|1. */
+LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
+
+/* ---- memory + queue (cudadevice.cpp:407-540) ------------------------------------------- */
+LRB_API int lrb_alloc(lrb_device *dev, size_t bytes, void **devptr);
+LRB_API int lrb_free(lrb_device *dev, void *devptr);
+LRB_API int lrb_h2d(lrb_device *dev, void *dst_dev, const void *src_host, size_t bytes, int blocking);
+LRB_API int lrb_d2h(lrb_device *dev, void *dst_host, const void *src_dev, size_t bytes, int blocking);
+LRB_API int lrb_flush(lrb_device *dev);
+LRB_API int lrb_sync(lrb_device *dev);                                   /* FinishQueue */
+
+/* ---- scenes ---------------------------------------------------------------------------- */
+/* Single-level BVH (replaces the BVHKernel ctor).  `nodes` is BVHAccel::bvhTree with its original,
+ * mesh-relative vertex indices; `xyz` the concatenation of every mesh's vertices
+ * (Mesh::GetVertex(TRANS_IDENTITY, i), 12-B stride) and mesh_vertex_offsets[m] the first vertex of
+ * mesh m in it (bvhaccelhw.cpp:68-92,126-145).  n_nodes == 0 is the empty DataSet: every ray misses. */
+LRB_API int lrb_bvh_upload(lrb_device *dev, const lrb_bvh_node *nodes, uint32_t n_nodes,
+		const float *xyz, uint64_t n_vertices, const uint32_t *mesh_vertex_offsets, uint32_t n_meshes,
+		lrb_scene **out);
+/* Two-level MBVH (replaces the MBVHKernel ctor). */
+LRB_API int lrb_mbvh_upload(lrb_device *dev, const lrb_mbvh_desc *desc, lrb_scene **out);
+/* MBVHKernel::Update (mbvhaccelhw.cpp:442-466): new root tree + new inverse instance matrices;
+ * leaf trees, vertices and motion systems are kept. */
+LRB_API int lrb_mbvh_update(lrb_scene *scene, const lrb_bvh_node *root_nodes, uint32_t n_root_nodes,
+		const float *transforms_minv, uint32_t n_transforms);
+LRB_API int lrb_scene_free(lrb_scene *scene);
+LRB_API int lrb_scene_get_info(lrb_scene *scene, lrb_scene_info *out);
+
+/* ---- trace ----------------------------------------------------------------------------- */
+/* Accelerator_Intersect_RayBuffer: rays_dev = ray_count packed lrb_ray, hits_dev = ray_count packed
+ * lrb_rayhit, both DEVICE pointers (from lrb_alloc or any CUDA allocation of this device, peer-mapped
+ * memory included).  Asynchronous.  Rays with flags & LRB_RAY_FLAGS_MASKED are skipped and their
+ * RayHit is left untouched (bvh.cl:242-244). */
+LRB_API int lrb_trace(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count);
+/* Host-buffer convenience (the end-to-end path): H2D rays, trace, D2H hits, synchronise. */
+LRB_API int lrb_trace_host(lrb_scene *scene, const lrb_ray *rays, lrb_rayhit *hits, uint32_t ray_count);
+/* Same trace through the instrumented kernel; blocks and fills `stats`. hits_dev may be NULL. */
+LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
+		lrb_trace_stats_t *stats);
+
+/* ---- diagnostics ----------------------------------------------------------------------- */
+LRB_API const char *lrb_last_error_string(void);
+LRB_API int lrb_get_counters(lrb_device *dev, lrb_counters *out);
+LRB_API int lrb_reset_counters(lrb_device *dev);
+LRB_API const char *lrb_version_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUXRAYS_B200_H */

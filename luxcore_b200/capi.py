@@ -1,0 +1,298 @@
+"""ctypes binding of the C ABI declared in include/luxrays_b200.h (libluxrays_b200.so).
+
+This is the same boundary a LuxCore maintainer would bind from C++; Python uses it
+for the parity tests and the benchmark.  There is no fallback of any kind: a missing library or a
+missing CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libluxrays_b200.so")
+
+LRB_OK = 0
+LRB_ERR_INVALID, LRB_ERR_CUDA, LRB_ERR_NO_DEVICE, LRB_ERR_OOM, LRB_ERR_INTERNAL = 1, 2, 3, 4, 5
+NULL_INDEX = 0xFFFFFFFF
+RAY_FLAGS_MASKED = 1
+
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("mint", "<f4"), ("maxt", "<f4"), ("time", "<f4"),
+                      ("flags", "<u4"), ("pad", "<f4", 2)])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("b1", "<f4"), ("b2", "<f4"), ("meshIndex", "<u4"), ("triangleIndex", "<u4")])
+NODE_DTYPE = np.dtype([("w", "<u4", 6), ("nodeData", "<u4"), ("pad0", "<i4")])
+
+# every symbol include/luxrays_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "lrb_device_count", "lrb_device_create", "lrb_device_destroy", "lrb_device_get_props",
+    "lrb_device_set_stream", "lrb_device_get_stream", "lrb_device_set_option",
+    "lrb_alloc", "lrb_free", "lrb_h2d", "lrb_d2h", "lrb_flush", "lrb_sync",
+    "lrb_bvh_upload", "lrb_mbvh_upload", "lrb_mbvh_update", "lrb_scene_free", "lrb_scene_get_info",
+    "lrb_trace", "lrb_trace_host", "lrb_trace_stats",
+    "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
+]
+
+
+class DeviceProps(C.Structure):
+    _fields_ = [("cuda_ordinal", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int), ("sm_count", C.c_int),
+                ("l2_bytes", C.c_int), ("total_mem_bytes", C.c_uint64), ("name", C.c_char * 128)]
+
+
+class MBVHDesc(C.Structure):
+    _fields_ = [("root_nodes", C.c_void_p), ("n_root_nodes", C.c_uint32), ("n_leaves", C.c_uint32),
+                ("leaf_nodes", C.POINTER(C.c_void_p)), ("leaf_n_nodes", C.POINTER(C.c_uint32)),
+                ("leaf_vertices", C.POINTER(C.c_void_p)), ("leaf_n_vertices", C.POINTER(C.c_uint32)),
+                ("transforms_minv", C.c_void_p), ("n_transforms", C.c_uint32),
+                ("motion_systems", C.c_void_p), ("n_motion_systems", C.c_uint32),
+                ("interpolated_transforms", C.c_void_p), ("n_interpolated_transforms", C.c_uint32)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_ref_nodes", C.c_uint32), ("n_wide_nodes", C.c_uint32), ("n_triangles", C.c_uint32),
+                ("n_instances", C.c_uint32), ("stack_need", C.c_uint32), ("two_level", C.c_uint32),
+                ("device_bytes", C.c_uint64)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("rays_traced", C.c_uint64), ("trace_launches", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("device_bytes_in_use", C.c_uint64)]
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("wide_nodes", C.c_uint64), ("triangles", C.c_uint64),
+                ("instances", C.c_uint64), ("motion_samples", C.c_uint64), ("max_stack", C.c_uint64)]
+
+
+class LrbError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "luxrays_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built -- there is no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libluxrays_b200.so is missing (%s); run __graft_entry__.build() -- the B200 device "
+                              "has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
+        pvp = C.POINTER(C.c_void_p)
+        sig = {
+            "lrb_device_count": (i32, [C.POINTER(C.c_int)]),
+            "lrb_device_create": (i32, [i32, pvp]),
+            "lrb_device_destroy": (i32, [vp]),
+            "lrb_device_get_props": (i32, [vp, C.POINTER(DeviceProps)]),
+            "lrb_device_set_stream": (i32, [vp, vp]),
+            "lrb_device_get_stream": (i32, [vp, pvp]),
+            "lrb_device_set_option": (i32, [vp, C.c_char_p, C.c_char_p]),
+            "lrb_alloc": (i32, [vp, sz, pvp]),
+            "lrb_free": (i32, [vp, vp]),
+            "lrb_h2d": (i32, [vp, vp, vp, sz, i32]),
+            "lrb_d2h": (i32, [vp, vp, vp, sz, i32]),
+            "lrb_flush": (i32, [vp]),
+            "lrb_sync": (i32, [vp]),
+            "lrb_bvh_upload": (i32, [vp, vp, u32, vp, u64, vp, u32, pvp]),
+            "lrb_mbvh_upload": (i32, [vp, C.POINTER(MBVHDesc), pvp]),
+            "lrb_mbvh_update": (i32, [vp, vp, u32, vp, u32]),
+            "lrb_scene_free": (i32, [vp]),
+            "lrb_scene_get_info": (i32, [vp, C.POINTER(SceneInfo)]),
+            "lrb_trace": (i32, [vp, vp, vp, u32]),
+            "lrb_trace_host": (i32, [vp, vp, vp, u32]),
+            "lrb_trace_stats": (i32, [vp, vp, vp, u32, C.POINTER(TraceStats)]),
+            "lrb_last_error_string": (C.c_char_p, []),
+            "lrb_get_counters": (i32, [vp, C.POINTER(Counters)]),
+            "lrb_reset_counters": (i32, [vp]),
+            "lrb_version_string": (C.c_char_p, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != LRB_OK:
+        raise LrbError(rc, lib().lrb_last_error_string().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().lrb_device_count(C.byref(n))
+    if rc == LRB_ERR_NO_DEVICE:
+        return 0
+    _check(rc)
+    return n.value
+
+
+class Device:
+    """One B200 behind the C ABI (the object CUDAIntersectionDevice wraps on the C++ side)."""
+
+    def __init__(self, ordinal=0):
+        h = C.c_void_p()
+        _check(lib().lrb_device_create(ordinal, C.byref(h)))
+        self.h = h
+        self.ordinal = ordinal
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lrb_device_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def props(self):
+        p = DeviceProps()
+        _check(lib().lrb_device_get_props(self.h, C.byref(p)))
+        return p
+
+    def set_stream(self, cuda_stream_handle):
+        _check(lib().lrb_device_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def set_option(self, key, value):
+        _check(lib().lrb_device_set_option(self.h, key.encode(), str(value).encode()))
+
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().lrb_alloc(self.h, nbytes, C.byref(p)))
+        return p.value or 0
+
+    def free(self, devptr):
+        _check(lib().lrb_free(self.h, C.c_void_p(devptr)))
+
+    def h2d(self, devptr, arr, blocking=False):
+        arr = np.ascontiguousarray(arr)
+        _check(lib().lrb_h2d(self.h, C.c_void_p(devptr), _ptr(arr), arr.nbytes, 1 if blocking else 0))
+
+    def d2h(self, arr, devptr, blocking=True):
+        assert arr.flags["C_CONTIGUOUS"]
+        _check(lib().lrb_d2h(self.h, _ptr(arr), C.c_void_p(devptr), arr.nbytes, 1 if blocking else 0))
+
+    def sync(self):
+        _check(lib().lrb_sync(self.h))
+
+    def flush(self):
+        _check(lib().lrb_flush(self.h))
+
+    def counters(self):
+        c = Counters()
+        _check(lib().lrb_get_counters(self.h, C.byref(c)))
+        return c
+
+    def reset_counters(self):
+        _check(lib().lrb_reset_counters(self.h))
+
+    # ---- scenes ----
+    def upload_bvh(self, nodes, verts, mesh_vertex_offsets):
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == 32
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        offs = np.ascontiguousarray(mesh_vertex_offsets, dtype=np.uint32)
+        s = C.c_void_p()
+        _check(lib().lrb_bvh_upload(self.h, _ptr(nodes), nodes.shape[0], _ptr(verts), verts.shape[0],
+                                    _ptr(offs), offs.shape[0], C.byref(s)))
+        return Scene(self, s)
+
+    def upload_mbvh(self, root_nodes, leaf_nodes, leaf_verts, transforms_minv=None, motion_table=None, interps=None):
+        """root_nodes: BVHArrayNode[]; leaf_nodes / leaf_verts: one array per unique leaf;
+        transforms_minv: [n,4,4]; motion_table: uint32 [m,4] (ocl::MotionSystem); interps: uint8 [k*576]."""
+        root_nodes = np.ascontiguousarray(root_nodes)
+        leaf_nodes = [np.ascontiguousarray(a) for a in leaf_nodes]
+        leaf_verts = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in leaf_verts]
+        n = len(leaf_nodes)
+        d = MBVHDesc()
+        d.root_nodes = root_nodes.ctypes.data
+        d.n_root_nodes = root_nodes.shape[0]
+        d.n_leaves = n
+        ln = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in leaf_nodes])
+        lc = (C.c_uint32 * max(n, 1))(*[a.shape[0] for a in leaf_nodes])
+        lv = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in leaf_verts])
+        lvc = (C.c_uint32 * max(n, 1))(*[a.shape[0] for a in leaf_verts])
+        d.leaf_nodes = C.cast(ln, C.POINTER(C.c_void_p))
+        d.leaf_n_nodes = C.cast(lc, C.POINTER(C.c_uint32))
+        d.leaf_vertices = C.cast(lv, C.POINTER(C.c_void_p))
+        d.leaf_n_vertices = C.cast(lvc, C.POINTER(C.c_uint32))
+        keep = [root_nodes, leaf_nodes, leaf_verts, ln, lc, lv, lvc]
+        if transforms_minv is not None and len(transforms_minv):
+            tm = np.ascontiguousarray(transforms_minv, dtype=np.float32).reshape(-1, 16)
+            d.transforms_minv = tm.ctypes.data
+            d.n_transforms = tm.shape[0]
+            keep.append(tm)
+        if motion_table is not None and len(motion_table):
+            mt = np.ascontiguousarray(motion_table, dtype=np.uint32).reshape(-1, 4)
+            it = np.ascontiguousarray(interps, dtype=np.uint8)
+            d.motion_systems = mt.ctypes.data
+            d.n_motion_systems = mt.shape[0]
+            d.interpolated_transforms = it.ctypes.data
+            d.n_interpolated_transforms = it.shape[0] // 576
+            keep += [mt, it]
+        s = C.c_void_p()
+        _check(lib().lrb_mbvh_upload(self.h, C.byref(d), C.byref(s)))
+        del keep
+        return Scene(self, s)
+
+
+class Scene:
+    """A re-laid-out BVH / MBVH resident in HBM (what BVHKernel / MBVHKernel own)."""
+
+    def __init__(self, dev, handle):
+        self.dev = dev
+        self.h = handle
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().lrb_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.dev is not None and getattr(self.dev, "h", None):
+                self.free()
+        except Exception:
+            pass
+
+    def info(self):
+        i = SceneInfo()
+        _check(lib().lrb_scene_get_info(self.h, C.byref(i)))
+        return i
+
+    def update(self, root_nodes, transforms_minv):
+        root_nodes = np.ascontiguousarray(root_nodes)
+        tm = np.ascontiguousarray(transforms_minv, dtype=np.float32).reshape(-1, 16)
+        _check(lib().lrb_mbvh_update(self.h, _ptr(root_nodes), root_nodes.shape[0], _ptr(tm) if tm.shape[0] else None, tm.shape[0]))
+
+    def trace(self, rays_devptr, hits_devptr, n):
+        """Asynchronous EnqueueTraceRayBuffer on device pointers."""
+        _check(lib().lrb_trace(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n))
+
+    def trace_host(self, rays, hits=None):
+        """Host arrays in, host array out (H2D + trace + D2H inside)."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 48
+        if hits is None:
+            hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        assert hits.dtype.itemsize == 20 and hits.shape[0] == rays.shape[0]
+        _check(lib().lrb_trace_host(self.h, _ptr(rays), _ptr(hits), rays.shape[0]))
+        return hits
+
+    def trace_host_ptr(self, rays_hostptr, hits_hostptr, n):
+        _check(lib().lrb_trace_host(self.h, C.c_void_p(rays_hostptr), C.c_void_p(hits_hostptr), n))
+
+    def trace_stats(self, rays_devptr, hits_devptr, n):
+        st = TraceStats()
+        _check(lib().lrb_trace_stats(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr or 0), n, C.byref(st)))
+        return st

@@ -1,0 +1,724 @@
+// device.cu -- implementation of the C ABI in include/luxrays_b200.h for sm_100a.
+//
+// Replaces, behind one flat interface, the reference's CUDADevice buffer/queue API
+// (src/luxrays/devices/cudadevice.cpp:407-540), the BVHKernel / MBVHKernel upload paths
+// (bvhaccelhw.cpp:38-237, mbvhaccelhw.cpp:41-306,308-466) and their kernel launches
+// (bvhaccelhw.cpp:259-268, mbvhaccelhw.cpp:468-507).  No NVRTC, no cuew, no OptiX.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "luxrays_b200.h"
+#include "layout.h"
+#include "relayout.h"
+#include "trace_kernels.cuh"
+
+using namespace lrb;
+
+static thread_local std::string g_lastError;
+
+static int Fail(int code, const std::string &msg) {
+	g_lastError = msg;
+	return code;
+}
+
+#define LRB_CUDA(call)                                                                              \
+	do {                                                                                            \
+		const cudaError_t e_ = (call);                                                              \
+		if (e_ != cudaSuccess) {                                                                    \
+			const int code_ = (e_ == cudaErrorMemoryAllocation) ? LRB_ERR_OOM :                     \
+					((e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? LRB_ERR_NO_DEVICE : LRB_ERR_CUDA); \
+			return Fail(code_, std::string(#call) + " failed: " + cudaGetErrorString(e_) +        \
+					" (" __FILE__ ":" + std::to_string(__LINE__) + ")");                            \
+		}                                                                                           \
+	} while (0)
+
+struct lrb_device {
+	int ordinal;
+	cudaStream_t ownStream;
+	cudaStream_t stream;            // the in-order queue in use (own or adopted)
+	cudaStream_t copyInStream, copyOutStream;   // lrb_trace_host pipeline
+	cudaDeviceProp prop;
+	lrb_counters counters;
+	std::mutex mtx;
+	std::unordered_map<void *, size_t> allocs;  // lrb_alloc bookkeeping (GetUsedMemory parity)
+	// options
+	int blockThreads;               // 64 or 128
+	int blocksPerSM;                // 0 = from occupancy
+	int persistent;                 // 1 = TracePersistent, 0 = TraceStatic
+	int smemDepth;                  // shared-memory stack entries per thread
+	int refillBelow;
+	int hostChunk;                  // rays per chunk in lrb_trace_host
+	// staging for lrb_trace_host
+	void *stageRays, *stageHits;
+	size_t stageRaysBytes, stageHitsBytes;
+	std::vector<cudaEvent_t> events;
+};
+
+struct lrb_scene {
+	lrb_device *dev;
+	WideScene host;                 // kept for MBVH (Update); cleared for single-level scenes
+	WideNode *dNodes;
+	TriRecord *dTris;
+	InstRecord *dInsts;
+	float *dMinv;
+	uint32_t *dMotionFirst, *dMotionLast;
+	DevInterp *dInterps;
+	size_t capNodes, capInsts;      // allocated element counts (Update re-uses them)
+	uint32_t *dCounter;
+	uint32_t *dSpillNode;
+	float *dSpillT;
+	size_t spillEntries;
+	TraceStats *dStats;
+	SceneView view;
+	lrb_scene_info info;
+};
+
+static int SetDev(lrb_device *dev) {
+	if (!dev)
+		return Fail(LRB_ERR_INVALID, "null device");
+	LRB_CUDA(cudaSetDevice(dev->ordinal));
+	return LRB_OK;
+}
+
+#define LRB_SETDEV(dev)                         \
+	do {                                        \
+		const int rc_ = SetDev(dev);            \
+		if (rc_ != LRB_OK) return rc_;          \
+	} while (0)
+
+extern "C" {
+
+const char *lrb_last_error_string(void) { return g_lastError.c_str(); }
+
+const char *lrb_version_string(void) { return "luxrays_b200 0.1 (sm_100a)"; }
+
+int lrb_device_count(int *count) {
+	if (!count)
+		return Fail(LRB_ERR_INVALID, "null count");
+	*count = 0;
+	int n = 0;
+	const cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return Fail(LRB_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+	}
+	*count = n;
+	return LRB_OK;
+}
+
+int lrb_device_create(int ordinal, lrb_device **out) {
+	if (!out)
+		return Fail(LRB_ERR_INVALID, "null out pointer");
+	*out = nullptr;
+	int n = 0;
+	const int rc = lrb_device_count(&n);
+	if (rc != LRB_OK)
+		return rc;
+	if (n == 0)
+		return Fail(LRB_ERR_NO_DEVICE, "no CUDA device present; this library has no CPU fallback");
+	if (ordinal < 0 || ordinal >= n)
+		return Fail(LRB_ERR_INVALID, "CUDA ordinal out of range");
+	LRB_CUDA(cudaSetDevice(ordinal));
+	lrb_device *dev = new lrb_device();
+	dev->ordinal = ordinal;
+	memset(&dev->counters, 0, sizeof(dev->counters));
+	dev->stageRays = dev->stageHits = nullptr;
+	dev->stageRaysBytes = dev->stageHitsBytes = 0;
+	cudaError_t e = cudaGetDeviceProperties(&dev->prop, ordinal);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->ownStream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->copyInStream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->copyOutStream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete dev;
+		return Fail(LRB_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(e));
+	}
+	dev->stream = dev->ownStream;
+	dev->blockThreads = 128;
+	dev->blocksPerSM = 0;
+	dev->persistent = 1;
+	dev->smemDepth = 24;
+	dev->refillBelow = 20;
+	dev->hostChunk = 1 << 20;
+	*out = dev;
+	return LRB_OK;
+}
+
+int lrb_device_destroy(lrb_device *dev) {
+	if (!dev)
+		return LRB_OK;
+	LRB_SETDEV(dev);
+	cudaStreamSynchronize(dev->stream);
+	for (size_t i = 0; i < dev->events.size(); ++i) cudaEventDestroy(dev->events[i]);
+	if (dev->stageRays) cudaFree(dev->stageRays);
+	if (dev->stageHits) cudaFree(dev->stageHits);
+	cudaStreamDestroy(dev->copyInStream);
+	cudaStreamDestroy(dev->copyOutStream);
+	cudaStreamDestroy(dev->ownStream);
+	delete dev;
+	return LRB_OK;
+}
+
+int lrb_device_get_props(lrb_device *dev, lrb_device_props *out) {
+	if (!dev || !out)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	memset(out, 0, sizeof(*out));
+	out->cuda_ordinal = dev->ordinal;
+	out->cc_major = dev->prop.major;
+	out->cc_minor = dev->prop.minor;
+	out->sm_count = dev->prop.multiProcessorCount;
+	out->l2_bytes = dev->prop.l2CacheSize;
+	out->total_mem_bytes = dev->prop.totalGlobalMem;
+	strncpy(out->name, dev->prop.name, sizeof(out->name) - 1);
+	return LRB_OK;
+}
+
+int lrb_device_set_stream(lrb_device *dev, void *s) {
+	if (!dev)
+		return Fail(LRB_ERR_INVALID, "null device");
+	dev->stream = s ? (cudaStream_t)s : dev->ownStream;
+	return LRB_OK;
+}
+
+int lrb_device_get_stream(lrb_device *dev, void **s) {
+	if (!dev || !s)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	*s = (void *)dev->stream;
+	return LRB_OK;
+}
+
+int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
+	if (!dev || !key || !value)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	const std::string k(key), v(value);
+	if (k == "kernel") {
+		if (v == "persistent") dev->persistent = 1;
+		else if (v == "simple" || v == "static") dev->persistent = 0;
+		else return Fail(LRB_ERR_INVALID, "kernel must be persistent|simple");
+		return LRB_OK;
+	}
+	const int iv = atoi(value);
+	if (k == "block_threads") {
+		if (iv != 32 && iv != 64 && iv != 96 && iv != 128)
+			return Fail(LRB_ERR_INVALID, "block_threads must be 32, 64, 96 or 128");
+		dev->blockThreads = iv;
+	} else if (k == "blocks_per_sm") {
+		if (iv < 0 || iv > 32) return Fail(LRB_ERR_INVALID, "blocks_per_sm out of range");
+		dev->blocksPerSM = iv;
+	} else if (k == "smem_depth") {
+		if (iv < 1 || iv > 128) return Fail(LRB_ERR_INVALID, "smem_depth out of range");
+		dev->smemDepth = iv;
+	} else if (k == "refill_below") {
+		if (iv < 1 || iv > 32) return Fail(LRB_ERR_INVALID, "refill_below out of range");
+		dev->refillBelow = iv;
+	} else if (k == "host_chunk") {
+		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
+		dev->hostChunk = iv;
+	} else
+		return Fail(LRB_ERR_INVALID, "unknown option: " + k);
+	return LRB_OK;
+}
+
+// ---- memory + queue ---------------------------------------------------------------------------
+
+int lrb_alloc(lrb_device *dev, size_t bytes, void **devptr) {
+	if (!devptr)
+		return Fail(LRB_ERR_INVALID, "null out pointer");
+	*devptr = nullptr;
+	LRB_SETDEV(dev);
+	if (bytes == 0)
+		return LRB_OK;
+	LRB_CUDA(cudaMalloc(devptr, bytes));
+	std::lock_guard<std::mutex> g(dev->mtx);
+	dev->allocs[*devptr] = bytes;
+	dev->counters.device_bytes_in_use += bytes;
+	return LRB_OK;
+}
+
+int lrb_free(lrb_device *dev, void *devptr) {
+	LRB_SETDEV(dev);
+	if (!devptr)
+		return LRB_OK;
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		std::unordered_map<void *, size_t>::iterator it = dev->allocs.find(devptr);
+		if (it == dev->allocs.end())
+			return Fail(LRB_ERR_INVALID, "pointer was not allocated by lrb_alloc on this device");
+		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, it->second);
+		dev->allocs.erase(it);
+	}
+	LRB_CUDA(cudaFree(devptr));
+	return LRB_OK;
+}
+
+int lrb_h2d(lrb_device *dev, void *dst, const void *src, size_t bytes, int blocking) {
+	LRB_SETDEV(dev);
+	if (bytes == 0)
+		return LRB_OK;
+	if (!dst || !src)
+		return Fail(LRB_ERR_INVALID, "null pointer in h2d");
+	LRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream));
+	if (blocking)
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	dev->counters.h2d_bytes += bytes;
+	return LRB_OK;
+}
+
+int lrb_d2h(lrb_device *dev, void *dst, const void *src, size_t bytes, int blocking) {
+	LRB_SETDEV(dev);
+	if (bytes == 0)
+		return LRB_OK;
+	if (!dst || !src)
+		return Fail(LRB_ERR_INVALID, "null pointer in d2h");
+	LRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
+	if (blocking)
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	dev->counters.d2h_bytes += bytes;
+	return LRB_OK;
+}
+
+int lrb_flush(lrb_device *dev) {
+	LRB_SETDEV(dev);
+	// CUDA submits eagerly; cuStreamQuery is what the reference uses to kick the queue
+	const cudaError_t e = cudaStreamQuery(dev->stream);
+	if (e != cudaSuccess && e != cudaErrorNotReady)
+		LRB_CUDA(e);
+	return LRB_OK;
+}
+
+int lrb_sync(lrb_device *dev) {
+	LRB_SETDEV(dev);
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	return LRB_OK;
+}
+
+int lrb_get_counters(lrb_device *dev, lrb_counters *out) {
+	if (!dev || !out)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	*out = dev->counters;
+	return LRB_OK;
+}
+
+int lrb_reset_counters(lrb_device *dev) {
+	if (!dev)
+		return Fail(LRB_ERR_INVALID, "null device");
+	const uint64_t inUse = dev->counters.device_bytes_in_use;
+	memset(&dev->counters, 0, sizeof(dev->counters));
+	dev->counters.device_bytes_in_use = inUse;
+	return LRB_OK;
+}
+
+// ---- scenes -----------------------------------------------------------------------------------
+
+}   // extern "C"
+
+template <class T> static int UploadArray(lrb_device *dev, const std::vector<T> &src, T **dst, size_t *cap, uint64_t *bytes) {
+	const size_t n = src.size();
+	if (cap && *dst && *cap >= n) {
+		// re-use the allocation (Update path)
+	} else {
+		if (*dst) { LRB_CUDA(cudaFree(*dst)); *dst = nullptr; }
+		if (n) {
+			LRB_CUDA(cudaMalloc((void **)dst, n * sizeof(T)));
+			if (bytes) *bytes += n * sizeof(T);
+		}
+		if (cap) *cap = n;
+	}
+	if (n) {
+		LRB_CUDA(cudaMemcpyAsync(*dst, src.data(), n * sizeof(T), cudaMemcpyHostToDevice, dev->stream));
+		dev->counters.h2d_bytes += n * sizeof(T);
+	}
+	return LRB_OK;
+}
+
+static void FillView(lrb_scene *s) {
+	SceneView &v = s->view;
+	v.nodes = s->dNodes;
+	v.tris = s->dTris;
+	v.insts = s->dInsts;
+	v.minv = s->dMinv;
+	v.motionFirst = s->dMotionFirst;
+	v.motionLast = s->dMotionLast;
+	v.interps = s->dInterps;
+	v.nWide = (uint32_t)s->host.wide.size();
+	v.rootWide = s->host.rootWide;
+	v.twoLevel = s->host.twoLevel ? 1u : 0u;
+	s->info.n_ref_nodes = s->host.nRefNodes;
+	s->info.n_wide_nodes = (uint32_t)s->host.wide.size();
+	s->info.n_triangles = (uint32_t)s->host.tris.size();
+	s->info.n_instances = (uint32_t)s->host.insts.size();
+	s->info.stack_need = s->host.stackNeed;
+	s->info.two_level = v.twoLevel;
+}
+
+static int UploadScene(lrb_scene *s) {
+	lrb_device *dev = s->dev;
+	uint64_t bytes = 0;
+	int rc;
+	if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.tris, &s->dTris, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.insts, &s->dInsts, &s->capInsts, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.minv, &s->dMinv, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.motionFirst, &s->dMotionFirst, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.motionLast, &s->dMotionLast, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.interps, &s->dInterps, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if (!s->dCounter) {
+		LRB_CUDA(cudaMalloc((void **)&s->dCounter, 256));
+		LRB_CUDA(cudaMalloc((void **)&s->dStats, sizeof(TraceStats)));
+		bytes += 256 + sizeof(TraceStats);
+	}
+	// the host vectors are pageable: wait for the copies before they can be released/modified
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	s->info.device_bytes += bytes;
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		dev->counters.device_bytes_in_use += bytes;
+	}
+	FillView(s);
+	return LRB_OK;
+}
+
+static lrb_scene *NewScene(lrb_device *dev) {
+	lrb_scene *s = new lrb_scene();
+	s->dev = dev;
+	s->dNodes = nullptr; s->dTris = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
+	s->dMotionFirst = s->dMotionLast = nullptr; s->dInterps = nullptr;
+	s->capNodes = s->capInsts = 0;
+	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
+	s->dStats = nullptr;
+	memset(&s->view, 0, sizeof(s->view));
+	memset(&s->info, 0, sizeof(s->info));
+	return s;
+}
+
+extern "C" {
+
+int lrb_scene_free(lrb_scene *s) {
+	if (!s)
+		return LRB_OK;
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	cudaStreamSynchronize(dev->stream);
+	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dInsts); cudaFree(s->dMinv);
+	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
+	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats);
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, s->info.device_bytes);
+	}
+	delete s;
+	return LRB_OK;
+}
+
+int lrb_bvh_upload(lrb_device *dev, const lrb_bvh_node *nodes, uint32_t nNodes, const float *xyz, uint64_t nVerts,
+		const uint32_t *meshVertexOffsets, uint32_t nMeshes, lrb_scene **out) {
+	if (!out)
+		return Fail(LRB_ERR_INVALID, "null out pointer");
+	*out = nullptr;
+	LRB_SETDEV(dev);
+	lrb_scene *s = NewScene(dev);
+	try {
+		BuildWideBVH(nodes, nNodes, xyz, nVerts, meshVertexOffsets, nMeshes, &s->host);
+	} catch (const std::bad_alloc &) {
+		delete s;
+		return Fail(LRB_ERR_OOM, "host out of memory during BVH re-layout");
+	} catch (const std::exception &e) {
+		delete s;
+		return Fail(LRB_ERR_INVALID, e.what());
+	}
+	const int rc = UploadScene(s);
+	if (rc != LRB_OK) {
+		lrb_scene_free(s);
+		return rc;
+	}
+	// single-level scenes never change: drop the host copy (the view / info keep the bookkeeping)
+	std::vector<WideNode>().swap(s->host.wide);
+	std::vector<TriRecord>().swap(s->host.tris);
+	*out = s;
+	return LRB_OK;
+}
+
+int lrb_mbvh_upload(lrb_device *dev, const lrb_mbvh_desc *desc, lrb_scene **out) {
+	if (!out || !desc)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	*out = nullptr;
+	LRB_SETDEV(dev);
+	lrb_scene *s = NewScene(dev);
+	try {
+		BuildWideMBVH(*desc, &s->host);
+	} catch (const std::bad_alloc &) {
+		delete s;
+		return Fail(LRB_ERR_OOM, "host out of memory during MBVH re-layout");
+	} catch (const std::exception &e) {
+		delete s;
+		return Fail(LRB_ERR_INVALID, e.what());
+	}
+	const int rc = UploadScene(s);
+	if (rc != LRB_OK) {
+		lrb_scene_free(s);
+		return rc;
+	}
+	// triangles are immutable under Update; the wide nodes / instances stay on the host
+	std::vector<TriRecord>().swap(s->host.tris);
+	s->host.tris.resize(0);
+	*out = s;
+	return LRB_OK;
+}
+
+int lrb_mbvh_update(lrb_scene *s, const lrb_bvh_node *rootNodes, uint32_t nRootNodes, const float *minv, uint32_t nTransforms) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	const uint32_t nTris = s->info.n_triangles;
+	try {
+		UpdateWideMBVHRoot(rootNodes, nRootNodes, minv, nTransforms, &s->host);
+	} catch (const std::exception &e) {
+		return Fail(LRB_ERR_INVALID, e.what());
+	}
+	// in-order with earlier traces on the stream; only the root tail, instances and matrices move
+	uint64_t bytes = 0;
+	int rc;
+	if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.insts, &s->dInsts, &s->capInsts, &bytes)) != LRB_OK) return rc;
+	if (s->host.minv.size()) {
+		LRB_CUDA(cudaMemcpyAsync(s->dMinv, s->host.minv.data(), s->host.minv.size() * sizeof(float), cudaMemcpyHostToDevice, dev->stream));
+		dev->counters.h2d_bytes += s->host.minv.size() * sizeof(float);
+	}
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	s->info.device_bytes += bytes;
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		dev->counters.device_bytes_in_use += bytes;
+	}
+	FillView(s);
+	s->info.n_triangles = nTris;
+	return LRB_OK;
+}
+
+int lrb_scene_get_info(lrb_scene *s, lrb_scene_info *out) {
+	if (!s || !out)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	*out = s->info;
+	return LRB_OK;
+}
+
+// ---- trace ------------------------------------------------------------------------------------
+
+}   // extern "C"
+
+template <class K> static int Occupancy(K kernel, int block, int smemBytes, int *blocksPerSM) {
+	if (smemBytes > 48 * 1024)
+		LRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+	LRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocksPerSM, kernel, block, smemBytes));
+	return LRB_OK;
+}
+
+static int EnsureSpill(lrb_scene *s, uint32_t residentDepth, int totalThreads) {
+	const uint32_t need = s->info.stack_need;
+	if (need <= residentDepth)
+		return LRB_OK;
+	const size_t entries = (size_t)(need - residentDepth) * (size_t)totalThreads;
+	if (entries <= s->spillEntries)
+		return LRB_OK;
+	lrb_device *dev = s->dev;
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	if (s->dSpillNode) { cudaFree(s->dSpillNode); cudaFree(s->dSpillT); s->dSpillNode = nullptr; s->dSpillT = nullptr; }
+	LRB_CUDA(cudaMalloc((void **)&s->dSpillNode, entries * sizeof(uint32_t)));
+	LRB_CUDA(cudaMalloc((void **)&s->dSpillT, entries * sizeof(float)));
+	s->info.device_bytes += (entries - s->spillEntries) * 8;
+	s->spillEntries = entries;
+	return LRB_OK;
+}
+
+static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream) {
+	lrb_device *dev = s->dev;
+	if (n == 0)
+		return LRB_OK;
+	if (!rays || (!hits && !stats))
+		return Fail(LRB_ERR_INVALID, "null ray/hit buffer");
+	if ((reinterpret_cast<uintptr_t>(rays) & 15u) != 0)
+		return Fail(LRB_ERR_INVALID, "ray buffer must be 16-byte aligned");
+
+	TraceArgs a;
+	memset(&a, 0, sizeof(a));
+	a.sc = s->view;
+	a.rays = (const lrb_ray *)rays;
+	a.hits = (lrb_rayhit *)hits;
+	a.rayCount = n;
+	a.counter = s->dCounter;
+	a.stats = s->dStats;
+	a.refillBelow = (uint32_t)dev->refillBelow;
+	const bool two = s->view.twoLevel != 0;
+	const int sm = dev->prop.multiProcessorCount;
+	int rc;
+
+	if (dev->persistent && !stats) {
+		const int block = dev->blockThreads;
+		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
+		const int smemBytes = depth * block * 8;
+		int bps = 0;
+		if (two) rc = Occupancy(TracePersistent<true>, block, smemBytes, &bps);
+		else rc = Occupancy(TracePersistent<false>, block, smemBytes, &bps);
+		if (rc != LRB_OK) return rc;
+		if (bps < 1)
+			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
+		if (dev->blocksPerSM > 0) bps = std::min(bps, dev->blocksPerSM);
+		// never launch more threads than rays
+		long long grid = (long long)sm * bps;
+		const long long maxUseful = ((long long)n + block - 1) / block;
+		if (grid > maxUseful) grid = maxUseful;
+		a.smemDepth = (uint32_t)depth;
+		if ((rc = EnsureSpill(s, (uint32_t)depth, (int)grid * block)) != LRB_OK) return rc;
+		a.spillNode = s->dSpillNode;
+		a.spillT = s->dSpillT;
+		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, sizeof(uint32_t), stream));
+		if (two) TracePersistent<true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+		else TracePersistent<false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+	} else {
+		const int block = dev->blockThreads;
+		int bps = 0;
+		if (stats) {
+			if (two) rc = Occupancy(TraceStatic<true, true>, block, 0, &bps);
+			else rc = Occupancy(TraceStatic<false, true>, block, 0, &bps);
+		} else {
+			if (two) rc = Occupancy(TraceStatic<true, false>, block, 0, &bps);
+			else rc = Occupancy(TraceStatic<false, false>, block, 0, &bps);
+		}
+		if (rc != LRB_OK) return rc;
+		if (bps < 1) bps = 1;
+		if (dev->blocksPerSM > 0) bps = std::min(bps, dev->blocksPerSM);
+		long long grid = (long long)sm * bps;
+		const long long maxUseful = ((long long)n + block - 1) / block;
+		if (grid > maxUseful) grid = maxUseful;
+		if ((rc = EnsureSpill(s, 32u, (int)grid * block)) != LRB_OK) return rc;
+		a.spillNode = s->dSpillNode;
+		a.spillT = s->dSpillT;
+		if (stats) {
+			LRB_CUDA(cudaMemsetAsync(s->dStats, 0, sizeof(TraceStats), stream));
+			if (two) TraceStatic<true, true><<<(unsigned)grid, block, 0, stream>>>(a);
+			else TraceStatic<false, true><<<(unsigned)grid, block, 0, stream>>>(a);
+		} else {
+			if (two) TraceStatic<true, false><<<(unsigned)grid, block, 0, stream>>>(a);
+			else TraceStatic<false, false><<<(unsigned)grid, block, 0, stream>>>(a);
+		}
+	}
+	LRB_CUDA(cudaGetLastError());
+	dev->counters.rays_traced += n;
+	dev->counters.trace_launches += 1;
+	dev->counters.kernel_launches += 1;
+	return LRB_OK;
+}
+
+extern "C" {
+
+int lrb_trace(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	LRB_SETDEV(s->dev);
+	return LaunchTrace(s, rays, hits, n, false, s->dev->stream);
+}
+
+int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {
+	if (!s || !out)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	memset(out, 0, sizeof(*out));
+	if (n == 0)
+		return LRB_OK;
+	const int rc = LaunchTrace(s, rays, hits, n, true, dev->stream);
+	if (rc != LRB_OK)
+		return rc;
+	TraceStats st;
+	LRB_CUDA(cudaMemcpyAsync(&st, s->dStats, sizeof(st), cudaMemcpyDeviceToHost, dev->stream));
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	out->rays = st.rays;
+	out->wide_nodes = st.wideNodes;
+	out->triangles = st.triangles;
+	out->instances = st.instances;
+	out->motion_samples = st.motionSamples;
+	out->max_stack = st.maxStack;
+	return LRB_OK;
+}
+
+// Host buffers in, host buffers out.  The batch is cut into chunks; chunk k+1 is copied in and
+// chunk k-1 copied out (separate streams, PCIe is full duplex) while chunk k is traced.
+int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	if (n == 0)
+		return LRB_OK;
+	if (!rays || !hits)
+		return Fail(LRB_ERR_INVALID, "null host buffer");
+	const size_t rb = (size_t)n * sizeof(lrb_ray), hb = (size_t)n * sizeof(lrb_rayhit);
+	if (dev->stageRaysBytes < rb) {
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+		if (dev->stageRays) cudaFree(dev->stageRays);
+		dev->stageRays = nullptr; dev->stageRaysBytes = 0;
+		LRB_CUDA(cudaMalloc(&dev->stageRays, rb));
+		dev->stageRaysBytes = rb;
+	}
+	if (dev->stageHitsBytes < hb) {
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+		if (dev->stageHits) cudaFree(dev->stageHits);
+		dev->stageHits = nullptr; dev->stageHitsBytes = 0;
+		LRB_CUDA(cudaMalloc(&dev->stageHits, hb));
+		dev->stageHitsBytes = hb;
+	}
+	// masked rays leave their RayHit untouched: the device copy must start from the caller's
+	// content, but only when some ray is masked; a cheap scan over the flags decides
+	bool anyMasked = false;
+	for (uint32_t i = 0; i < n; ++i)
+		if (rays[i].flags & LRB_RAY_FLAGS_MASKED) { anyMasked = true; break; }
+
+	const uint32_t chunk = (uint32_t)dev->hostChunk;
+	const uint32_t nChunks = (n + chunk - 1) / chunk;
+	while (dev->events.size() < 3 * (size_t)nChunks + 1) {
+		cudaEvent_t e;
+		LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		dev->events.push_back(e);
+	}
+	// everything queued so far on the main stream must be visible to the copy streams
+	cudaEvent_t start = dev->events[3 * (size_t)nChunks];
+	LRB_CUDA(cudaEventRecord(start, dev->stream));
+	LRB_CUDA(cudaStreamWaitEvent(dev->copyInStream, start, 0));
+	LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, start, 0));
+	for (uint32_t c = 0; c < nChunks; ++c) {
+		const uint32_t first = c * chunk, cnt = std::min(chunk, n - first);
+		lrb_ray *dR = (lrb_ray *)dev->stageRays + first;
+		lrb_rayhit *dH = (lrb_rayhit *)dev->stageHits + first;
+		cudaEvent_t in = dev->events[3 * c], done = dev->events[3 * c + 1];
+		LRB_CUDA(cudaMemcpyAsync(dR, rays + first, (size_t)cnt * sizeof(lrb_ray), cudaMemcpyHostToDevice, dev->copyInStream));
+		if (anyMasked)
+			LRB_CUDA(cudaMemcpyAsync(dH, hits + first, (size_t)cnt * sizeof(lrb_rayhit), cudaMemcpyHostToDevice, dev->copyInStream));
+		LRB_CUDA(cudaEventRecord(in, dev->copyInStream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, in, 0));
+		const int rc = LaunchTrace(s, dR, dH, cnt, false, dev->stream);
+		if (rc != LRB_OK)
+			return rc;
+		LRB_CUDA(cudaEventRecord(done, dev->stream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, done, 0));
+		LRB_CUDA(cudaMemcpyAsync(hits + first, dH, (size_t)cnt * sizeof(lrb_rayhit), cudaMemcpyDeviceToHost, dev->copyOutStream));
+	}
+	cudaEvent_t out = dev->events[3 * (size_t)(nChunks - 1) + 2];
+	LRB_CUDA(cudaEventRecord(out, dev->copyOutStream));
+	LRB_CUDA(cudaStreamWaitEvent(dev->stream, out, 0));
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	dev->counters.h2d_bytes += rb + (anyMasked ? hb : 0);
+	dev->counters.d2h_bytes += hb;
+	return LRB_OK;
+}
+
+}   // extern "C"

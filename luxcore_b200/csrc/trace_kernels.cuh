@@ -1,0 +1,244 @@
+// trace_kernels.cuh -- sm_100a closest-hit kernels (replace bvh.cl / mbvh.cl
+// Accelerator_Intersect_RayBuffer, include/luxrays/accelerators/bvh.cl:228-260, mbvh.cl:351-383).
+//
+// TracePersistent: persistent warps, one ray per lane.  A warp pulls ray indices from a global
+// atomic counter; lanes whose ray finished are re-filled in bulk (one atomicAdd per warp, the
+// lanes' slots assigned with a ballot + popc prefix) as soon as the number of live lanes drops
+// under a threshold, so incoherent bounce rays do not leave a warp running with a handful of
+// lanes.  The traversal stack is a per-lane column in shared memory (bank = lane, conflict-free
+// at any mix of depths); entries beyond the shared depth spill to a global scratch column.
+// Nodes/triangles are fetched with 128-bit read-only loads (ld.global.nc.v4).
+//
+// TraceStatic: same per-ray code, static grid-stride assignment, stack in local memory.  Kept as
+// the "simple" variant for A/B measurements and as the instrumented (STATS) kernel.
+#ifndef LRB_TRACE_KERNELS_CUH
+#define LRB_TRACE_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "traverse.h"
+
+namespace lrb {
+
+// ---- stacks ---------------------------------------------------------------------------------
+
+// Shared-memory column per thread + global spill.
+struct SmemStack {
+	uint32_t *sNode;        // &smemNodes[threadIdx.x], stride = blockDim.x
+	float *sT;
+	uint32_t *gNode;        // &spillNodes[globalThread], stride = totalThreads (may be NULL when no spill is needed)
+	float *gT;
+	uint32_t stride, gStride;
+	int depthSmem;
+	int sp;
+
+	__device__ __forceinline__ void push(uint32_t n, float t) {
+		if (sp < depthSmem) {
+			sNode[sp * stride] = n;
+			sT[sp * stride] = t;
+		} else {
+			const size_t o = (size_t)(sp - depthSmem) * gStride;
+			gNode[o] = n;
+			gT[o] = t;
+		}
+		++sp;
+	}
+	__device__ __forceinline__ void pop(uint32_t &n, float &t) {
+		--sp;
+		if (sp < depthSmem) {
+			n = sNode[sp * stride];
+			t = sT[sp * stride];
+		} else {
+			const size_t o = (size_t)(sp - depthSmem) * gStride;
+			n = gNode[o];
+			t = gT[o];
+		}
+	}
+	__device__ __forceinline__ bool empty() const { return sp == 0; }
+	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
+};
+
+// Local-memory stack + global spill.
+template <int CAP> struct LocalStack {
+	uint32_t node[CAP];
+	float t0[CAP];
+	uint32_t *gNode;
+	float *gT;
+	uint32_t gStride;
+	int sp;
+
+	__device__ __forceinline__ void push(uint32_t n, float t) {
+		if (sp < CAP) {
+			node[sp] = n;
+			t0[sp] = t;
+		} else {
+			const size_t o = (size_t)(sp - CAP) * gStride;
+			gNode[o] = n;
+			gT[o] = t;
+		}
+		++sp;
+	}
+	__device__ __forceinline__ void pop(uint32_t &n, float &t) {
+		--sp;
+		if (sp < CAP) {
+			n = node[sp];
+			t = t0[sp];
+		} else {
+			const size_t o = (size_t)(sp - CAP) * gStride;
+			n = gNode[o];
+			t = gT[o];
+		}
+	}
+	__device__ __forceinline__ bool empty() const { return sp == 0; }
+	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
+};
+
+struct TraceArgs {
+	SceneView sc;
+	const lrb_ray *rays;
+	lrb_rayhit *hits;
+	uint32_t rayCount;
+	uint32_t *counter;          // persistent kernel: next unassigned ray (zeroed before launch)
+	uint32_t *spillNode;        // global stack spill, [spillDepth][totalThreads]
+	float *spillT;
+	uint32_t smemDepth;         // stack entries held in shared memory per thread
+	uint32_t refillBelow;       // re-fill when fewer live lanes than this
+	TraceStats *stats;          // STATS kernels only
+};
+
+__device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray &r) {
+	const float4 *p = reinterpret_cast<const float4 *>(rays + i);    // 48-B records, 16-B aligned
+	const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+	r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z;
+	r.d[0] = a.w; r.d[1] = b.x; r.d[2] = b.y;
+	r.mint = b.z; r.maxt = b.w;
+	r.time = c.x; r.flags = __float_as_uint(c.y);
+}
+
+__device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const RayState &s, float rayMaxt) {
+	lrb_rayhit h;
+	WriteHit(s, rayMaxt, &h);
+	// 20-B records are only 4-B aligned: five scalar stores
+	float *p = reinterpret_cast<float *>(hits + i);
+	p[0] = h.t; p[1] = h.b1; p[2] = h.b2;
+	reinterpret_cast<uint32_t *>(p)[3] = h.meshIndex;
+	reinterpret_cast<uint32_t *>(p)[4] = h.triangleIndex;
+}
+
+// ---- persistent, warp-cooperative kernel ----------------------------------------------------
+
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
+	extern __shared__ uint32_t smem[];
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t totalThreads = gridDim.x * blockDim.x;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+
+	SmemStack stk;
+	stk.sNode = smem + threadIdx.x;
+	stk.sT = reinterpret_cast<float *>(smem + a.smemDepth * blockDim.x) + threadIdx.x;
+	stk.stride = blockDim.x;
+	stk.gNode = a.spillNode ? a.spillNode + gtid : nullptr;
+	stk.gT = a.spillT ? a.spillT + gtid : nullptr;
+	stk.gStride = totalThreads;
+	stk.depthSmem = (int)a.smemDepth;
+	stk.sp = 0;
+
+	RayState s;
+	uint32_t rayIdx = 0;
+	float rayMaxt = 0.f;
+	bool active = false;
+	bool exhausted = false;
+
+	for (;;) {
+		// ---- re-fill idle lanes ----
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (!exhausted && idle) {
+			const int nIdle = __popc(idle);
+			const int leader = __ffs(idle) - 1;
+			uint32_t base = 0;
+			if ((int)lane == leader)
+				base = atomicAdd(a.counter, (uint32_t)nIdle);
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (!active) {
+				const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+				if (idx < a.rayCount) {
+					lrb_ray r;
+					LoadRay(a.rays, idx, r);
+					// masked rays are skipped and their RayHit is left untouched (bvh.cl:242-244)
+					if (!(r.flags & LRB_RAY_FLAGS_MASKED)) {
+						rayIdx = idx;
+						rayMaxt = r.maxt;
+						if (InitRay(a.sc, r, s)) {
+							stk.sp = 0;
+							active = true;
+						} else
+							StoreHit(a.hits, idx, s, rayMaxt);  // empty scene: miss
+					}
+				}
+			}
+			if (base + (uint32_t)nIdle >= a.rayCount)
+				exhausted = true;
+		}
+		unsigned live = __ballot_sync(0xffffffffu, active);
+		if (live == 0) {
+			if (exhausted)
+				break;
+			continue;
+		}
+
+		// ---- traverse until too few lanes are alive ----
+		const int floorLanes = exhausted ? 1 : (int)a.refillBelow;
+		do {
+			if (active) {
+				if (!Step<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
+					StoreHit(a.hits, rayIdx, s, rayMaxt);
+					active = false;
+				}
+			}
+			live = __ballot_sync(0xffffffffu, active);
+		} while (__popc(live) >= floorLanes);
+	}
+}
+
+// ---- static grid-stride kernel (simple variant + instrumented variant) -----------------------
+
+template <bool TWO_LEVEL, bool STATS>
+__global__ void __launch_bounds__(128) TraceStatic(const TraceArgs a) {
+	const uint32_t totalThreads = gridDim.x * blockDim.x;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	LocalStack<32> stk;
+	stk.gNode = a.spillNode ? a.spillNode + gtid : nullptr;
+	stk.gT = a.spillT ? a.spillT + gtid : nullptr;
+	stk.gStride = totalThreads;
+	TraceStats local;
+	local.rays = local.wideNodes = local.triangles = local.instances = local.motionSamples = local.maxStack = 0;
+	unsigned long long nRays = 0;
+
+	for (uint32_t i = gtid; i < a.rayCount; i += totalThreads) {
+		lrb_ray r;
+		LoadRay(a.rays, i, r);
+		if (r.flags & LRB_RAY_FLAGS_MASKED)
+			continue;
+		++nRays;
+		RayState s;
+		stk.sp = 0;
+		if (InitRay(a.sc, r, s)) {
+			while (Step<TWO_LEVEL, STATS>(a.sc, a.rays[i], s, stk, &local)) { }
+		}
+		if (a.hits)
+			StoreHit(a.hits, i, s, r.maxt);
+	}
+	if (STATS) {
+		atomicAdd(&a.stats->wideNodes, local.wideNodes);
+		atomicAdd(&a.stats->triangles, local.triangles);
+		atomicAdd(&a.stats->instances, local.instances);
+		atomicAdd(&a.stats->motionSamples, local.motionSamples);
+		atomicMax(&a.stats->maxStack, local.maxStack);
+		atomicAdd(&a.stats->rays, nRays);
+	}
+}
+
+}   // namespace lrb
+
+#endif

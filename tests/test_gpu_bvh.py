@@ -1,0 +1,79 @@
+"""GPU parity: the CUDA device (through the C ABI) against the oracle on identical ray batches."""
+import numpy as np
+import pytest
+
+import helpers as H
+from luxcore_b200 import capi
+from luxcore_b200 import rays as R
+from luxcore_b200 import scenes as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = capi.Device(0)
+    yield d
+    d.close()
+
+
+def _rays_for(desc, n, seed):
+    lo, hi = desc.bbox()
+    pad = 0.05 * (hi - lo)
+    a = R.to_numpy_rays(R.uniform_rays(lo - pad, hi + pad, n, seed=seed))
+    side = int(np.sqrt(n))
+    b = R.to_numpy_rays(R.camera_rays(desc.cam, side, side, seed=seed + 1))
+    return np.concatenate([a, b])
+
+
+@pytest.mark.parametrize("kernel", ["persistent", "simple"])
+@pytest.mark.parametrize("name,tree_type,n", [("cornell", 4, 100000), ("cornell", 2, 50000), ("cornell", 8, 50000),
+                                              ("bigmonkey", 4, 200000), ("kitchen", 4, 1000000), ("kitchen", 2, 300000),
+                                              ("classroom", 4, 500000), ("luxball", 8, 300000)])
+def test_bvh_matches_oracle(dev, kernel, name, tree_type, n):
+    dev.set_option("kernel", kernel)
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=tree_type)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    rays = _rays_for(desc, n, seed=21)
+    ref = bvh.intersect(rays)
+    got = scene.trace_host(rays)
+    rep = H.compare_hits(got, ref, rays, what="%s k=%d %s" % (name, tree_type, kernel))
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
+    dev.set_option("kernel", "persistent")
+
+
+def test_empty_scene_all_miss(dev):
+    nodes = np.zeros(0, dtype=capi.NODE_DTYPE)
+    scene = dev.upload_bvh(nodes, np.zeros((0, 3), np.float32), np.zeros(0, np.uint32))
+    rays = R.to_numpy_rays(R.uniform_rays([-1, -1, -1], [1, 1, 1], 1000, seed=5))
+    rays["maxt"][:500] = 7.5
+    got = scene.trace_host(rays)
+    assert (got["meshIndex"] == H.NULL).all() and (got["triangleIndex"] == H.NULL).all()
+    assert (got["t"] == rays["maxt"]).all()
+    scene.free()
+
+
+def test_masked_rays_leave_hits_untouched(dev):
+    desc = S.load_fixture("cornell")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    rays = _rays_for(desc, 10000, seed=3)
+    mask = np.random.default_rng(0).random(rays.shape[0]) < 0.4
+    rays["flags"][mask] = capi.RAY_FLAGS_MASKED
+    hits = np.zeros(rays.shape[0], dtype=capi.HIT_DTYPE)
+    hits["t"] = 123.0
+    hits["meshIndex"] = 77
+    hits["triangleIndex"] = 88
+    scene.trace_host(rays, hits)
+    assert (hits["t"][mask] == 123.0).all() and (hits["meshIndex"][mask] == 77).all() and (hits["triangleIndex"][mask] == 88).all()
+    ref = bvh.intersect(rays)
+    H.compare_hits(hits[~mask], ref[~mask], rays[~mask], what="masked")
+    scene.free()
