@@ -1,0 +1,73 @@
+// luxrays/core/bvh/bvhbuild.h -- flattened BVH node type and the host-side builders (reference:
+// include/luxrays/core/bvh/bvhbuild.h:32-86, bvhbuild_types.cl:21-42).
+//
+// Builders emit the reference's depth-first skip-list array of 32-byte BVHArrayNode records:
+//   CLASSIC            restated from src/luxrays/core/bvh/bvhclassicbuild.cpp (bit-identical arrays)
+//   EMBREE_BINNED_SAH  the reference calls Embree's rtcBuildBVH (bvhembreebuild.cpp:218-280), a
+//   EMBREE_MORTON      third-party library; here both names select this tree's own from-scratch
+//                      binned-SAH k-ary builder (same array format, same "one triangle per leaf,
+//                      <= treeType children per node" contract; topology is ours).
+#ifndef _LUXRAYS_B200_BVHBUILD_H
+#define _LUXRAYS_B200_BVHBUILD_H
+
+#include <deque>
+#include <vector>
+
+#include "luxrays/luxrays.h"
+#include "luxrays/core/trianglemesh.h"
+
+namespace luxrays {
+
+namespace ocl {
+// bit-identical to ocl::BVHArrayNode
+typedef struct {
+	union {
+		struct { float bboxMin[3]; float bboxMax[3]; } bvhNode;
+		struct { unsigned int v[3]; unsigned int meshIndex, triangleIndex; } triangleLeaf;
+		struct { unsigned int leafIndex; unsigned int transformIndex, motionIndex; unsigned int meshOffsetIndex; } bvhLeaf;
+	};
+	unsigned int nodeData;
+	int pad0;
+} BVHArrayNode;
+
+typedef struct {
+	unsigned int interpolatedTransformFirstIndex, interpolatedTransformLastIndex;
+	unsigned int interpolatedInverseTransformFirstIndex, interpolatedInverseTransformLastIndex;
+} MotionSystem;
+}   // namespace ocl
+
+static_assert(sizeof(ocl::BVHArrayNode) == 32, "BVHArrayNode must stay 32 bytes");
+
+#define BVHNodeData_IsLeaf(nodeData) ((nodeData) & 0x80000000u)
+#define BVHNodeData_GetSkipIndex(nodeData) ((nodeData) & 0x7fffffffu)
+
+typedef struct {
+	u_int treeType;
+	int costSamples, isectCost, traversalCost;
+	float emptyBonus;
+} BVHParams;
+
+// One build primitive: a triangle (BVH) or a whole mesh (MBVH root).
+struct BVHTreeNode {
+	BBox bbox;
+	union {
+		struct { u_int meshIndex, triangleIndex; } triangleLeaf;
+		struct { u_int leafIndex; u_int transformIndex, motionIndex; u_int meshOffsetIndex; bool isMotionMesh; } bvhLeaf;
+	};
+	BVHTreeNode *leftChild;
+	BVHTreeNode *rightSibling;
+};
+
+// meshes != NULL: leaves are triangles (vertex indices are copied from the mesh);
+// meshes == NULL: leaves carry the bvhLeaf payload (MBVH root tree).
+// The caller owns the returned array (delete[]).
+extern ocl::BVHArrayNode *BuildBVH(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes,
+		std::vector<BVHTreeNode *> &leafList);
+extern ocl::BVHArrayNode *BuildEmbreeBVHBinnedSAH(const BVHParams &params, u_int *nNodes,
+		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
+extern ocl::BVHArrayNode *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes,
+		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
+
+}   // namespace luxrays
+
+#endif

@@ -1,0 +1,6 @@
+// Forwarder: the reference keeps this type in include/luxrays/core/geometry/motionsystem.h; in the B200 host
+// layer all geometry value types live in one header.
+#ifndef _LUXRAYS_B200_FWD_MOTIONSYSTEM_H
+#define _LUXRAYS_B200_FWD_MOTIONSYSTEM_H
+#include "luxrays/core/geometry.h"
+#endif
