@@ -11,6 +11,7 @@
 #include "luxrays/core/hardwareintersectiondevice.h"
 
 struct lrb_device;
+struct lrb_scene;
 
 namespace luxrays {
 
@@ -105,6 +106,9 @@ public:
 	// Single ray: traced on the GPU as a batch of one (the reference calls the CPU
 	// accel->Intersect here; this build has no CPU intersection code).
 	virtual bool TraceRay(const Ray *ray, RayHit *rayHit);
+
+	// the C-ABI scene of the running kernel (nullptr before Start)
+	lrb_scene *GetNativeScene() const;
 
 	friend class Context;
 

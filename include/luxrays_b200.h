@@ -122,7 +122,7 @@ typedef struct {
 typedef struct {
 	uint32_t n_ref_nodes;          /* BVHArrayNode count received */
 	uint32_t n_wide_nodes;         /* 128-B wide nodes after re-layout */
-	uint32_t n_triangles;          /* 48-B pre-gathered triangle records */
+	uint32_t n_triangles;          /* 64-B pre-gathered triangle records */
 	uint32_t n_instances;          /* 32-B instance records (MBVH) */
 	uint32_t stack_need;           /* worst-case traversal stack entries */
 	uint32_t two_level;            /* 0 = BVH, 1 = MBVH */
@@ -141,7 +141,7 @@ typedef struct {
 typedef struct {
 	uint64_t rays;                 /* non-masked rays */
 	uint64_t wide_nodes;           /* 128-B node fetches */
-	uint64_t triangles;            /* 48-B triangle record fetches */
+	uint64_t triangles;            /* 64-B triangle record fetches */
 	uint64_t instances;            /* instance entries (32-B record + 64-B matrix) */
 	uint64_t motion_samples;       /* motion leaves entered */
 	uint64_t max_stack;            /* deepest stack seen */
@@ -156,7 +156,8 @@ LRB_API int lrb_device_get_props(lrb_device *dev, lrb_device_props *out);
  * NULL restores the device's own stream. */
 LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
 LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
-/* Tunables: "block_threads", "blocks_per_sm", "kernel" = "persistent"|"simple", "l2_persist" = 0|1. */
+/* Tunables (strings): "kernel" = "persistent"|"simple", "block_threads", "blocks_per_sm", "smem_depth",
+ * "refill_below", "tri_bias", "host_chunk". */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
 
 /* ---- memory + queue (cudadevice.cpp:407-540) ------------------------------------------- */
@@ -190,8 +191,12 @@ LRB_API int lrb_scene_get_info(lrb_scene *scene, lrb_scene_info *out);
  * memory included).  Asynchronous.  Rays with flags & LRB_RAY_FLAGS_MASKED are skipped and their
  * RayHit is left untouched (bvh.cl:242-244). */
 LRB_API int lrb_trace(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count);
-/* Host-buffer convenience (the end-to-end path): H2D rays, trace, D2H hits, synchronise. */
-LRB_API int lrb_trace_host(lrb_scene *scene, const lrb_ray *rays, lrb_rayhit *hits, uint32_t ray_count);
+/* Host-buffer path (end to end): rays are copied in, traced and the hits copied out in chunks, with
+ * the copies of neighbouring chunks overlapping the trace of the current one; synchronises before
+ * returning.  preload_hits != 0 first uploads the caller's hit buffer, so that the RayHit of masked
+ * rays keeps its previous content (what AllocBufferRW(&hits, hostHits, ...) does in the reference
+ * sequence); with 0 the RayHit of a masked ray is unspecified. */
+LRB_API int lrb_trace_host(lrb_scene *scene, const lrb_ray *rays, lrb_rayhit *hits, uint32_t ray_count, int preload_hits);
 /* Same trace through the instrumented kernel; blocks and fills `stats`. hits_dev may be NULL. */
 LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
 		lrb_trace_stats_t *stats);
@@ -201,6 +206,9 @@ LRB_API const char *lrb_last_error_string(void);
 LRB_API int lrb_get_counters(lrb_device *dev, lrb_counters *out);
 LRB_API int lrb_reset_counters(lrb_device *dev);
 LRB_API const char *lrb_version_string(void);
+/* Roofline denominator probe: streams `bytes` with 128-bit read-only loads `iters` times and reports
+ * GB/s.  A buffer that fits in L2 (e.g. 32 MiB) measures L2 bandwidth, a multi-GiB one HBM.  Blocks. */
+LRB_API int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double *gb_per_s);
 
 #ifdef __cplusplus
 }

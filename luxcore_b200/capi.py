@@ -30,6 +30,7 @@ EXPORTS = [
     "lrb_bvh_upload", "lrb_mbvh_upload", "lrb_mbvh_update", "lrb_scene_free", "lrb_scene_get_info",
     "lrb_trace", "lrb_trace_host", "lrb_trace_stats",
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
+    "lrb_measure_read_bandwidth",
 ]
 
 
@@ -102,12 +103,13 @@ def lib():
             "lrb_scene_free": (i32, [vp]),
             "lrb_scene_get_info": (i32, [vp, C.POINTER(SceneInfo)]),
             "lrb_trace": (i32, [vp, vp, vp, u32]),
-            "lrb_trace_host": (i32, [vp, vp, vp, u32]),
+            "lrb_trace_host": (i32, [vp, vp, vp, u32, i32]),
             "lrb_trace_stats": (i32, [vp, vp, vp, u32, C.POINTER(TraceStats)]),
             "lrb_last_error_string": (C.c_char_p, []),
             "lrb_get_counters": (i32, [vp, C.POINTER(Counters)]),
             "lrb_reset_counters": (i32, [vp]),
             "lrb_version_string": (C.c_char_p, []),
+            "lrb_measure_read_bandwidth": (i32, [vp, sz, i32, C.POINTER(C.c_double)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -193,6 +195,12 @@ class Device:
         _check(lib().lrb_get_counters(self.h, C.byref(c)))
         return c
 
+    def measure_read_bandwidth(self, nbytes, iters=20):
+        """GB/s of a streaming 128-bit read kernel over an nbytes buffer (L2-resident if it fits)."""
+        g = C.c_double(0)
+        _check(lib().lrb_measure_read_bandwidth(self.h, nbytes, iters, C.byref(g)))
+        return g.value
+
     def reset_counters(self):
         _check(lib().lrb_reset_counters(self.h))
 
@@ -254,12 +262,13 @@ class Scene:
         self.h = handle
 
     def free(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self.dev is not None:
             lib().lrb_scene_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
+            # dev is None for borrowed handles (hostapi.Session.native_scene)
             if self.dev is not None and getattr(self.dev, "h", None):
                 self.free()
         except Exception:
@@ -283,14 +292,15 @@ class Scene:
         """Host arrays in, host array out (H2D + trace + D2H inside)."""
         rays = np.ascontiguousarray(rays)
         assert rays.dtype.itemsize == 48
+        preload = hits is not None
         if hits is None:
             hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
         assert hits.dtype.itemsize == 20 and hits.shape[0] == rays.shape[0]
-        _check(lib().lrb_trace_host(self.h, _ptr(rays), _ptr(hits), rays.shape[0]))
+        _check(lib().lrb_trace_host(self.h, _ptr(rays), _ptr(hits), rays.shape[0], 1 if preload else 0))
         return hits
 
-    def trace_host_ptr(self, rays_hostptr, hits_hostptr, n):
-        _check(lib().lrb_trace_host(self.h, C.c_void_p(rays_hostptr), C.c_void_p(hits_hostptr), n))
+    def trace_host_ptr(self, rays_hostptr, hits_hostptr, n, preload_hits=False):
+        _check(lib().lrb_trace_host(self.h, C.c_void_p(rays_hostptr), C.c_void_p(hits_hostptr), n, 1 if preload_hits else 0))
 
     def trace_stats(self, rays_devptr, hits_devptr, n):
         st = TraceStats()

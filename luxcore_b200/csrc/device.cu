@@ -57,6 +57,7 @@ struct lrb_device {
 	int persistent;                 // 1 = TracePersistent, 0 = TraceStatic
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
+	int triBias;
 	int hostChunk;                  // rays per chunk in lrb_trace_host
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
@@ -148,6 +149,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->persistent = 1;
 	dev->smemDepth = 24;
 	dev->refillBelow = 20;
+	dev->triBias = 4;
 	dev->hostChunk = 1 << 20;
 	*out = dev;
 	return LRB_OK;
@@ -220,6 +222,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "refill_below") {
 		if (iv < 1 || iv > 32) return Fail(LRB_ERR_INVALID, "refill_below out of range");
 		dev->refillBelow = iv;
+	} else if (k == "tri_bias") {
+		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
+		dev->triBias = iv;
 	} else if (k == "host_chunk") {
 		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
 		dev->hostChunk = iv;
@@ -314,6 +319,59 @@ int lrb_reset_counters(lrb_device *dev) {
 	const uint64_t inUse = dev->counters.device_bytes_in_use;
 	memset(&dev->counters, 0, sizeof(dev->counters));
 	dev->counters.device_bytes_in_use = inUse;
+	return LRB_OK;
+}
+
+// ---- bandwidth probe --------------------------------------------------------------------------
+
+}   // extern "C"
+
+__global__ void __launch_bounds__(256) ReadProbeKernel(const uint4 *__restrict__ src, size_t n, unsigned *sink) {
+	unsigned acc = 0;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	// four independent 16-B loads in flight per thread
+	for (; i + 3 * stride < n; i += 4 * stride) {
+		const uint4 a = __ldg(src + i), b = __ldg(src + i + stride), c = __ldg(src + i + 2 * stride), d = __ldg(src + i + 3 * stride);
+		acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+	}
+	for (; i < n; i += stride) {
+		const uint4 a = __ldg(src + i);
+		acc ^= a.x ^ a.y ^ a.z ^ a.w;
+	}
+	if (acc == 0x9e3779b9u)
+		*sink = acc;    // practically never: keeps the loads alive
+}
+
+extern "C" {
+
+int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double *gbps) {
+	if (!gbps || bytes < 4096 || iters < 1)
+		return Fail(LRB_ERR_INVALID, "bad argument");
+	LRB_SETDEV(dev);
+	void *buf = nullptr;
+	unsigned *sink = nullptr;
+	LRB_CUDA(cudaMalloc(&buf, bytes));
+	LRB_CUDA(cudaMalloc((void **)&sink, 4));
+	LRB_CUDA(cudaMemsetAsync(buf, 1, bytes, dev->stream));
+	cudaEvent_t e0, e1;
+	LRB_CUDA(cudaEventCreate(&e0));
+	LRB_CUDA(cudaEventCreate(&e1));
+	const size_t n = bytes / 16;
+	const int grid = dev->prop.multiProcessorCount * 8;
+	for (int w = 0; w < 3; ++w)
+		ReadProbeKernel<<<grid, 256, 0, dev->stream>>>((const uint4 *)buf, n, sink);
+	LRB_CUDA(cudaEventRecord(e0, dev->stream));
+	for (int it = 0; it < iters; ++it)
+		ReadProbeKernel<<<grid, 256, 0, dev->stream>>>((const uint4 *)buf, n, sink);
+	LRB_CUDA(cudaEventRecord(e1, dev->stream));
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	float ms = 0.f;
+	LRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaFree(buf); cudaFree(sink);
+	dev->counters.kernel_launches += iters + 3;
+	*gbps = (double)n * 16.0 * iters / (ms * 1e-3) / 1e9;
 	return LRB_OK;
 }
 
@@ -558,6 +616,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.counter = s->dCounter;
 	a.stats = s->dStats;
 	a.refillBelow = (uint32_t)dev->refillBelow;
+	a.triBias = (uint32_t)dev->triBias;
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;
@@ -653,7 +712,7 @@ int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_
 
 // Host buffers in, host buffers out.  The batch is cut into chunks; chunk k+1 is copied in and
 // chunk k-1 copied out (separate streams, PCIe is full duplex) while chunk k is traced.
-int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n) {
+int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, int preloadHits) {
 	if (!s)
 		return Fail(LRB_ERR_INVALID, "null scene");
 	lrb_device *dev = s->dev;
@@ -677,11 +736,7 @@ int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t
 		LRB_CUDA(cudaMalloc(&dev->stageHits, hb));
 		dev->stageHitsBytes = hb;
 	}
-	// masked rays leave their RayHit untouched: the device copy must start from the caller's
-	// content, but only when some ray is masked; a cheap scan over the flags decides
-	bool anyMasked = false;
-	for (uint32_t i = 0; i < n; ++i)
-		if (rays[i].flags & LRB_RAY_FLAGS_MASKED) { anyMasked = true; break; }
+	const bool anyMasked = preloadHits != 0;
 
 	const uint32_t chunk = (uint32_t)dev->hostChunk;
 	const uint32_t nChunks = (n + chunk - 1) / chunk;

@@ -11,8 +11,9 @@
 //     INNER children in struct-of-arrays form (the boxes are copied bit-for-bit from the children's
 //     own BVHArrayNode records) and their wide-node indices, so one fetch replaces up to five
 //     dependent 32-B fetches of the reference walk.
-//   TriRecord (48 B, 16-B aligned): the three vertices pre-gathered next to meshIndex /
-//     triangleIndex, one per reference triangle leaf; the leaf children of one node are contiguous.
+//   TriRecord (64 B, 64-B aligned = two 256-bit loads): the three vertices pre-gathered next to
+//     meshIndex / triangleIndex, one per reference triangle leaf; the leaf children of one node are
+//     contiguous.
 //   InstRecord (32 B): one per MBVH root leaf (bvhLeaf payload, bvhbuild_types.cl:33-37).
 //
 // Reference leaves carry no box of their own (bvhclassicbuild.cpp:196-214), so -- exactly like
@@ -46,10 +47,11 @@ struct __attribute__((aligned(128))) WideNode {
 	uint32_t pad;
 };
 
-struct __attribute__((aligned(16))) TriRecord {
+struct __attribute__((aligned(64))) TriRecord {
 	float p0[3], p1[3], p2[3];
 	uint32_t meshIndex, triangleIndex;
 	uint32_t order;         // index of the leaf in its reference BVHArrayNode array
+	uint32_t pad[4];        // 64 B: two 256-bit loads, never straddles a 128-B line
 };
 
 struct __attribute__((aligned(16))) InstRecord {
@@ -78,7 +80,7 @@ enum {
 };
 
 static_assert(sizeof(WideNode) == 128, "WideNode");
-static_assert(sizeof(TriRecord) == 48, "TriRecord");
+static_assert(sizeof(TriRecord) == 64, "TriRecord");
 static_assert(sizeof(InstRecord) == 32, "InstRecord");
 static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
 

@@ -81,6 +81,7 @@ static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr) {
 	tr->meshIndex = mesh;
 	tr->triangleIndex = nd.triangleLeaf.triangleIndex;
 	tr->order = c;
+	tr->pad[0] = tr->pad[1] = tr->pad[2] = tr->pad[3] = 0;
 }
 
 static void FillInst(const TreeInput &in, uint32_t c, InstRecord *ir) {

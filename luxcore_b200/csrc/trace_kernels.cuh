@@ -103,6 +103,7 @@ struct TraceArgs {
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
+	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	TraceStats *stats;          // STATS kernels only
 };
 
@@ -188,12 +189,26 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 		}
 
 		// ---- traverse until too few lanes are alive ----
+		// Every iteration the warp runs ONE of two branch-free phases, whichever has more lanes
+		// ready: a node phase (pop / fetch a 128-B node / four box tests / ordered push) or a
+		// triangle phase (one pending leaf triangle per lane).  A lane holding pending triangles
+		// waits for a triangle phase; batching the two kinds of work keeps lanes converged on
+		// incoherent rays instead of serialising "my node had leaves" against "mine had not".
 		const int floorLanes = exhausted ? 1 : (int)a.refillBelow;
 		do {
-			if (active) {
-				if (!Step<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
-					StoreHit(a.hits, rayIdx, s, rayMaxt);
-					active = false;
+			const bool wantTri = active && s.pendCount != 0;
+			const bool wantNode = active && s.pendCount == 0;
+			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
+			const int nNode = __popc(__ballot_sync(0xffffffffu, wantNode));
+			if (nTri * (int)a.triBias >= nNode * 4) {
+				if (wantTri)
+					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+			} else {
+				if (wantNode) {
+					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
+						StoreHit(a.hits, rayIdx, s, rayMaxt);
+						active = false;
+					}
 				}
 			}
 			live = __ballot_sync(0xffffffffu, active);

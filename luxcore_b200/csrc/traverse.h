@@ -42,8 +42,15 @@
 #define LRB_LDG4(p) __ldg(reinterpret_cast<const float4 *>(p))
 #define LRB_LDGU4(p) __ldg(reinterpret_cast<const uint4 *>(p))
 #define LRB_INF __int_as_float(0x7f800000)
+#define LRB_FMAX(a, b) fmaxf((a), (b))
+#define LRB_FMIN(a, b) fminf((a), (b))
+#define LRB_F2U(x) __float_as_uint(x)
 #else
 #define LRB_INF __builtin_huge_valf()
+/* fmaxf/fminf semantics of the device (the non-NaN operand wins) */
+#define LRB_FMAX(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) > (b) ? (a) : (b))))
+#define LRB_FMIN(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) < (b) ? (a) : (b))))
+#define LRB_F2U(x) lrb::HostF2U(x)
 #define LRB_MUL(a, b) ((a) * (b))
 #define LRB_ADD(a, b) ((a) + (b))
 #define LRB_SUB(a, b) ((a) - (b))
@@ -56,6 +63,23 @@ namespace lrb {
 #if !defined(__CUDACC__)
 struct float4 { float x, y, z, w; };
 struct uint4 { uint32_t x, y, z, w; };
+#endif
+
+// 32 bytes fetched by ONE load instruction: Blackwell's 256-bit LDG (ld.global.nc.v8.f32,
+// SASS LDG.E.ENL2.256.CONSTANT) halves the L1 data-pipe wavefronts of a divergent node fetch.
+struct F8 { float v[8]; };
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ F8 Ld256(const void *p) {
+	F8 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+		: "l"(p));
+	return r;
+}
+#else
+static inline F8 Ld256(const void *p) { F8 r; __builtin_memcpy(&r, p, 32); return r; }
+static inline uint32_t HostF2U(float x) { uint32_t u; __builtin_memcpy(&u, &x, 4); return u; }
 #endif
 
 #if !defined(__CUDA_ARCH__)
@@ -83,6 +107,7 @@ struct RayState {
 	uint32_t bestInst, bestTri;     // reference array order of the current best hit
 	uint32_t curInstOrder, curMeshOffset;
 	uint32_t cur;           // wide node to visit next, or kNullIndex when the stack must be popped
+	uint32_t pendBase, pendCount;   // leaf triangles of the last visited node still to be tested
 	bool inInstance;
 };
 
@@ -91,58 +116,56 @@ LRB_HD float Dot3(float ax, float ay, float az, float bx, float by, float bz) {
 	return LRB_ADD(LRB_ADD(LRB_MUL(ax, bx), LRB_MUL(ay, by)), LRB_MUL(az, bz));
 }
 
-// Triangle::Intersect, triangle.h:55-89.  Returns true and t/b1/b2 when the triangle is hit
-// within [mint, maxt].
-LRB_HD bool TriangleTest(const RayState &r, const float4 a, const float4 b, const float p2z,
+// Triangle::Intersect, triangle.h:55-89, evaluated without branches: every quantity is computed
+// and the reference's chain of early-outs becomes one predicate.  `!(x < 0)` keeps the reference's
+// behaviour for NaN (a NaN barycentric does not reject), and divisor == 0 rejects explicitly.
+LRB_HD bool TriangleTest(const RayState &r, const float p0x, const float p0y, const float p0z,
+		const float p1x, const float p1y, const float p1z, const float p2x, const float p2y, const float p2z,
 		float *tOut, float *b1Out, float *b2Out) {
-	// TriRecord as three 16-B words: a = p0.xyz p1.x ; b = p1.yz p2.xy ; c = p2.z meshIndex triangleIndex order
-	const float p0x = a.x, p0y = a.y, p0z = a.z;
-	const float p1x = a.w, p1y = b.x, p1z = b.y;
-	const float p2x = b.z, p2y = b.w;
-
 	const float e1x = LRB_SUB(p1x, p0x), e1y = LRB_SUB(p1y, p0y), e1z = LRB_SUB(p1z, p0z);
 	const float e2x = LRB_SUB(p2x, p0x), e2y = LRB_SUB(p2y, p0y), e2z = LRB_SUB(p2z, p0z);
 	// s1 = Cross(d, e2)   (vector.h:159-163)
 	const float s1x = LRB_SUB(LRB_MUL(r.dy, e2z), LRB_MUL(r.dz, e2y));
 	const float s1y = LRB_SUB(LRB_MUL(r.dz, e2x), LRB_MUL(r.dx, e2z));
 	const float s1z = LRB_SUB(LRB_MUL(r.dx, e2y), LRB_MUL(r.dy, e2x));
-
 	const float divisor = Dot3(s1x, s1y, s1z, e1x, e1y, e1z);
-	if (divisor == 0.f)
-		return false;
 	const float invDivisor = LRB_RCP(divisor);
 
 	const float ddx = LRB_SUB(r.ox, p0x), ddy = LRB_SUB(r.oy, p0y), ddz = LRB_SUB(r.oz, p0z);
 	const float b1 = LRB_MUL(Dot3(ddx, ddy, ddz, s1x, s1y, s1z), invDivisor);
-	if (b1 < 0.f)
-		return false;
-
 	// s2 = Cross(dd, e1)
 	const float s2x = LRB_SUB(LRB_MUL(ddy, e1z), LRB_MUL(ddz, e1y));
 	const float s2y = LRB_SUB(LRB_MUL(ddz, e1x), LRB_MUL(ddx, e1z));
 	const float s2z = LRB_SUB(LRB_MUL(ddx, e1y), LRB_MUL(ddy, e1x));
 	const float b2 = LRB_MUL(Dot3(r.dx, r.dy, r.dz, s2x, s2y, s2z), invDivisor);
-	if (b2 < 0.f)
-		return false;
-
 	const float b0 = LRB_SUB(LRB_SUB(1.f, b1), b2);
-	if (b0 < 0.f)
-		return false;
-
 	const float t = LRB_MUL(Dot3(e2x, e2y, e2z, s2x, s2y, s2z), invDivisor);
-	if (t < r.mint || t > r.maxt)
-		return false;
+
+	const bool hit = (divisor != 0.f) & !(b1 < 0.f) & !(b2 < 0.f) & !(b0 < 0.f) & !(t < r.mint) & !(t > r.maxt);
 	*tOut = t; *b1Out = b1; *b2Out = b2;
-	return true;
+	return hit;
 }
 
-// One slab of BBox::IntersectP (bbox.cpp:152-161) with the reference's exact select semantics.
+// One slab of BBox::IntersectP (bbox.cpp:152-161).  The swap keeps the reference's exact semantics
+// (no swap when either value is NaN); the interval updates use max/min that ignore a NaN operand,
+// which is what the reference's `tNear > t0 ? tNear : t0` does for a non-NaN t0.
 LRB_HD void Slab(float lo, float hi, float o, float inv, float &t0, float &t1) {
-	float tNear = LRB_MUL(LRB_SUB(lo, o), inv);
-	float tFar = LRB_MUL(LRB_SUB(hi, o), inv);
-	if (tNear > tFar) { const float s = tNear; tNear = tFar; tFar = s; }
-	t0 = tNear > t0 ? tNear : t0;
-	t1 = tFar < t1 ? tFar : t1;
+	const float a = LRB_MUL(LRB_SUB(lo, o), inv);
+	const float b = LRB_MUL(LRB_SUB(hi, o), inv);
+	const bool sw = a > b;
+	const float tNear = sw ? b : a;
+	const float tFar = sw ? a : b;
+	t0 = LRB_FMAX(t0, tNear);
+	t1 = LRB_FMIN(t1, tFar);
+}
+
+// Entry distance of one child box, or +inf when the ray misses it / the slot is unused.
+LRB_HD float ChildEntry(const RayState &s, bool used, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+	float t0 = s.mint, t1 = s.maxt;
+	Slab(lox, hix, s.ox, s.ix, t0, t1);
+	Slab(loy, hiy, s.oy, s.iy, t0, t1);
+	Slab(loz, hiz, s.oz, s.iz, t0, t1);
+	return (used & !(t0 > t1)) ? t0 : LRB_INF;
 }
 
 LRB_HD void SetRay(RayState &s, float ox, float oy, float oz, float dx, float dy, float dz) {
@@ -286,19 +309,47 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	s.time = ray.time;
 	s.b1 = 0.f; s.b2 = 0.f;
 	s.hitMesh = kNullIndex; s.hitTri = kNullIndex;
-	// order 0 can never be beaten, so a hit at exactly t == ray.maxt is rejected as in the
-	// reference (its `t < rayHit->t` fails against the initial rayHit->t = maxt)
 	s.bestInst = 0; s.bestTri = 0;
 	s.curInstOrder = 0; s.curMeshOffset = 0;
+	s.pendBase = 0; s.pendCount = 0;
 	s.inInstance = false;
 	s.cur = sc.nWide ? sc.rootWide : kNullIndex;
 	return sc.nWide != 0;
 }
 
-// One traversal step: visit s.cur (or pop).  Returns false when the ray is finished.
-// STACK provides push(uint32_t node, float t0) / pop(uint32_t&, float&) / empty().
+// Tests ONE pending leaf triangle of the last visited node.
+//   accept: strictly closer, or exactly as close as the current hit but earlier in the reference's
+//   depth-first array (so a hit at exactly t == ray.maxt is rejected while nothing was hit yet,
+//   like the reference's `t < rayHit->t` against the initial rayHit->t = maxt).
+template <bool TWO_LEVEL, bool STATS>
+LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
+	s.pendCount -= 1;
+	const char *tp = reinterpret_cast<const char *>(sc.tris + (s.pendBase + s.pendCount));
+	const F8 a = Ld256(tp), b = Ld256(tp + 32);    // p0 p1 p2.xy | p2.z mesh tri order pad
+	if (STATS) stats->triangles++;
+	float t, b1, b2;
+	const bool hit = TriangleTest(s, a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7], b.v[0], &t, &b1, &b2);
+	const uint32_t mesh = LRB_F2U(b.v[1]), tri = LRB_F2U(b.v[2]), order = LRB_F2U(b.v[3]);
+	const uint32_t instOrder = TWO_LEVEL ? s.curInstOrder : 0u;
+	const bool closer = t < s.maxt;
+	const bool tieWin = (t == s.maxt) & (s.hitMesh != kNullIndex) &
+			((instOrder < s.bestInst) | ((instOrder == s.bestInst) & (order < s.bestTri)));
+	if (hit & (closer | tieWin)) {
+		s.maxt = t;
+		s.b1 = b1; s.b2 = b2;
+		s.hitMesh = TWO_LEVEL ? (mesh + s.curMeshOffset) : mesh;
+		s.hitTri = tri;
+		s.bestInst = instOrder;
+		s.bestTri = order;
+	}
+}
+
+// Visits one wide node (popping the stack first when needed): box-tests its inner children,
+// orders them near-to-far, pushes all but the nearest, and records the node's leaf triangles as
+// pending work for TriStep.  Returns false when the ray is finished.
+// STACK provides push(uint32_t node, float t0) / pop(uint32_t&, float&) / empty() / depth().
 template <bool TWO_LEVEL, bool STATS, class STACK>
-LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
 	uint32_t cur = s.cur;
 	if (cur == kNullIndex) {
 		// pop until something is still worth visiting
@@ -316,8 +367,9 @@ LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STAC
 				}
 				if (cur & kTagInstance) {
 					// enter a leaf tree (mbvhaccel.cpp:312-333)
-					const uint4 ir = LRB_LDGU4(&sc.insts[cur & ~kTagInstance]);
-					const uint4 ir2 = LRB_LDGU4(reinterpret_cast<const char *>(&sc.insts[cur & ~kTagInstance]) + 16);
+					const char *ip = reinterpret_cast<const char *>(&sc.insts[cur & ~kTagInstance]);
+					const uint4 ir = LRB_LDGU4(ip);
+					const uint4 ir2 = LRB_LDGU4(ip + 16);
 					if (STATS) stats->instances++;
 					if (ir.x == kNullIndex)
 						continue;       // empty leaf tree
@@ -347,75 +399,43 @@ LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STAC
 		}
 	}
 
-	const WideNode *node = sc.nodes + cur;
+	// ---- fetch the 128-byte node with four 256-bit loads ----
+	const char *np = reinterpret_cast<const char *>(sc.nodes + cur);
 	if (STATS) stats->wideNodes++;
-	const float4 nminx = LRB_LDG4(node->bminx), nminy = LRB_LDG4(node->bminy), nminz = LRB_LDG4(node->bminz);
-	const float4 nmaxx = LRB_LDG4(node->bmaxx), nmaxy = LRB_LDG4(node->bmaxy), nmaxz = LRB_LDG4(node->bmaxz);
-	const uint4 kids = LRB_LDGU4(node->child);
-	const uint4 meta = LRB_LDGU4(&node->leafBase);      // leafBase, counts, next, pad
-	const uint32_t nInner = meta.y & 0xffu;
-	const uint32_t nLeaf = meta.y >> 8;
+	const F8 A = Ld256(np);          // bminx[4] bminy[4]
+	const F8 B = Ld256(np + 32);     // bminz[4] bmaxx[4]
+	const F8 C = Ld256(np + 64);     // bmaxy[4] bmaxz[4]
+	const F8 D = Ld256(np + 96);     // child[4] leafBase counts next pad
+	const uint32_t counts = LRB_F2U(D.v[5]);
+	const uint32_t nInner = counts & 0xffu;
+	const uint32_t nLeaf = counts >> 8;
+	const uint32_t leafBase = LRB_F2U(D.v[4]);
+	const uint32_t next = LRB_F2U(D.v[6]);
 
-	// ---- leaf children -------------------------------------------------------------------
+	// ---- leaf children ----
 	if (TWO_LEVEL && !s.inInstance) {
 		// root tree: leaves are instances; they have no box of their own in the reference, so each
 		// one is entered (mbvhaccel.cpp:312).  Defer them through the stack.
 		for (uint32_t j = 0; j < nLeaf; ++j)
-			stk.push(kTagInstance | (meta.x + j), 0.f);
+			stk.push(kTagInstance | (leafBase + j), 0.f);
 	} else {
-		for (uint32_t j = 0; j < nLeaf; ++j) {
-			const char *tp = reinterpret_cast<const char *>(sc.tris + (meta.x + j));
-			const float4 a = LRB_LDG4(tp), b = LRB_LDG4(tp + 16), cf = LRB_LDG4(tp + 32);
-			const uint4 c = LRB_LDGU4(tp + 32);
-			if (STATS) stats->triangles++;
-			float t, b1, b2;
-			if (TriangleTest(s, a, b, cf.x, &t, &b1, &b2)) {
-				const uint32_t instOrder = TWO_LEVEL ? s.curInstOrder : 0u;
-				const bool closer = t < s.maxt;
-				const bool tieWin = (t == s.maxt) && (s.hitMesh != kNullIndex) &&
-						(instOrder < s.bestInst || (instOrder == s.bestInst && c.w < s.bestTri));
-				if (closer || tieWin) {
-					s.maxt = t;
-					s.b1 = b1; s.b2 = b2;
-					s.hitMesh = TWO_LEVEL ? (c.y + s.curMeshOffset) : c.y;
-					s.hitTri = c.z;
-					s.bestInst = instOrder;
-					s.bestTri = c.w;
-				}
-			}
-		}
+		s.pendBase = leafBase;
+		s.pendCount = nLeaf;
 	}
 
-	// ---- inner children: box tests, near-to-far ordering ------------------------------------
-	float d0, d1, d2, d3;       // entry distances, +inf = not hit
+	// ---- inner children: box tests (all four slots, no branches), near-to-far ordering ----
 	const float kInf = LRB_INF;
-	{
-		float t0 = s.mint, t1 = s.maxt;
-		Slab(nminx.x, nmaxx.x, s.ox, s.ix, t0, t1); Slab(nminy.x, nmaxy.x, s.oy, s.iy, t0, t1); Slab(nminz.x, nmaxz.x, s.oz, s.iz, t0, t1);
-		d0 = (nInner > 0 && !(t0 > t1)) ? t0 : kInf;
-	}
-	{
-		float t0 = s.mint, t1 = s.maxt;
-		Slab(nminx.y, nmaxx.y, s.ox, s.ix, t0, t1); Slab(nminy.y, nmaxy.y, s.oy, s.iy, t0, t1); Slab(nminz.y, nmaxz.y, s.oz, s.iz, t0, t1);
-		d1 = (nInner > 1 && !(t0 > t1)) ? t0 : kInf;
-	}
-	{
-		float t0 = s.mint, t1 = s.maxt;
-		Slab(nminx.z, nmaxx.z, s.ox, s.ix, t0, t1); Slab(nminy.z, nmaxy.z, s.oy, s.iy, t0, t1); Slab(nminz.z, nmaxz.z, s.oz, s.iz, t0, t1);
-		d2 = (nInner > 2 && !(t0 > t1)) ? t0 : kInf;
-	}
-	{
-		float t0 = s.mint, t1 = s.maxt;
-		Slab(nminx.w, nmaxx.w, s.ox, s.ix, t0, t1); Slab(nminy.w, nmaxy.w, s.oy, s.iy, t0, t1); Slab(nminz.w, nmaxz.w, s.oz, s.iz, t0, t1);
-		d3 = (nInner > 3 && !(t0 > t1)) ? t0 : kInf;
-	}
-	// A box whose entry distance is +inf but which passed the test (mint = maxt = +inf) cannot
-	// contain an acceptable hit closer than +inf; treating it as "not hit" is exact because the
-	// triangle test rejects t > maxt and a tie at +inf never beats order 0.
-	uint32_t c0 = kids.x, c1 = kids.y, c2 = kids.z, c3 = kids.w;
+	float d0 = ChildEntry(s, nInner > 0, A.v[0], A.v[4], B.v[0], B.v[4], C.v[0], C.v[4]);
+	float d1 = ChildEntry(s, nInner > 1, A.v[1], A.v[5], B.v[1], B.v[5], C.v[1], C.v[5]);
+	float d2 = ChildEntry(s, nInner > 2, A.v[2], A.v[6], B.v[2], B.v[6], C.v[2], C.v[6]);
+	float d3 = ChildEntry(s, nInner > 3, A.v[3], A.v[7], B.v[3], B.v[7], C.v[3], C.v[7]);
+	// A box that passes with entry distance +inf (mint = maxt = +inf) cannot hold an acceptable hit:
+	// the triangle test rejects t > maxt and a tie at +inf never wins; "not hit" is exact.
+	uint32_t c0 = LRB_F2U(D.v[0]), c1 = LRB_F2U(D.v[1]), c2 = LRB_F2U(D.v[2]), c3 = LRB_F2U(D.v[3]);
 
-	// sorting network on (distance, child): ascending
-#define LRB_CSWAP(da, ca, db, cb) { if (db < da) { const float td = da; da = db; db = td; const uint32_t tc = ca; ca = cb; cb = tc; } }
+	// sorting network on (distance, child), ascending, written with selects
+#define LRB_CSWAP(da, ca, db, cb) { const bool sw_ = db < da; const float lo_ = sw_ ? db : da, hi_ = sw_ ? da : db; \
+		const uint32_t cl_ = sw_ ? cb : ca, ch_ = sw_ ? ca : cb; da = lo_; db = hi_; ca = cl_; cb = ch_; }
 	LRB_CSWAP(d0, c0, d1, c1)
 	LRB_CSWAP(d2, c2, d3, c3)
 	LRB_CSWAP(d0, c0, d2, c2)
@@ -424,14 +444,24 @@ LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STAC
 #undef LRB_CSWAP
 
 	// continuation node (reference nodes with more than four inner children): always visited
-	if (meta.z != kNullIndex)
-		stk.push(meta.z, -kInf);
+	if (next != kNullIndex)
+		stk.push(next, -kInf);
 	// push far-to-near, keep the nearest
 	if (d3 < kInf) stk.push(c3, d3);
 	if (d2 < kInf) stk.push(c2, d2);
 	if (d1 < kInf) stk.push(c1, d1);
 	s.cur = (d0 < kInf) ? c0 : kNullIndex;
 	if (STATS) { const unsigned long long d = stk.depth(); if (d > stats->maxStack) stats->maxStack = d; }
+	return true;
+}
+
+// One node visit followed by all of its triangle tests (static kernel, host emulation).
+template <bool TWO_LEVEL, bool STATS, class STACK>
+LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+	if (!NodeStep<TWO_LEVEL, STATS>(sc, worldRay, s, stk, stats))
+		return false;
+	while (s.pendCount)
+		TriStep<TWO_LEVEL, STATS>(sc, s, stats);
 	return true;
 }
 

@@ -253,6 +253,12 @@ void CUDAIntersectionDevice::SetDataSet(DataSet *newDataSet) {
 	accel = dataSet->GetAccelerator(t);
 }
 
+extern lrb_scene *NativeSceneOf(HardwareIntersectionKernel *k);
+
+lrb_scene *CUDAIntersectionDevice::GetNativeScene() const {
+	return kernel ? NativeSceneOf(kernel) : nullptr;
+}
+
 void CUDAIntersectionDevice::Update() {
 	kernel->Update(dataSet);
 }

@@ -31,11 +31,23 @@ static void *DevPtr(HardwareDeviceBuffer *b, const char *what) {
 	return cb->GetDevicePointer();
 }
 
+// lets tools reach the C-ABI scene behind a kernel object (statistics, host-buffer pipeline)
+class B200SceneOwner {
+public:
+	virtual ~B200SceneOwner() { }
+	virtual lrb_scene *NativeScene() const = 0;
+};
+
+lrb_scene *NativeSceneOf(HardwareIntersectionKernel *k) {
+	B200SceneOwner *o = dynamic_cast<B200SceneOwner *>(k);
+	return o ? o->NativeScene() : nullptr;
+}
+
 //------------------------------------------------------------------------------
 // BVHKernel
 //------------------------------------------------------------------------------
 
-class BVHKernel : public HardwareIntersectionKernel {
+class BVHKernel : public HardwareIntersectionKernel, public B200SceneOwner {
 public:
 	BVHKernel(HardwareIntersectionDevice &dev, const BVHAccel &bvh) : HardwareIntersectionKernel(dev), scene(nullptr) {
 		lrb_device *nd = NativeOf(dev);
@@ -65,6 +77,7 @@ public:
 	virtual ~BVHKernel() { lrb_scene_free(scene); }
 
 	virtual void Update(const DataSet *) { throw std::runtime_error("BVHAccel does not support Update()"); }
+	virtual lrb_scene *NativeScene() const { return scene; }
 
 	virtual void EnqueueTraceRayBuffer(HardwareDeviceBuffer *rayBuff, HardwareDeviceBuffer *rayHitBuff, const unsigned int rayCount) {
 		if (rayCount == 0)
@@ -83,7 +96,7 @@ HardwareIntersectionKernel *BVHAccel::NewHardwareIntersectionKernel(HardwareInte
 // MBVHKernel
 //------------------------------------------------------------------------------
 
-class MBVHKernel : public HardwareIntersectionKernel {
+class MBVHKernel : public HardwareIntersectionKernel, public B200SceneOwner {
 public:
 	MBVHKernel(HardwareIntersectionDevice &dev, const MBVHAccel &acc) : HardwareIntersectionKernel(dev), mbvh(acc), scene(nullptr) {
 		lrb_device *nd = NativeOf(dev);
@@ -135,6 +148,8 @@ public:
 		Check(lrb_mbvh_upload(nd, &d, &scene), "MBVHKernel upload");
 	}
 	virtual ~MBVHKernel() { lrb_scene_free(scene); }
+
+	virtual lrb_scene *NativeScene() const { return scene; }
 
 	// after MBVHAccel::Update(): new root tree, refreshed inverse instance matrices
 	virtual void Update(const DataSet *) {

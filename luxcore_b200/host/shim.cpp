@@ -231,6 +231,11 @@ LRH_API void *lrh_native_device(void *sp) {
 	return s->device ? s->device->GetNativeHandle() : nullptr;
 }
 
+LRH_API void *lrh_native_scene(void *sp) {
+	Session *s = (Session *)sp;
+	return s->device ? s->device->GetNativeScene() : nullptr;
+}
+
 LRH_API int lrh_accelerator_type(void *sp) {
 	Session *s = (Session *)sp;
 	return s->accel ? (int)s->accel->GetType() : -1;

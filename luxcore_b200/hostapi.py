@@ -20,7 +20,7 @@ EXPORTS = [
     "lrh_last_error", "lrh_create", "lrh_destroy", "lrh_device_description_count", "lrh_add_shape", "lrh_add_plain",
     "lrh_add_instance", "lrh_add_motion", "lrh_preprocess", "lrh_build_accelerator", "lrh_bvh_node_count",
     "lrh_bvh_nodes", "lrh_mbvh_root_node_count", "lrh_mbvh_root_nodes", "lrh_mbvh_leaf_count",
-    "lrh_mbvh_leaf_node_count", "lrh_mbvh_leaf_nodes", "lrh_mesh_bbox", "lrh_start", "lrh_stop", "lrh_native_device",
+    "lrh_mbvh_leaf_node_count", "lrh_mbvh_leaf_nodes", "lrh_mesh_bbox", "lrh_start", "lrh_stop", "lrh_native_device", "lrh_native_scene",
     "lrh_accelerator_type", "lrh_trace_host", "lrh_trace_device", "lrh_finish", "lrh_trace_ray",
     "lrh_set_instance_transform", "lrh_update", "lrh_stats_total_rays", "lrh_used_memory", "lrh_machine_epsilon",
     "lrh_matrix_inverse",
@@ -59,6 +59,7 @@ def lib():
             "lrh_start": (i32, [vp, i32]),
             "lrh_stop": (i32, [vp]),
             "lrh_native_device": (vp, [vp]),
+            "lrh_native_scene": (vp, [vp]),
             "lrh_accelerator_type": (i32, [vp]),
             "lrh_trace_host": (i32, [vp, vp, vp, u32, i32]),
             "lrh_trace_device": (i32, [vp, vp, vp, u32]),
@@ -200,6 +201,14 @@ class Session:
 
     def native_device(self):
         return lib().lrh_native_device(self.h)
+
+    def native_scene(self):
+        """capi.Scene view of the running kernel's C-ABI scene (not owned)."""
+        h = lib().lrh_native_scene(self.h)
+        if not h:
+            raise HostError("session not started")
+        sc = capi.Scene(None, C.c_void_p(h))
+        return sc
 
     def set_stream(self, cuda_stream_handle):
         capi._check(capi.lib().lrb_device_set_stream(C.c_void_p(self.native_device()), C.c_void_p(cuda_stream_handle or 0)))

@@ -160,3 +160,25 @@ def grid_mesh(nx, ny, z=0.0, size=1.0):
             tris.append((a, b, d))
             tris.append((a, d, c))
     return v.astype(np.float32), np.asarray(tris, dtype=np.uint32)
+
+
+def world_triangles(desc):
+    """World-space (p0, e1, e2) of every triangle of every dataset mesh, plus the per-mesh offset of
+    its first triangle -- what a path tracer's shading stage would look up from a RayHit.  Motion
+    meshes are taken at their first key.  Used only to synthesise bounce-ray batches."""
+    p0s, e1s, e2s, offs = [], [], [], []
+    total = 0
+    for m in desc.meshes:
+        v, t = desc.shapes[m.shape]
+        if m.kind == INSTANCE:
+            v = transform_points(m.xform, v)
+        elif m.kind == MOTION:
+            v = transform_points(np.linalg.inv(m.motion_xforms[0].astype(np.float64)).astype(np.float32), v)
+        a = v[t[:, 0]]
+        p0s.append(a)
+        e1s.append(v[t[:, 1]] - a)
+        e2s.append(v[t[:, 2]] - a)
+        offs.append(total)
+        total += t.shape[0]
+    return (np.concatenate(p0s).astype(np.float32), np.concatenate(e1s).astype(np.float32),
+            np.concatenate(e2s).astype(np.float32), np.asarray(offs, dtype=np.int64))
