@@ -58,6 +58,7 @@ struct lrb_device {
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
 	int triBias;
+	int triDrain;
 	int hostChunk;                  // rays per chunk in lrb_trace_host
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
@@ -147,9 +148,10 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->blockThreads = 128;
 	dev->blocksPerSM = 0;
 	dev->persistent = 1;
-	dev->smemDepth = 24;
+	dev->smemDepth = 12;
 	dev->refillBelow = 20;
-	dev->triBias = 4;
+	dev->triBias = 8;
+	dev->triDrain = 0;
 	dev->hostChunk = 1 << 20;
 	*out = dev;
 	return LRB_OK;
@@ -225,6 +227,8 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "tri_bias") {
 		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
 		dev->triBias = iv;
+	} else if (k == "tri_drain") {
+		dev->triDrain = iv ? 1 : 0;
 	} else if (k == "host_chunk") {
 		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
 		dev->hostChunk = iv;
@@ -407,9 +411,7 @@ static void FillView(lrb_scene *s) {
 	v.motionFirst = s->dMotionFirst;
 	v.motionLast = s->dMotionLast;
 	v.interps = s->dInterps;
-	v.nWide = (uint32_t)s->host.wide.size();
-	v.rootWide = s->host.rootWide;
-	v.twoLevel = s->host.twoLevel ? 1u : 0u;
+	FillRootOfView(s->host, &v);
 	s->info.n_ref_nodes = s->host.nRefNodes;
 	s->info.n_wide_nodes = (uint32_t)s->host.wide.size();
 	s->info.n_triangles = (uint32_t)s->host.tris.size();
@@ -617,6 +619,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.stats = s->dStats;
 	a.refillBelow = (uint32_t)dev->refillBelow;
 	a.triBias = (uint32_t)dev->triBias;
+	a.triDrain = (uint32_t)dev->triDrain;
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;
@@ -626,8 +629,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
-		if (two) rc = Occupancy(TracePersistent<true>, block, smemBytes, &bps);
-		else rc = Occupancy(TracePersistent<false>, block, smemBytes, &bps);
+		const bool spill = s->info.stack_need > (uint32_t)depth;
+		if (two) rc = spill ? Occupancy(TracePersistent<true, true>, block, smemBytes, &bps) : Occupancy(TracePersistent<true, false>, block, smemBytes, &bps);
+		else rc = spill ? Occupancy(TracePersistent<false, true>, block, smemBytes, &bps) : Occupancy(TracePersistent<false, false>, block, smemBytes, &bps);
 		if (rc != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
@@ -641,8 +645,13 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, sizeof(uint32_t), stream));
-		if (two) TracePersistent<true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
-		else TracePersistent<false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+		if (two) {
+			if (spill) TracePersistent<true, true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+			else TracePersistent<true, false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+		} else {
+			if (spill) TracePersistent<false, true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+			else TracePersistent<false, false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+		}
 	} else {
 		const int block = dev->blockThreads;
 		int bps = 0;

@@ -96,6 +96,12 @@ struct SceneView {
 	uint32_t nWide;                 // 0 => empty scene, every ray misses
 	uint32_t rootWide;              // wide index where traversal starts
 	uint32_t twoLevel;
+	// The top-level root box travels in the kernel parameters (constant bank): its test costs no
+	// memory access and rays that miss the scene never touch a node.  rootHasBox == 0 when the
+	// tree's root is itself a leaf (it has no box in the reference either).
+	uint32_t rootHasBox;
+	uint32_t rootChild;             // wide index of the real root node
+	float rootBox[6];               // min xyz, max xyz of the reference's node 0
 };
 
 }   // namespace lrb

@@ -268,6 +268,25 @@ static_assert(sizeof(OclInterp) == LRB_INTERPOLATED_TRANSFORM_SIZE, "ocl::Interp
 
 }   // namespace
 
+void FillRootOfView(const WideScene &w, SceneView *v) {
+	v->nWide = (uint32_t)w.wide.size();
+	v->rootWide = w.rootWide;
+	v->twoLevel = w.twoLevel ? 1u : 0u;
+	v->rootHasBox = 0;
+	v->rootChild = 0;
+	for (int i = 0; i < 6; ++i) v->rootBox[i] = 0.f;
+	if (w.wide.empty() || w.rootWide == kNullIndex)
+		return;
+	const WideNode &e = w.wide[w.rootWide];
+	// the one-child entry node ConvertTree puts in front of a tree whose root is an inner node
+	if (e.counts == 1u && e.next == kNullIndex) {
+		v->rootHasBox = 1;
+		v->rootChild = e.child[0];
+		v->rootBox[0] = e.bminx[0]; v->rootBox[1] = e.bminy[0]; v->rootBox[2] = e.bminz[0];
+		v->rootBox[3] = e.bmaxx[0]; v->rootBox[4] = e.bmaxy[0]; v->rootBox[5] = e.bmaxz[0];
+	}
+}
+
 void PackInterp(const void *src, DevInterp *d) {
 	OclInterp it;
 	memcpy(&it, src, sizeof(it));

@@ -48,6 +48,10 @@ void BuildWideMBVH(const lrb_mbvh_desc &desc, WideScene *out);
 void UpdateWideMBVHRoot(const lrb_bvh_node *rootNodes, uint32_t nRootNodes, const float *minv,
 		uint32_t nTransforms, WideScene *scene);
 
+// Fills nWide/rootWide/twoLevel/rootHasBox/rootChild/rootBox of a view from the host-side scene
+// (pointers are left to the caller).
+void FillRootOfView(const WideScene &scene, SceneView *view);
+
 // Re-pack one 576-byte ocl::InterpolatedTransform into a DevInterp.
 void PackInterp(const void *oclInterpolatedTransform, DevInterp *out);
 

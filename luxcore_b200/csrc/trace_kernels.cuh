@@ -22,8 +22,9 @@ namespace lrb {
 
 // ---- stacks ---------------------------------------------------------------------------------
 
-// Shared-memory column per thread + global spill.
-struct SmemStack {
+// Shared-memory column per thread + global spill (compiled out when the scene's worst-case stack
+// fits the shared depth, which the host knows at launch).
+template <bool SPILL> struct SmemStack {
 	uint32_t *sNode;        // &smemNodes[threadIdx.x], stride = blockDim.x
 	float *sT;
 	uint32_t *gNode;        // &spillNodes[globalThread], stride = totalThreads (may be NULL when no spill is needed)
@@ -33,7 +34,7 @@ struct SmemStack {
 	int sp;
 
 	__device__ __forceinline__ void push(uint32_t n, float t) {
-		if (sp < depthSmem) {
+		if (!SPILL || sp < depthSmem) {
 			sNode[sp * stride] = n;
 			sT[sp * stride] = t;
 		} else {
@@ -45,7 +46,7 @@ struct SmemStack {
 	}
 	__device__ __forceinline__ void pop(uint32_t &n, float &t) {
 		--sp;
-		if (sp < depthSmem) {
+		if (!SPILL || sp < depthSmem) {
 			n = sNode[sp * stride];
 			t = sT[sp * stride];
 		} else {
@@ -103,6 +104,7 @@ struct TraceArgs {
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
+	uint32_t triDrain;          // 1: a triangle phase tests every pending triangle of its lanes
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	TraceStats *stats;          // STATS kernels only
 };
@@ -128,14 +130,14 @@ __device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const Ray
 
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-template <bool TWO_LEVEL>
+template <bool TWO_LEVEL, bool SPILL>
 __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalThreads = gridDim.x * blockDim.x;
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 
-	SmemStack stk;
+	SmemStack<SPILL> stk;
 	stk.sNode = smem + threadIdx.x;
 	stk.sT = reinterpret_cast<float *>(smem + a.smemDepth * blockDim.x) + threadIdx.x;
 	stk.stride = blockDim.x;
@@ -199,13 +201,19 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 			const bool wantTri = active && s.pendCount != 0;
 			const bool wantNode = active && s.pendCount == 0;
 			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
-			const int nNode = __popc(__ballot_sync(0xffffffffu, wantNode));
+			const unsigned nodeMask = __ballot_sync(0xffffffffu, wantNode);
+			const int nNode = __popc(nodeMask);
 			if (nTri * (int)a.triBias >= nNode * 4) {
-				if (wantTri)
+				if (wantTri) {
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+					if (a.triDrain) {
+						while (s.pendCount)
+							TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+					}
+				}
 			} else {
 				if (wantNode) {
-					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
+					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr, nodeMask)) {
 						StoreHit(a.hits, rayIdx, s, rayMaxt);
 						active = false;
 					}

@@ -313,8 +313,17 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	s.curInstOrder = 0; s.curMeshOffset = 0;
 	s.pendBase = 0; s.pendCount = 0;
 	s.inInstance = false;
-	s.cur = sc.nWide ? sc.rootWide : kNullIndex;
-	return sc.nWide != 0;
+	if (!sc.nWide) {
+		s.cur = kNullIndex;
+		return false;
+	}
+	if (sc.rootHasBox) {
+		// root box test (bvhaccel.cpp:245-255 at currentNode == 0) straight from the parameters
+		const float d = ChildEntry(s, true, sc.rootBox[0], sc.rootBox[1], sc.rootBox[2], sc.rootBox[3], sc.rootBox[4], sc.rootBox[5]);
+		s.cur = (d < LRB_INF) ? sc.rootChild : kNullIndex;     // kNullIndex + empty stack => finished at the first step
+	} else
+		s.cur = sc.rootWide;
+	return true;
 }
 
 // Tests ONE pending leaf triangle of the last visited node.
@@ -349,13 +358,19 @@ LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
 // pending work for TriStep.  Returns false when the ray is finished.
 // STACK provides push(uint32_t node, float t0) / pop(uint32_t&, float&) / empty() / depth().
 template <bool TWO_LEVEL, bool STATS, class STACK>
-LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats,
+		const uint32_t convergeMask = 0) {
 	uint32_t cur = s.cur;
+	bool alive = true;
 	if (cur == kNullIndex) {
-		// pop until something is still worth visiting
+		// pop until something is still worth visiting.  No early return from inside this region:
+		// its only exit is the end of the loop, so the lanes that had nothing to pop and the lanes
+		// that popped meet again BEFORE the node fetch instead of running it one group at a time.
 		for (;;) {
-			if (stk.empty())
-				return false;
+			if (stk.empty()) {
+				alive = false;
+				break;
+			}
 			float t0;
 			stk.pop(cur, t0);
 			if (TWO_LEVEL) {
@@ -398,6 +413,13 @@ LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, 
 			break;
 		}
 	}
+#if defined(__CUDA_ARCH__)
+	if (convergeMask)
+		__syncwarp(convergeMask);
+#endif
+	if (!alive)
+		return false;
+	// a finished lane must not fetch: point it at a valid node? -- not needed, it returned above.
 
 	// ---- fetch the 128-byte node with four 256-bit loads ----
 	const char *np = reinterpret_cast<const char *>(sc.nodes + cur);

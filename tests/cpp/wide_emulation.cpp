@@ -37,9 +37,7 @@ static SceneView View(const WideScene &w) {
 	v.motionFirst = w.motionFirst.data();
 	v.motionLast = w.motionLast.data();
 	v.interps = w.interps.data();
-	v.nWide = (uint32_t)w.wide.size();
-	v.rootWide = w.rootWide;
-	v.twoLevel = w.twoLevel;
+	FillRootOfView(w, &v);
 	return v;
 }
 

@@ -42,10 +42,17 @@ def flattened_from_oracle(desc, osc):
     return np.concatenate(verts) if verts else np.zeros((0, 3), np.float32), np.asarray(offs, dtype=np.uint32)
 
 
-def compare_hits(got, ref, rays=None, brute_second=None, rel_tol=1e-5, what=""):
+TIE_EPS = 1e-5     # "two nearest hits within epsilon": |t1 - t2| <= TIE_EPS * max(1, t)   
+
+
+def compare_hits(got, ref, rays=None, second_t=None, rel_tol=1e-5, what=""):
     """Parity rule of BASELINE.json: hit/miss, meshIndex and triangleIndex bit-exact; t, b1, b2
-    within rel_tol relative (they are expected to be bit-identical for the single-level BVH).
-    Returns a dict of mismatch counts; raises AssertionError with a readable report otherwise."""
+    within rel_tol relative (they are expected to be bit-identical wherever the arithmetic is
+    identical).  When `second_t` (the second-nearest hit distance per ray, from the oracle's brute
+    force) is given, an index mismatch is tolerated for rays whose two nearest hits lie within
+    TIE_EPS in t -- the only exemption BASELINE.json allows; it is needed where libm and CUDA
+    sinf/acosf differ by an ulp (motion blur).  Returns a dict of counts; raises AssertionError with
+    a readable report otherwise."""
     got = np.asarray(got)
     ref = np.asarray(ref)
     assert got.shape == ref.shape
@@ -54,15 +61,26 @@ def compare_hits(got, ref, rays=None, brute_second=None, rel_tol=1e-5, what=""):
     bad = miss_g != miss_r
     both = ~miss_g & ~miss_r
     bad |= both & ((got["meshIndex"] != ref["meshIndex"]) | (got["triangleIndex"] != ref["triangleIndex"]))
+    n_tie_exempt = 0
+    if second_t is not None and bad.any():
+        with np.errstate(invalid="ignore"):
+            tref = np.where(miss_r, got["t"], ref["t"])
+            near = np.abs(second_t - tref) <= TIE_EPS * np.maximum(1.0, np.abs(tref))
+            # a hit/miss flip is a tie only when the single hit sits within eps of the ray's maxt/mint limits
+            exempt = bad & both & near & (np.abs(got["t"] - ref["t"]) <= TIE_EPS * np.maximum(1.0, np.abs(ref["t"])))
+        n_tie_exempt = int(exempt.sum())
+        bad &= ~exempt
+        both = both & ~exempt
 
     def close(a, b):
-        return np.abs(a - b) <= rel_tol * np.maximum(1.0, np.abs(b))
+        with np.errstate(invalid="ignore"):
+            return np.abs(a - b) <= rel_tol * np.maximum(1.0, np.abs(b))
     val_bad = both & ~bad & ~(close(got["t"], ref["t"]) & close(got["b1"], ref["b1"]) & close(got["b2"], ref["b2"]))
     miss_t_bad = miss_g & miss_r & (got["t"] != ref["t"]) & ~(np.isnan(got["t"]) & np.isnan(ref["t"]))
     exact = both & ~bad & (got["t"] == ref["t"]) & (got["b1"] == ref["b1"]) & (got["b2"] == ref["b2"])
     rep = {"n": int(got.shape[0]), "hits": int(both.sum()), "index_mismatch": int(bad.sum()),
            "value_mismatch": int(val_bad.sum()), "miss_t_mismatch": int(miss_t_bad.sum()),
-           "bit_exact_hits": int(exact.sum())}
+           "bit_exact_hits": int(exact.sum()), "tie_exempt": n_tie_exempt}
     if rep["index_mismatch"] or rep["value_mismatch"] or rep["miss_t_mismatch"]:
         idx = np.nonzero(bad | val_bad | miss_t_bad)[0][:8]
         lines = ["%s parity FAILED: %r" % (what, rep)]
@@ -70,6 +88,52 @@ def compare_hits(got, ref, rays=None, brute_second=None, rel_tol=1e-5, what=""):
             lines.append("  ray %d: got %r  ref %r%s" % (i, got[i], ref[i], ("  ray %r" % (rays[i],)) if rays is not None else ""))
         raise AssertionError("\n".join(lines))
     return rep
+
+
+def mbvh_arrays(desc, ombvh):
+    """The arrays MBVHKernel hands to lrb_mbvh_upload, taken from the oracle's MBVHAccel restatement."""
+    n = ombvh.leaf_count()
+    leaf_nodes = [ombvh.leaf_nodes(i) for i in range(n)]
+    leaf_verts = [desc.shapes[ombvh.leaf_mesh(i)][0] for i in range(n)]
+    table, interps = ombvh.motion_systems()
+    return {"root_nodes": ombvh.root_nodes(), "leaf_nodes": leaf_nodes, "leaf_verts": leaf_verts,
+            "transforms_minv": ombvh.transforms_minv(), "motion_table": table, "interps": interps}
+
+
+def fill_mbvh_desc(arr):
+    """-> (capi.MBVHDesc, keepalive list)"""
+    from luxcore_b200 import capi
+    root = np.ascontiguousarray(arr["root_nodes"])
+    ln = [np.ascontiguousarray(a) for a in arr["leaf_nodes"]]
+    lv = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in arr["leaf_verts"]]
+    n = len(ln)
+    d = capi.MBVHDesc()
+    d.root_nodes = root.ctypes.data
+    d.n_root_nodes = root.shape[0]
+    d.n_leaves = n
+    a1 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in ln])
+    a2 = (C.c_uint32 * max(n, 1))(*[a.shape[0] for a in ln])
+    a3 = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in lv])
+    a4 = (C.c_uint32 * max(n, 1))(*[a.shape[0] for a in lv])
+    d.leaf_nodes = C.cast(a1, C.POINTER(C.c_void_p))
+    d.leaf_n_nodes = C.cast(a2, C.POINTER(C.c_uint32))
+    d.leaf_vertices = C.cast(a3, C.POINTER(C.c_void_p))
+    d.leaf_n_vertices = C.cast(a4, C.POINTER(C.c_uint32))
+    keep = [root, ln, lv, a1, a2, a3, a4]
+    tm = np.ascontiguousarray(arr["transforms_minv"], dtype=np.float32).reshape(-1, 16)
+    if tm.shape[0]:
+        d.transforms_minv = tm.ctypes.data
+        d.n_transforms = tm.shape[0]
+        keep.append(tm)
+    mt = np.ascontiguousarray(arr["motion_table"], dtype=np.uint32).reshape(-1, 4)
+    if mt.shape[0]:
+        it = np.ascontiguousarray(arr["interps"], dtype=np.uint8)
+        d.motion_systems = mt.ctypes.data
+        d.n_motion_systems = mt.shape[0]
+        d.interpolated_transforms = it.ctypes.data
+        d.n_interpolated_transforms = it.shape[0] // 576
+        keep += [mt, it]
+    return d, keep
 
 
 class Emu:
@@ -115,6 +179,19 @@ class Emu:
         offs = np.ascontiguousarray(offs, dtype=np.uint32)
         return cls(cls.lib().emu_bvh_create(nodes.ctypes.data, nodes.shape[0], verts.ctypes.data, verts.shape[0],
                                             offs.ctypes.data, offs.shape[0]))
+
+    @classmethod
+    def mbvh(cls, arr):
+        d, keep = fill_mbvh_desc(arr)
+        e = cls(cls.lib().emu_mbvh_create(C.byref(d)))
+        del keep
+        return e
+
+    def update(self, root_nodes, minv):
+        root_nodes = np.ascontiguousarray(root_nodes)
+        minv = np.ascontiguousarray(minv, dtype=np.float32).reshape(-1, 16)
+        if self.lib().emu_mbvh_update(self.h, root_nodes.ctypes.data, root_nodes.shape[0], minv.ctypes.data, minv.shape[0]) != 0:
+            raise RuntimeError(self.lib().emu_last_error().decode())
 
     def __del__(self):
         if getattr(self, "h", None):

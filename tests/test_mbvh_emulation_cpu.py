@@ -1,0 +1,83 @@
+"""Two-level (MBVH) parity on the CPU: product re-layout + traversal body vs the oracle's
+MBVHAccel::Intersect restatement, on instanced and motion-blurred scenes."""
+import numpy as np
+import pytest
+
+import helpers as H
+import scene_zoo as Z
+from luxcore_b200 import rays as R, scenes as S
+from oracle import oracle as O
+
+
+def _rays(desc, n, seed, time_range=None):
+    lo, hi = desc.bbox()
+    pad = 0.1 * (hi - lo)
+    a = R.to_numpy_rays(R.uniform_rays(lo - pad, hi + pad, n, seed=seed, time_range=time_range))
+    side = int(np.sqrt(n))
+    b = R.to_numpy_rays(R.camera_rays(desc.cam, side, side, seed=seed + 1, time_range=time_range))
+    return np.concatenate([a, b])
+
+
+def _check(desc, tree_type, n, time_range=None, motion=False):
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=tree_type)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    rays = _rays(desc, n, 31, time_range)
+    ref, cnt = mb.intersect(rays, count=True)
+    got, st = emu.trace(rays, want_stats=True)
+    # instances: identical arithmetic -> bit-exact; motion: sinf/acosf may differ between libm and
+    # CUDA on the GPU, but the CPU emulation uses the same libm as the oracle
+    rep = H.compare_hits(got, ref, rays, what="%s k=%d" % (desc.name, tree_type))
+    assert rep["hits"] > 0.1 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    assert st["max_stack"] <= emu.info()["stack_need"]
+    if motion:
+        assert st["motion_samples"] > 0
+    # topology-free pin of the oracle itself
+    brute, second = osc.brute(rays[:3000], two_level=True, want_second=True)
+    with np.errstate(invalid="ignore"):
+        tie = np.abs(second - brute["t"]) <= 1e-5 * np.maximum(1.0, np.abs(brute["t"]))
+    r3 = ref[:3000]
+    same = (r3["meshIndex"] == brute["meshIndex"]) & ((r3["triangleIndex"] == brute["triangleIndex"]) | (brute["meshIndex"] == H.NULL))
+    assert (same | tie).all()
+    return rep
+
+
+@pytest.mark.parametrize("tree_type", [2, 4, 8])
+def test_instances_zoo(tree_type):
+    _check(Z.instances_scene(), tree_type, 15000)
+
+
+def test_motion_zoo():
+    _check(Z.motion_scene(), 4, 15000, time_range=(-0.1, 1.1), motion=True)
+
+
+def test_bigmonkey_instances():
+    _check(S.load_fixture("bigmonkey-instances"), 4, 20000)
+
+
+def test_bigmonkey_motion():
+    _check(S.load_fixture("bigmonkey-motion"), 4, 20000, time_range=(0.0, 1.0), motion=True)
+
+
+def test_lightinstances_subset():
+    _check(S.load_fixture("lightinstances", max_objects=300), 4, 20000)
+
+
+def test_mbvh_update_root_only():
+    desc = Z.instances_scene(12)
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    rays = _rays(desc, 8000, 41)
+    H.compare_hits(emu.trace(rays), mb.intersect(rays), rays, what="before update")
+    # move two instances (scene edit), Update() rebuilds only the root tree
+    inst = [i for i, m in enumerate(desc.meshes) if m.kind == S.INSTANCE]
+    for k, i in enumerate(inst[:2]):
+        m = Z.translate(1.5 * (k + 1), -2.0, 0.5) @ Z.rot_z(33.0 * (k + 1))
+        osc.set_instance_transform(i, m)
+    mb.update()
+    emu.update(mb.root_nodes(), mb.transforms_minv())
+    ref = mb.intersect(rays)
+    rep = H.compare_hits(emu.trace(rays), ref, rays, what="after update")
+    assert rep["bit_exact_hits"] == rep["hits"]
