@@ -45,12 +45,20 @@
 #define LRB_FMAX(a, b) fmaxf((a), (b))
 #define LRB_FMIN(a, b) fminf((a), (b))
 #define LRB_F2U(x) __float_as_uint(x)
+/* Slerp's sinf/acosf (quaternion.cpp:150-156): the reference gets glibc's results, which are the
+ * correctly rounded float in all but vanishingly rare cases.  CUDA's sinf/acosf are 1-2 ulp
+ * functions, enough to move b1/b2 of distant triangles past the 1e-5 tolerance, so the device
+ * evaluates them in double precision and rounds once (motion leaves only; not on the hot path). */
+#define LRB_SINF(x) ((float)sin((double)(x)))
+#define LRB_ACOSF(x) ((float)acos((double)(x)))
 #else
 #define LRB_INF __builtin_huge_valf()
 /* fmaxf/fminf semantics of the device (the non-NaN operand wins) */
 #define LRB_FMAX(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) > (b) ? (a) : (b))))
 #define LRB_FMIN(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) < (b) ? (a) : (b))))
 #define LRB_F2U(x) lrb::HostF2U(x)
+#define LRB_SINF(x) sinf(x)
+#define LRB_ACOSF(x) acosf(x)
 #define LRB_MUL(a, b) ((a) * (b))
 #define LRB_ADD(a, b) ((a) + (b))
 #define LRB_SUB(a, b) ((a) - (b))
@@ -236,10 +244,10 @@ LRB_HD void MotionSample(const SceneView &sc, uint32_t motionIndex, float time, 
 		cosPhi = LRB_MUL(cosPhi, sign);
 		float f1, f2;
 		if (LRB_SUB(1.f, cosPhi) > 1e-6f) {
-			const float phi = acosf(cosPhi);
-			const float sinPhi = sinf(phi);
-			f1 = LRB_DIV(sinf(LRB_MUL(LRB_SUB(1.f, le), phi)), sinPhi);
-			f2 = LRB_DIV(sinf(LRB_MUL(le, phi)), sinPhi);
+			const float phi = LRB_ACOSF(cosPhi);
+			const float sinPhi = LRB_SINF(phi);
+			f1 = LRB_DIV(LRB_SINF(LRB_MUL(LRB_SUB(1.f, le), phi)), sinPhi);
+			f2 = LRB_DIV(LRB_SINF(LRB_MUL(le, phi)), sinPhi);
 		} else {
 			f1 = LRB_SUB(1.f, le);
 			f2 = le;

@@ -97,7 +97,7 @@ def test_motion_scene_sah_trees():
         mb.set_leaf_nodes(i, s.mbvh_leaf_nodes(i))
     rays = _rays(desc, 200000, 95, time_range=(0.0, 1.0))
     _, second = osc.brute(rays, two_level=True, want_second=True)
-    rep = H.compare_hits(s.trace_host(rays), mb.intersect(rays), rays, second_t=second, what="host/motion/sah")
+    rep = H.compare_hits(s.trace_host(rays), mb.intersect(rays), rays, second_t=second, what="host/motion/sah", libm_outlier_frac=1e-4)
     assert rep["hits"] > 0 and rep["tie_exempt"] <= 1e-4 * rep["n"]
     s.stop()
     s.close()

@@ -62,9 +62,10 @@ def test_motion_within_tolerance(dev, which, n):
     got = scene.trace_host(rays)
     # CUDA sinf/acosf vs libm: t may move by an ulp, so index flips are tolerated only on near-ties
     _, second = osc.brute(rays, two_level=True, want_second=True)
-    rep = H.compare_hits(got, ref, rays, second_t=second, rel_tol=1e-5, what=which)
+    rep = H.compare_hits(got, ref, rays, second_t=second, rel_tol=1e-5, what=which, libm_outlier_frac=1e-4)
     assert rep["hits"] > 0.1 * rep["n"]
     assert rep["tie_exempt"] <= 1e-4 * rep["n"]
+    assert rep["bit_exact_hits"] >= 0.995 * rep["hits"]     # double-rounded sin/acos reproduce glibc almost always
     scene.free()
 
 
