@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--depth", type=int, default=2, help="bounce depth of the ray batch")
     ap.add_argument("--builder", default="EMBREE_BINNED_SAH")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "none"])
+    ap.add_argument("--chunks", type=int, default=8, help="pieces per batch for the overlapped gather")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="device option key=value")
@@ -180,7 +181,8 @@ def main():
     workload = "%s-%dM-bounce%d" % (args.scene, args.rays >> 20, args.depth) if args.rays >= (1 << 20) else "%s-%d-bounce%d" % (args.scene, args.rays, args.depth)
     config = {"workload": workload, "scene": "scenes/%s (fixture tests/golden/scenes/%s.npz)" % (args.scene, args.scene),
               "accelerator": "BVH", "builder": args.builder, "treetype": 4, "rays_per_batch_per_gpu": args.rays,
-              "ray_kind": "incoherent diffuse bounce, path depth %d" % args.depth, "parallelism": "replicated BVH, ray batches sharded x%d" % n_gpus,
+              "ray_kind": "incoherent diffuse bounce, path depth %d" % args.depth,
+              "parallelism": "replicated BVH, one %d-ray batch per GPU x%d, RayHit gathered on rank 0 (%s)" % (args.rays, n_gpus, args.gather if n_gpus > 1 else "n/a"),
               "l2_policy": "inputs larger than L2 (48 B x rays + 20 B x rays per step >> 126 MB)"}
 
     if args.impl == "reference":
@@ -220,18 +222,42 @@ def main():
     hits = torch.empty((n, 20), dtype=torch.uint8, device=device)
 
     # ---- multi-GPU: RayHit gather onto rank 0 ----
-    gathered = None
-    if world > 1 and args.gather != "none":
+    #   p2p  : rank 0 owns the gather buffer; the other ranks map it over NVLink (CUDA IPC) and
+    #          lrb_trace_gather pushes each traced chunk into it while the next chunk is traced
+    #   nccl : trace, then torch.distributed gather (the baseline way)
+    from luxcore_b200 import shard
+    dev_view = capi.Device.borrow(sess.native_device())
+    gather_mode = args.gather if world > 1 else "none"
+    gbuf_local, gbuf_peer, my_dst, glist = 0, 0, 0, None
+    if gather_mode == "p2p":
         import torch.distributed as dist
-        if args.gather == "nccl":
-            gathered = torch.empty((world * n, 20), dtype=torch.uint8, device=device) if rank == 0 else None
-            glist = [gathered[i * n:(i + 1) * n] for i in range(world)] if rank == 0 else None
+        if rank == 0:
+            gbuf_local = dev_view.alloc(world * n * 20)
+            handle = [dev_view.ipc_get_handle(gbuf_local)]
+        else:
+            handle = [None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank == 0:
+            my_dst = gbuf_local
+        else:
+            gbuf_peer = dev_view.ipc_open_handle(handle[0])
+            my_dst = gbuf_peer + rank * n * 20
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+    elif gather_mode == "nccl":
+        gathered = torch.empty((world * n, 20), dtype=torch.uint8, device=device) if rank == 0 else None
+        glist = [gathered[i * n:(i + 1) * n] for i in range(world)] if rank == 0 else None
 
     def step():
-        sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
-        if world > 1 and args.gather == "nccl":
+        if gather_mode == "p2p":
             import torch.distributed as dist
-            dist.gather(hits, glist, dst=0)
+            # rank 0 traces straight into its slice of the gather buffer (no copy at all)
+            scene.trace_gather(rays.data_ptr(), my_dst if rank == 0 else hits.data_ptr(), n, my_dst, args.chunks)
+            dist.all_reduce(flag)           # 4-byte "batch complete" signal, ordered after the pushes
+        else:
+            sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
+            if gather_mode == "nccl":
+                import torch.distributed as dist
+                dist.gather(hits, glist, dst=0)
 
     def barrier():
         if world > 1:
@@ -248,31 +274,44 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_start.record()
     for i in range(args.steps):
-        ev[i][0].record()
-        sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
-        ev[i][1].record()
-        if world > 1 and args.gather == "nccl":
-            import torch.distributed as dist
-            dist.gather(hits, glist, dst=0)
+        step()
     e_stop.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     c1 = sess.counters()
-    total_ms = e_start.elapsed_time(e_stop)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = shard.max_over_ranks(e_start.elapsed_time(e_stop), device)
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
-    launches = int(c1.trace_launches - c0.trace_launches)
+    launches = int(shard.sum_over_ranks(c1.trace_launches - c0.trace_launches, device)) if world > 1 else int(c1.trace_launches - c0.trace_launches)
+
+    # kernel-only time of one whole-batch launch (roofline numerator), measured live with CUDA events
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a_, b_ in kev:
+        a_.record()
+        sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
+        b_.record()
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in kev]))
+
+    # ---- gather verification (not timed): rank 0's buffer == every rank's local hits ----
+    gather_ok = None
+    if gather_mode in ("p2p", "nccl"):
+        import torch.distributed as dist
+        sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
+        torch.cuda.synchronize()
+        ref_all = shard.gather_hits(hits, dst=0, counts=[n] * world)
+        if rank == 0:
+            if gather_mode == "p2p":
+                got = np.empty(world * n * 20, dtype=np.uint8)
+                dev_view.d2h(got, gbuf_local, blocking=True)
+                gather_ok = bool(got.tobytes() == ref_all.cpu().numpy().tobytes())
+            else:
+                gather_ok = bool(torch.equal(gathered, ref_all))
+        del ref_all
 
     # ---- end to end: pinned host buffers in, pinned host buffers out, through the C ABI ----
     h_rays = torch.empty((n, 48), dtype=torch.uint8, pin_memory=True)
@@ -311,6 +350,8 @@ def main():
            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic rays (seeded, generated on the GPU) over the reference's kitchen scene geometry",
            "config": config, "gpu_launches": launches,
+           "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "verified": gather_ok,
+                      "bytes_per_step_into_rank0": (world - 1) * n * 20 if world > 1 else 0},
            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 20,
                    "api": "lrb_trace_host (C ABI, pinned host buffers, chunked copy/trace overlap)",
                    "plugin_sequence_mrays_per_s": round(n / plugin_s / 1e6, 2)}}
@@ -338,7 +379,7 @@ def main():
         alg = a_ref if a_ref is not None else a_impl
         achieved = alg * n / (kern_ms * 1e-3) / 1e9
         try:
-            l2_bw = capi.Device.measure_read_bandwidth(_DevView(sess.native_device()), 32 << 20, 20)
+            l2_bw = dev_view.measure_read_bandwidth(32 << 20, 20)
         except Exception:
             l2_bw = None
         out["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -359,18 +400,20 @@ def main():
                         "device_bytes": int(info.device_bytes), "host_build_s": round(build_s, 3)}
         print(json.dumps(out), flush=True)
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        if gbuf_peer:
+            dev_view.ipc_close_handle(gbuf_peer)
+        dist.barrier()
+        if gbuf_local:
+            dev_view.free(gbuf_local)
     sess.stop()
     sess.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-
-
-class _DevView:
-    """capi.Device method access on a borrowed native handle."""
-    def __init__(self, h):
-        import ctypes
-        self.h = ctypes.c_void_p(h)
 
 
 def run_reference(args, rank, world, config):

@@ -201,6 +201,24 @@ LRB_API int lrb_trace_host(lrb_scene *scene, const lrb_ray *rays, lrb_rayhit *hi
 LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
 		lrb_trace_stats_t *stats);
 
+/* ---- multi-GPU: RayHit gather over NVLink ------------------------------------------------- */
+/* The BVH is replicated and every GPU traces its own slice of the rays (one process per GPU); the
+ * only exchange of the path is collecting the RayHit slices in one buffer.  That buffer lives on
+ * one GPU, is exported with lrb_ipc_get_handle and opened (peer-mapped over NVLink) by the other
+ * processes with lrb_ipc_open_handle.  Handles are the 64 opaque bytes of cudaIpcMemHandle_t; the
+ * pointer must be the start of an allocation made by lrb_alloc. */
+#define LRB_IPC_HANDLE_BYTES 64
+LRB_API int lrb_ipc_get_handle(lrb_device *dev, void *devptr, unsigned char handle[LRB_IPC_HANDLE_BYTES]);
+LRB_API int lrb_ipc_open_handle(lrb_device *dev, const unsigned char handle[LRB_IPC_HANDLE_BYTES], void **devptr);
+LRB_API int lrb_ipc_close_handle(lrb_device *dev, void *devptr);
+/* Trace + gather, overlapped: the batch is cut into n_chunks pieces; as soon as a piece is traced
+ * its RayHit range is pushed to gather_dst_dev (this rank's slice of the gather buffer: local or
+ * peer-mapped memory) by the copy engine on a second stream while the next piece is being traced.
+ * hits_dev keeps the local copy; gather_dst_dev == hits_dev skips the push.  Asynchronous: later
+ * work on the device's stream is ordered after the last push. */
+LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
+		void *gather_dst_dev, uint32_t n_chunks);
+
 /* ---- diagnostics ----------------------------------------------------------------------- */
 LRB_API const char *lrb_last_error_string(void);
 LRB_API int lrb_get_counters(lrb_device *dev, lrb_counters *out);

@@ -31,6 +31,7 @@ EXPORTS = [
     "lrb_trace", "lrb_trace_host", "lrb_trace_stats",
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
+    "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather",
 ]
 
 
@@ -110,6 +111,10 @@ def lib():
             "lrb_reset_counters": (i32, [vp]),
             "lrb_version_string": (C.c_char_p, []),
             "lrb_measure_read_bandwidth": (i32, [vp, sz, i32, C.POINTER(C.c_double)]),
+            "lrb_ipc_get_handle": (i32, [vp, vp, C.c_char_p]),
+            "lrb_ipc_open_handle": (i32, [vp, C.c_char_p, pvp]),
+            "lrb_ipc_close_handle": (i32, [vp, vp]),
+            "lrb_trace_gather": (i32, [vp, vp, vp, u32, vp, u32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -140,16 +145,26 @@ def device_count():
 class Device:
     """One B200 behind the C ABI (the object CUDAIntersectionDevice wraps on the C++ side)."""
 
-    def __init__(self, ordinal=0):
-        h = C.c_void_p()
-        _check(lib().lrb_device_create(ordinal, C.byref(h)))
-        self.h = h
+    def __init__(self, ordinal=0, _borrow=None):
+        if _borrow is not None:
+            self.h = C.c_void_p(_borrow)
+            self.owned = False
+        else:
+            h = C.c_void_p()
+            _check(lib().lrb_device_create(ordinal, C.byref(h)))
+            self.h = h
+            self.owned = True
         self.ordinal = ordinal
 
+    @classmethod
+    def borrow(cls, native_handle):
+        """Wrap an lrb_device* owned by someone else (e.g. a hostapi.Session)."""
+        return cls(_borrow=native_handle)
+
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self.owned:
             lib().lrb_device_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -203,6 +218,20 @@ class Device:
 
     def reset_counters(self):
         _check(lib().lrb_reset_counters(self.h))
+
+    # ---- multi-GPU gather buffer sharing ----
+    def ipc_get_handle(self, devptr):
+        buf = C.create_string_buffer(64)
+        _check(lib().lrb_ipc_get_handle(self.h, C.c_void_p(devptr), buf))
+        return buf.raw
+
+    def ipc_open_handle(self, handle_bytes):
+        p = C.c_void_p()
+        _check(lib().lrb_ipc_open_handle(self.h, C.c_char_p(handle_bytes), C.byref(p)))
+        return p.value
+
+    def ipc_close_handle(self, devptr):
+        _check(lib().lrb_ipc_close_handle(self.h, C.c_void_p(devptr)))
 
     # ---- scenes ----
     def upload_bvh(self, nodes, verts, mesh_vertex_offsets):
@@ -301,6 +330,11 @@ class Scene:
 
     def trace_host_ptr(self, rays_hostptr, hits_hostptr, n, preload_hits=False):
         _check(lib().lrb_trace_host(self.h, C.c_void_p(rays_hostptr), C.c_void_p(hits_hostptr), n, 1 if preload_hits else 0))
+
+    def trace_gather(self, rays_devptr, hits_devptr, n, gather_dst_devptr, n_chunks=8):
+        """Trace + overlapped push of the RayHit slice into the (possibly peer-mapped) gather buffer."""
+        _check(lib().lrb_trace_gather(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n,
+                                      C.c_void_p(gather_dst_devptr), n_chunks))
 
     def trace_stats(self, rays_devptr, hits_devptr, n):
         st = TraceStats()

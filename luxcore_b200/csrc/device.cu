@@ -719,6 +719,78 @@ int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_
 	return LRB_OK;
 }
 
+int lrb_ipc_get_handle(lrb_device *dev, void *devptr, unsigned char handle[LRB_IPC_HANDLE_BYTES]) {
+	if (!devptr || !handle)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	LRB_SETDEV(dev);
+	static_assert(sizeof(cudaIpcMemHandle_t) == LRB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+	cudaIpcMemHandle_t h;
+	LRB_CUDA(cudaIpcGetMemHandle(&h, devptr));
+	memcpy(handle, &h, sizeof(h));
+	return LRB_OK;
+}
+
+int lrb_ipc_open_handle(lrb_device *dev, const unsigned char handle[LRB_IPC_HANDLE_BYTES], void **devptr) {
+	if (!devptr || !handle)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	*devptr = nullptr;
+	LRB_SETDEV(dev);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof(h));
+	// maps the exporter's allocation into this process and enables peer access from this device
+	LRB_CUDA(cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return LRB_OK;
+}
+
+int lrb_ipc_close_handle(lrb_device *dev, void *devptr) {
+	LRB_SETDEV(dev);
+	if (devptr)
+		LRB_CUDA(cudaIpcCloseMemHandle(devptr));
+	return LRB_OK;
+}
+
+int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, void *dst, uint32_t nChunks) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	if (n == 0)
+		return LRB_OK;
+	if (!rays || !hits || !dst)
+		return Fail(LRB_ERR_INVALID, "null buffer");
+	if (nChunks < 1) nChunks = 1;
+	if (nChunks > 1024) nChunks = 1024;
+	// chunk boundaries on multiples of 4 rays keep every RayHit range 16-byte aligned (4 x 20 B)
+	uint32_t per = ((n + nChunks - 1) / nChunks + 3u) & ~3u;
+	const bool push = dst != hits;
+	while (push && dev->events.size() < 2 * (size_t)nChunks + 2) {
+		cudaEvent_t e;
+		LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		dev->events.push_back(e);
+	}
+	uint32_t c = 0;
+	for (uint32_t first = 0; first < n; first += per, ++c) {
+		const uint32_t cnt = std::min(per, n - first);
+		const lrb_ray *r = (const lrb_ray *)rays + first;
+		lrb_rayhit *h = (lrb_rayhit *)hits + first;
+		const int rc = LaunchTrace(s, r, h, cnt, false, dev->stream);
+		if (rc != LRB_OK)
+			return rc;
+		if (push) {
+			cudaEvent_t traced = dev->events[2 * c];
+			LRB_CUDA(cudaEventRecord(traced, dev->stream));
+			LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, traced, 0));
+			LRB_CUDA(cudaMemcpyAsync((lrb_rayhit *)dst + first, h, (size_t)cnt * sizeof(lrb_rayhit), cudaMemcpyDefault, dev->copyOutStream));
+		}
+	}
+	if (push) {
+		cudaEvent_t done = dev->events[2 * (size_t)nChunks + 1];
+		LRB_CUDA(cudaEventRecord(done, dev->copyOutStream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, done, 0));
+	}
+	return LRB_OK;
+}
+
 // Host buffers in, host buffers out.  The batch is cut into chunks; chunk k+1 is copied in and
 // chunk k-1 copied out (separate streams, PCIe is full duplex) while chunk k is traced.
 int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, int preloadHits) {
