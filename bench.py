@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--depth", type=int, default=2, help="bounce depth of the ray batch")
     ap.add_argument("--builder", default="EMBREE_BINNED_SAH")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "none"])
-    ap.add_argument("--chunks", type=int, default=8, help="pieces per batch for the overlapped gather")
+    ap.add_argument("--chunks", type=int, default=0, help="0 = fused in-kernel push; >= 1 = launches per batch for the copy-engine push")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="device option key=value")

@@ -211,11 +211,15 @@ LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_d
 LRB_API int lrb_ipc_get_handle(lrb_device *dev, void *devptr, unsigned char handle[LRB_IPC_HANDLE_BYTES]);
 LRB_API int lrb_ipc_open_handle(lrb_device *dev, const unsigned char handle[LRB_IPC_HANDLE_BYTES], void **devptr);
 LRB_API int lrb_ipc_close_handle(lrb_device *dev, void *devptr);
-/* Trace + gather, overlapped: the batch is cut into n_chunks pieces; as soon as a piece is traced
- * its RayHit range is pushed to gather_dst_dev (this rank's slice of the gather buffer: local or
- * peer-mapped memory) by the copy engine on a second stream while the next piece is being traced.
- * hits_dev keeps the local copy; gather_dst_dev == hits_dev skips the push.  Asynchronous: later
- * work on the device's stream is ordered after the last push. */
+/* Trace + gather, overlapped.  gather_dst_dev is this rank's slice of the gather buffer (local or
+ * peer-mapped memory); hits_dev keeps the local copy; gather_dst_dev == hits_dev skips the push.
+ *   n_chunks == 0 (default): FUSED -- one persistent kernel traces and, as each run of 32 768 ray
+ *     indices is retired (release/acquire counters), a few copier warps of the same kernel stream
+ *     that RayHit range to gather_dst_dev with 16-byte stores over NVLink while the other warps keep
+ *     tracing.  No second launch, no copy engine, no NCCL.
+ *   n_chunks >= 1: the batch is cut into n_chunks launches; each traced piece is pushed by the copy
+ *     engine on a second stream while the next piece is traced.
+ * Asynchronous: later work on the device's stream is ordered after the last push. */
 LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
 		void *gather_dst_dev, uint32_t n_chunks);
 

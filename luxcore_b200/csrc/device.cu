@@ -59,6 +59,7 @@ struct lrb_device {
 	int refillBelow;
 	int triBias;
 	int triDrain;
+	int pushCopiers;                // copier warps of the fused trace + gather kernel
 	int hostChunk;                  // rays per chunk in lrb_trace_host
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
@@ -81,6 +82,8 @@ struct lrb_scene {
 	float *dSpillT;
 	size_t spillEntries;
 	TraceStats *dStats;
+	uint32_t *dChunkDone;           // fused push: retired-ray counters per chunk
+	size_t chunkDoneCap;
 	SceneView view;
 	lrb_scene_info info;
 };
@@ -152,6 +155,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->refillBelow = 20;
 	dev->triBias = 8;
 	dev->triDrain = 0;
+	dev->pushCopiers = 32;
 	dev->hostChunk = 1 << 20;
 	*out = dev;
 	return LRB_OK;
@@ -227,6 +231,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "tri_bias") {
 		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
 		dev->triBias = iv;
+	} else if (k == "push_copiers") {
+		if (iv < 1 || iv > 1024) return Fail(LRB_ERR_INVALID, "push_copiers out of range");
+		dev->pushCopiers = iv;
 	} else if (k == "tri_drain") {
 		dev->triDrain = iv ? 1 : 0;
 	} else if (k == "host_chunk") {
@@ -455,6 +462,7 @@ static lrb_scene *NewScene(lrb_device *dev) {
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
 	s->dStats = nullptr;
+	s->dChunkDone = nullptr; s->chunkDoneCap = 0;
 	memset(&s->view, 0, sizeof(s->view));
 	memset(&s->info, 0, sizeof(s->info));
 	return s;
@@ -470,7 +478,7 @@ int lrb_scene_free(lrb_scene *s) {
 	cudaStreamSynchronize(dev->stream);
 	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
-	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats);
+	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dChunkDone);
 	{
 		std::lock_guard<std::mutex> g(dev->mtx);
 		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, s->info.device_bytes);
@@ -600,7 +608,21 @@ static int EnsureSpill(lrb_scene *s, uint32_t residentDepth, int totalThreads) {
 	return LRB_OK;
 }
 
-static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream) {
+typedef void (*PersistentKernel)(const TraceArgs);
+
+static PersistentKernel PickPersistent(bool two, bool spill, bool push) {
+	if (two) {
+		if (spill) return push ? TracePersistent<true, true, true> : TracePersistent<true, true, false>;
+		return push ? TracePersistent<true, false, true> : TracePersistent<true, false, false>;
+	}
+	if (spill) return push ? TracePersistent<false, true, true> : TracePersistent<false, true, false>;
+	return push ? TracePersistent<false, false, true> : TracePersistent<false, false, false>;
+}
+
+static const uint32_t kPushChunkShift = 15;     // 32 768 rays = 640 KiB of RayHit per pushed chunk
+
+static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream,
+		lrb_rayhit *pushDst = nullptr) {
 	lrb_device *dev = s->dev;
 	if (n == 0)
 		return LRB_OK;
@@ -630,9 +652,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
-		if (two) rc = spill ? Occupancy(TracePersistent<true, true>, block, smemBytes, &bps) : Occupancy(TracePersistent<true, false>, block, smemBytes, &bps);
-		else rc = spill ? Occupancy(TracePersistent<false, true>, block, smemBytes, &bps) : Occupancy(TracePersistent<false, false>, block, smemBytes, &bps);
-		if (rc != LRB_OK) return rc;
+		const bool push = pushDst != nullptr;
+		PersistentKernel kernel = PickPersistent(two, spill, push);
+		if ((rc = Occupancy(kernel, block, smemBytes, &bps)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
 		if (dev->blocksPerSM > 0) bps = std::min(bps, dev->blocksPerSM);
@@ -645,13 +667,27 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, sizeof(uint32_t), stream));
-		if (two) {
-			if (spill) TracePersistent<true, true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
-			else TracePersistent<true, false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
-		} else {
-			if (spill) TracePersistent<false, true><<<(unsigned)grid, block, smemBytes, stream>>>(a);
-			else TracePersistent<false, false><<<(unsigned)grid, block, smemBytes, stream>>>(a);
+		if (push) {
+			// the copier warps must be co-resident with the tracers they wait for: the grid never
+			// exceeds sm * bps resident blocks, and a block needs at least two warps
+			if (block < 64 || grid < 2)
+				return Fail(LRB_ERR_INVALID, "fused push needs block_threads >= 64 and at least two blocks");
+			const size_t nChunks = ((size_t)n >> kPushChunkShift) + 1;
+			if (s->chunkDoneCap < nChunks) {
+				LRB_CUDA(cudaStreamSynchronize(stream));
+				cudaFree(s->dChunkDone);
+				s->dChunkDone = nullptr; s->chunkDoneCap = 0;
+				LRB_CUDA(cudaMalloc((void **)&s->dChunkDone, nChunks * sizeof(uint32_t)));
+				s->chunkDoneCap = nChunks;
+			}
+			LRB_CUDA(cudaMemsetAsync(s->dChunkDone, 0, nChunks * sizeof(uint32_t), stream));
+			a.pushDst = pushDst;
+			a.chunkDone = s->dChunkDone;
+			a.chunkShift = kPushChunkShift;
+			a.nCopiers = (uint32_t)std::min<long long>(dev->pushCopiers, grid / 2);
+			if (a.nCopiers < 1) a.nCopiers = 1;
 		}
+		kernel<<<(unsigned)grid, block, smemBytes, stream>>>(a);
 	} else {
 		const int block = dev->blockThreads;
 		int bps = 0;
@@ -758,7 +794,16 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 		return LRB_OK;
 	if (!rays || !hits || !dst)
 		return Fail(LRB_ERR_INVALID, "null buffer");
-	if (nChunks < 1) nChunks = 1;
+	if (nChunks == 0) {
+		// fused: ONE kernel traces and pushes completed 32 768-ray chunks to the gather buffer itself
+		if (dst == hits)
+			return LaunchTrace(s, rays, hits, n, false, dev->stream);
+		if (!dev->persistent)
+			return Fail(LRB_ERR_INVALID, "the fused trace + gather kernel is the persistent kernel");
+		if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0 || (reinterpret_cast<uintptr_t>(hits) & 15u) != 0)
+			return Fail(LRB_ERR_INVALID, "hit buffers must be 16-byte aligned for the fused push");
+		return LaunchTrace(s, rays, hits, n, false, dev->stream, (lrb_rayhit *)dst);
+	}
 	if (nChunks > 1024) nChunks = 1024;
 	// chunk boundaries on multiples of 4 rays keep every RayHit range 16-byte aligned (4 x 20 B)
 	uint32_t per = ((n + nChunks - 1) / nChunks + 3u) & ~3u;

@@ -107,6 +107,11 @@ struct TraceArgs {
 	uint32_t triDrain;          // 1: a triangle phase tests every pending triangle of its lanes
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	TraceStats *stats;          // STATS kernels only
+	// fused RayHit push (PUSH kernels): see TracePersistent
+	lrb_rayhit *pushDst;        // this rank's slice of the gather buffer (peer-mapped over NVLink)
+	uint32_t *chunkDone;        // retired-ray counters, one per chunk of (1 << chunkShift) rays (zeroed before launch)
+	uint32_t chunkShift;
+	uint32_t nCopiers;          // warp 0 of blocks [0, nCopiers) pushes completed chunks instead of tracing
 };
 
 __device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray &r) {
@@ -130,10 +135,63 @@ __device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const Ray
 
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-template <bool TWO_LEVEL, bool SPILL>
+// A retired ray (hit written, or masked) is counted into its chunk with RELEASE semantics, so a
+// copier warp that ACQUIRES the full count sees every RayHit of the chunk.
+template <bool PUSH>
+__device__ __forceinline__ void Retire(const TraceArgs &a, uint32_t idx) {
+	if (PUSH)
+		asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(a.chunkDone + (idx >> a.chunkShift)) : "memory");
+}
+
+// Copier warp of the fused trace + gather kernel: waits for chunks of the local RayHit buffer to
+// complete and streams them into the gather buffer on the destination GPU with 16-byte stores over
+// NVLink, while the other warps keep tracing.  Chunks complete roughly in index order because ray
+// indices are handed out in increasing order.
+__device__ __forceinline__ void CopierLoop(const TraceArgs &a, const uint32_t copier, const uint32_t lane) {
+	const uint32_t chunkRays = 1u << a.chunkShift;
+	const uint32_t nChunks = (a.rayCount + chunkRays - 1) >> a.chunkShift;
+	for (uint32_t c = copier; c < nChunks; c += a.nCopiers) {
+		const uint32_t first = c << a.chunkShift;
+		const uint32_t cnt = min(chunkRays, a.rayCount - first);
+		for (;;) {
+			uint32_t done;
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.chunkDone + c) : "memory");
+			if (done >= cnt)
+				break;
+			__nanosleep(512);
+		}
+		// 20-B records, chunk starts are multiples of 4 rays => 16-B aligned byte ranges
+		const size_t bytes = (size_t)cnt * sizeof(lrb_rayhit);
+		const uint4 *src = reinterpret_cast<const uint4 *>(a.hits + first);
+		uint4 *dst = reinterpret_cast<uint4 *>(a.pushDst + first);
+		const uint32_t nVec = (uint32_t)(bytes / 16);
+		uint32_t i = lane;
+		for (; i + 7 * 32 < nVec; i += 8 * 32) {
+			uint4 v[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + i + k * 32);    // L2 (written by other SMs)
+#pragma unroll
+			for (int k = 0; k < 8; ++k) dst[i + k * 32] = v[k];
+		}
+		for (; i < nVec; i += 32)
+			dst[i] = __ldcg(src + i);
+		// tail of a last chunk whose ray count is not a multiple of 4
+		const uint32_t tailWords = (uint32_t)((bytes - (size_t)nVec * 16) / 4);
+		if (lane < tailWords)
+			reinterpret_cast<uint32_t *>(dst + nVec)[lane] = __ldcg(reinterpret_cast<const uint32_t *>(src + nVec) + lane);
+	}
+}
+
+template <bool TWO_LEVEL, bool SPILL, bool PUSH>
 __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
+	if (PUSH) {
+		if ((threadIdx.x >> 5) == 0 && blockIdx.x < a.nCopiers) {
+			CopierLoop(a, blockIdx.x, lane);
+			return;
+		}
+	}
 	const uint32_t totalThreads = gridDim.x * blockDim.x;
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 
@@ -215,6 +273,7 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 				if (wantNode) {
 					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr, nodeMask)) {
 						StoreHit(a.hits, rayIdx, s, rayMaxt);
+						Retire<PUSH>(a, rayIdx);
 						active = false;
 					}
 				}

@@ -77,3 +77,39 @@ def test_masked_rays_leave_hits_untouched(dev):
     ref = bvh.intersect(rays)
     H.compare_hits(hits[~mask], ref[~mask], rays[~mask], what="masked")
     scene.free()
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 5])
+@pytest.mark.parametrize("n", [1000, 32768 * 3 + 1234, 500000])
+def test_trace_gather_pushes_every_hit(dev, chunks, n):
+    """lrb_trace_gather (fused in-kernel push for chunks == 0, copy-engine push otherwise): the gather
+    slice must end up byte-identical to the local RayHit buffer, including masked rays' records."""
+    desc = S.load_fixture("kitchen")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    rays = _rays_for(desc, n, seed=33)[:n]
+    mask = np.random.default_rng(1).random(n) < 0.1
+    rays["flags"][mask] = capi.RAY_FLAGS_MASKED
+    d_rays = dev.alloc(n * 48)
+    d_hits = dev.alloc(n * 20)
+    d_dst = dev.alloc(n * 20 + 64)
+    dev.h2d(d_rays, rays, blocking=True)
+    pre = np.full(n, 7, dtype=np.uint8).repeat(20)
+    dev.h2d(d_hits, pre, blocking=True)          # masked records keep this content
+    dev.h2d(d_dst, np.zeros(n * 20 + 64, np.uint8), blocking=True)
+    scene.trace_gather(d_rays, d_hits, n, d_dst, chunks)
+    dev.sync()
+    local = np.zeros(n, dtype=capi.HIT_DTYPE)
+    pushed = np.zeros(n * 20 + 64, dtype=np.uint8)
+    dev.d2h(local, d_hits)
+    dev.d2h(pushed, d_dst)
+    assert pushed[:n * 20].tobytes() == local.tobytes()
+    assert (pushed[n * 20:] == 0).all()          # nothing written past the slice
+    ref = bvh.intersect(rays)
+    H.compare_hits(local[~mask], ref[~mask], what="trace_gather")
+    assert (local.view(np.uint8).reshape(n, 20)[mask] == 7).all()
+    for p in (d_rays, d_hits, d_dst):
+        dev.free(p)
+    scene.free()
