@@ -65,6 +65,7 @@ struct lrb_device {
 	void *stageRays, *stageHits;
 	size_t stageRaysBytes, stageHitsBytes;
 	std::vector<cudaEvent_t> events;
+	uint32_t *pushWatch;            // watchdog word of the last fused push launch (checked by lrb_sync)
 };
 
 struct lrb_scene {
@@ -139,6 +140,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	memset(&dev->counters, 0, sizeof(dev->counters));
 	dev->stageRays = dev->stageHits = nullptr;
 	dev->stageRaysBytes = dev->stageHitsBytes = 0;
+	dev->pushWatch = nullptr;
 	cudaError_t e = cudaGetDeviceProperties(&dev->prop, ordinal);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->ownStream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->copyInStream, cudaStreamNonBlocking);
@@ -314,6 +316,14 @@ int lrb_flush(lrb_device *dev) {
 int lrb_sync(lrb_device *dev) {
 	LRB_SETDEV(dev);
 	LRB_CUDA(cudaStreamSynchronize(dev->stream));
+	// watchdog of the fused trace + gather kernel (see CopierLoop)
+	if (dev->pushWatch) {
+		uint32_t w = 0;
+		LRB_CUDA(cudaMemcpy(&w, dev->pushWatch, sizeof(w), cudaMemcpyDeviceToHost));
+		dev->pushWatch = nullptr;
+		if (w != 0)
+			return Fail(LRB_ERR_INTERNAL, "fused trace+gather kernel: a RayHit chunk never completed (watchdog)");
+	}
 	return LRB_OK;
 }
 
@@ -476,6 +486,8 @@ int lrb_scene_free(lrb_scene *s) {
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
 	cudaStreamSynchronize(dev->stream);
+	if (s->dCounter && dev->pushWatch == s->dCounter + 1)
+		dev->pushWatch = nullptr;
 	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
 	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dChunkDone);
@@ -666,8 +678,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		if ((rc = EnsureSpill(s, (uint32_t)depth, (int)grid * block)) != LRB_OK) return rc;
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
-		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, sizeof(uint32_t), stream));
+		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
 		if (push) {
+			dev->pushWatch = s->dCounter + 1;
 			// the copier warps must be co-resident with the tracers they wait for: the grid never
 			// exceeds sm * bps resident blocks, and a block needs at least two warps
 			if (block < 64 || grid < 2)

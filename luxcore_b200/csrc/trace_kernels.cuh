@@ -153,12 +153,19 @@ __device__ __forceinline__ void CopierLoop(const TraceArgs &a, const uint32_t co
 	for (uint32_t c = copier; c < nChunks; c += a.nCopiers) {
 		const uint32_t first = c << a.chunkShift;
 		const uint32_t cnt = min(chunkRays, a.rayCount - first);
-		for (;;) {
+		// bounded wait (~8 s): a chunk that never completes is a bug, not a reason to hang the GPU;
+		// the watchdog word is checked by the host at the next lrb_sync
+		bool ok = false;
+		for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
 			uint32_t done;
 			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.chunkDone + c) : "memory");
-			if (done >= cnt)
-				break;
+			if (done >= cnt) { ok = true; break; }
 			__nanosleep(512);
+		}
+		if (!ok) {
+			if (lane == 0)
+				atomicExch(a.counter + 1, 0xdeadu);
+			return;
 		}
 		// 20-B records, chunk starts are multiples of 4 rays => 16-B aligned byte ranges
 		const size_t bytes = (size_t)cnt * sizeof(lrb_rayhit);
@@ -236,6 +243,8 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 						} else
 							StoreHit(a.hits, idx, s, rayMaxt);  // empty scene: miss
 					}
+					if (!active)
+						Retire<PUSH>(a, idx);       // masked ray, or answered without traversal
 				}
 			}
 			if (base + (uint32_t)nIdle >= a.rayCount)
