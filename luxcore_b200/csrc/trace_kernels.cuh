@@ -135,12 +135,41 @@ __device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const Ray
 
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-// A retired ray (hit written, or masked) is counted into its chunk with RELEASE semantics, so a
-// copier warp that ACQUIRES the full count sees every RayHit of the chunk.
-template <bool PUSH>
-__device__ __forceinline__ void Retire(const TraceArgs &a, uint32_t idx) {
-	if (PUSH)
-		asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(a.chunkDone + (idx >> a.chunkShift)) : "memory");
+// Retired rays (hit written, or masked) are counted into their chunk of the local RayHit buffer.
+// Each lane accumulates (chunk, count) locally; the counts are published once per warp every few
+// re-fill rounds with RELEASE semantics (one MEMBAR.GPU for many rays: __syncwarp orders every
+// lane's RayHit stores before the leader's release), so a copier warp that ACQUIRES the full count
+// sees every RayHit of the chunk.
+struct RetireState {
+	uint32_t chunk, count;
+};
+
+__device__ __forceinline__ void RetireRay(const TraceArgs &a, RetireState &rs, const uint32_t idx) {
+	const uint32_t c = idx >> a.chunkShift;
+	if (rs.count && c != rs.chunk) {
+		// crossed a chunk boundary before the warp published: release this lane's own count now
+		asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.chunkDone + rs.chunk), "r"(rs.count) : "memory");
+		rs.count = 0;
+	}
+	rs.chunk = c;
+	rs.count += 1;
+}
+
+__device__ __forceinline__ void PublishRetired(const TraceArgs &a, const uint32_t lane, RetireState &rs) {
+	__syncwarp();
+	unsigned todo = __ballot_sync(0xffffffffu, rs.count != 0);
+	while (todo) {
+		const int src = __ffs(todo) - 1;
+		const uint32_t c = __shfl_sync(0xffffffffu, rs.chunk, src);
+		const bool mine = rs.count != 0 && rs.chunk == c;
+		const unsigned same = __ballot_sync(0xffffffffu, mine);
+		const uint32_t cnt = __reduce_add_sync(0xffffffffu, mine ? rs.count : 0u);
+		if ((int)lane == src)
+			asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.chunkDone + c), "r"(cnt) : "memory");
+		if (mine)
+			rs.count = 0;
+		todo &= ~same;
+	}
 }
 
 // Copier warp of the fused trace + gather kernel: waits for chunks of the local RayHit buffer to
@@ -156,11 +185,11 @@ __device__ __forceinline__ void CopierLoop(const TraceArgs &a, const uint32_t co
 		// bounded wait (~8 s): a chunk that never completes is a bug, not a reason to hang the GPU;
 		// the watchdog word is checked by the host at the next lrb_sync
 		bool ok = false;
-		for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+		for (uint32_t spin = 0; spin < (1u << 21); ++spin) {
 			uint32_t done;
 			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.chunkDone + c) : "memory");
 			if (done >= cnt) { ok = true; break; }
-			__nanosleep(512);
+			__nanosleep(4096);
 		}
 		if (!ok) {
 			if (lane == 0)
@@ -217,8 +246,15 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 	float rayMaxt = 0.f;
 	bool active = false;
 	bool exhausted = false;
+	RetireState rs;                 // PUSH: rays this lane retired since the last publication
+	rs.chunk = 0; rs.count = 0;
+	uint32_t round = 0;
 
 	for (;;) {
+		if (PUSH) {
+			if (exhausted || (++round & 3u) == 0)
+				PublishRetired(a, lane, rs);
+		}
 		// ---- re-fill idle lanes ----
 		const unsigned idle = __ballot_sync(0xffffffffu, !active);
 		if (!exhausted && idle) {
@@ -243,8 +279,8 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 						} else
 							StoreHit(a.hits, idx, s, rayMaxt);  // empty scene: miss
 					}
-					if (!active)
-						Retire<PUSH>(a, idx);       // masked ray, or answered without traversal
+					if (PUSH && !active)        // masked ray, or answered without traversal
+						RetireRay(a, rs, idx);
 				}
 			}
 			if (base + (uint32_t)nIdle >= a.rayCount)
@@ -252,8 +288,11 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 		}
 		unsigned live = __ballot_sync(0xffffffffu, active);
 		if (live == 0) {
-			if (exhausted)
+			if (exhausted) {
+				if (PUSH)
+					PublishRetired(a, lane, rs);    // e.g. trailing masked rays
 				break;
+			}
 			continue;
 		}
 
@@ -282,7 +321,8 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 				if (wantNode) {
 					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr, nodeMask)) {
 						StoreHit(a.hits, rayIdx, s, rayMaxt);
-						Retire<PUSH>(a, rayIdx);
+						if (PUSH)
+							RetireRay(a, rs, rayIdx);
 						active = false;
 					}
 				}
