@@ -156,7 +156,7 @@ LRB_API int lrb_device_get_props(lrb_device *dev, lrb_device_props *out);
  * NULL restores the device's own stream. */
 LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
 LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
-/* Tunables (strings): "kernel" = "persistent"|"simple", "block_threads", "blocks_per_sm", "smem_depth",
+/* Tunables (strings): "kernel" = "persistent"|"simple", "blocks_per_sm", "smem_depth",
  * "refill_below", "tri_bias", "host_chunk". */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
 

@@ -52,13 +52,11 @@ struct lrb_device {
 	std::mutex mtx;
 	std::unordered_map<void *, size_t> allocs;  // lrb_alloc bookkeeping (GetUsedMemory parity)
 	// options
-	int blockThreads;               // 64 or 128
 	int blocksPerSM;                // 0 = from occupancy
 	int persistent;                 // 1 = TracePersistent, 0 = TraceStatic
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
 	int triBias;
-	int triDrain;
 	int pushCopiers;                // copier warps of the fused trace + gather kernel
 	int hostChunk;                  // rays per chunk in lrb_trace_host
 	// staging for lrb_trace_host
@@ -150,13 +148,11 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 		return Fail(LRB_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(e));
 	}
 	dev->stream = dev->ownStream;
-	dev->blockThreads = 128;
 	dev->blocksPerSM = 0;
 	dev->persistent = 1;
 	dev->smemDepth = 12;
 	dev->refillBelow = 20;
 	dev->triBias = 8;
-	dev->triDrain = 0;
 	dev->pushCopiers = 32;
 	dev->hostChunk = 1 << 20;
 	*out = dev;
@@ -217,11 +213,7 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 		return LRB_OK;
 	}
 	const int iv = atoi(value);
-	if (k == "block_threads") {
-		if (iv != 32 && iv != 64 && iv != 96 && iv != 128)
-			return Fail(LRB_ERR_INVALID, "block_threads must be 32, 64, 96 or 128");
-		dev->blockThreads = iv;
-	} else if (k == "blocks_per_sm") {
+	if (k == "blocks_per_sm") {
 		if (iv < 0 || iv > 32) return Fail(LRB_ERR_INVALID, "blocks_per_sm out of range");
 		dev->blocksPerSM = iv;
 	} else if (k == "smem_depth") {
@@ -236,8 +228,6 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "push_copiers") {
 		if (iv < 1 || iv > 1024) return Fail(LRB_ERR_INVALID, "push_copiers out of range");
 		dev->pushCopiers = iv;
-	} else if (k == "tri_drain") {
-		dev->triDrain = iv ? 1 : 0;
 	} else if (k == "host_chunk") {
 		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
 		dev->hostChunk = iv;
@@ -653,13 +643,12 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.stats = s->dStats;
 	a.refillBelow = (uint32_t)dev->refillBelow;
 	a.triBias = (uint32_t)dev->triBias;
-	a.triDrain = (uint32_t)dev->triDrain;
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;
 
 	if (dev->persistent && !stats) {
-		const int block = dev->blockThreads;
+		const int block = kTraceBlock;
 		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
@@ -702,7 +691,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		}
 		kernel<<<(unsigned)grid, block, smemBytes, stream>>>(a);
 	} else {
-		const int block = dev->blockThreads;
+		const int block = kTraceBlock;
 		int bps = 0;
 		if (stats) {
 			if (two) rc = Occupancy(TraceStatic<true, true>, block, 0, &bps);

@@ -3,21 +3,31 @@
 // The reference traverses a depth-first skip-list of 32-byte BVHArrayNode records, one box or
 // one triangle per record, with 3 x 12-byte unaligned vertex gathers per leaf
 // (include/luxrays/accelerators/bvh.cl:136-217).  On upload we keep every reference box VALUE
-// and every triangle, but re-lay them out for 128-bit vector loads:
+// and every triangle, but re-lay them out for 256-bit vector loads:
 //
 //   WideNode  (128 B, 128-B aligned = one L2 line / four 32-B sectors)
 //     one per reference inner node (plus continuation nodes when a reference node has more than
-//     four inner children, i.e. accelerator.bvh.treetype = 8).  Holds the boxes of up to four
-//     INNER children in struct-of-arrays form (the boxes are copied bit-for-bit from the children's
-//     own BVHArrayNode records) and their wide-node indices, so one fetch replaces up to five
-//     dependent 32-B fetches of the reference walk.
+//     four children, i.e. accelerator.bvh.treetype = 8).  Holds, in struct-of-arrays form, one box
+//     and one reference per child:
+//       * inner child    : its own box, copied bit-for-bit from its BVHArrayNode record; the
+//                          reference is the child's wide-node index;
+//       * triangle leaf  : the triangle's build box -- bounds of the three vertices grown by
+//                          MachineEpsilon::E(bbox), the box BVHAccel::Init hands to the builders
+//                          (bvhaccel.cpp:116-122) and therefore a subset of the parent's box; the
+//                          reference is kTagTri | TriRecord index;
+//       * MBVH root leaf : an unbounded box (the reference enters every instance of a visited root
+//                          node, mbvhaccel.cpp:312); the reference is kTagInstance | InstRecord index;
+//       * unused slot    : the empty box (+inf, -inf) and kNullIndex.
+//     One fetch replaces up to five dependent 32-B fetches of the reference walk, and every child
+//     (node or triangle) is ordered near-to-far and culled by its entry distance.
 //   TriRecord (64 B, 64-B aligned = two 256-bit loads): the three vertices pre-gathered next to
-//     meshIndex / triangleIndex, one per reference triangle leaf; the leaf children of one node are
-//     contiguous.
+//     meshIndex / triangleIndex, one per reference triangle leaf.
 //   InstRecord (32 B): one per MBVH root leaf (bvhLeaf payload, bvhbuild_types.cl:33-37).
 //
-// Reference leaves carry no box of their own (bvhclassicbuild.cpp:196-214), so -- exactly like
-// the reference -- every leaf child of a visited node is tested without a box pre-test.
+// Reference leaves carry no box of their own in the array (bvhclassicbuild.cpp:196-214): the
+// reference tests every leaf child of a visited node.  The leaf box used here only skips triangle
+// tests that cannot succeed (a hit point lies on the triangle, i.e. >= 128 ulp / 1e-5 inside the
+// grown box), so results are unchanged; see DESIGN.md "leaf boxes".
 //
 // `order` fields record the position of the leaf in the reference's depth-first array.  The
 // reference keeps the FIRST hit in array order among hits with exactly equal t (strict `t <
@@ -33,17 +43,22 @@ namespace lrb {
 static const uint32_t kNullIndex = 0xffffffffu;
 static const uint32_t kWideSlots = 4;
 
-// stack entry tags (two-level traversal)
-static const uint32_t kTagInstance = 0x80000000u;   // entry = kTagInstance | instance record index
-static const uint32_t kStackSentinel = 0xffffffffu; // pop => leave the current instance
+// child / stack references: bits 31-30 give the kind
+static const uint32_t kTagTri = 0x40000000u;        // kTagTri | TriRecord index
+static const uint32_t kTagInstance = 0x80000000u;   // kTagInstance | InstRecord index
+static const uint32_t kRefIndexMask = 0x3fffffffu;
+static const uint32_t kStackSentinel = 0xfffffffeu; // pop => leave the current instance
+static const uint32_t kMaxRefIndex = 0x3ffffff0u;   // node / triangle / instance counts stay below this
+
+enum { kNodeEntry = 1 };    // WideNode::flags: one-child entry node carrying a tree's root box
 
 struct __attribute__((aligned(128))) WideNode {
-	float bminx[4], bminy[4], bminz[4];
-	float bmaxx[4], bmaxy[4], bmaxz[4];
-	uint32_t child[4];      // wide-node index of inner child k, k < nInner
-	uint32_t leafBase;      // first TriRecord (or InstRecord, in an MBVH root tree) of this node
-	uint32_t counts;        // bits 0-7 nInner, bits 8-31 nLeaf
+	float lox[4], loy[4], loz[4];
+	float hix[4], hiy[4], hiz[4];
+	uint32_t child[4];      // reference of slot k (wide index, kTagTri|i, kTagInstance|i) or kNullIndex
 	uint32_t next;          // continuation node holding further children, or kNullIndex
+	uint32_t nChild;        // used slots (host-side bookkeeping; the kernels test child != kNullIndex)
+	uint32_t flags;
 	uint32_t pad;
 };
 

@@ -7,7 +7,9 @@
 #include "relayout.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 
 namespace lrb {
@@ -101,6 +103,72 @@ static void FillInst(const TreeInput &in, uint32_t c, InstRecord *ir) {
 	ir->pad[0] = (*in.leafStackNeed)[nd.bvhLeaf.leafIndex];   // host-side bookkeeping only
 }
 
+// MachineEpsilon::E (include/luxrays/core/epsilon.h:48-86) with the default clamp 1e-5 .. 1e-1.
+static inline float EpsOf(float v) {
+	union { float f; uint32_t i; } mf;
+	mf.f = v;
+	mf.i += 0x80u;
+	const float e = fabsf(mf.f - v);
+	return e > 1e-5f ? (e < 1e-1f ? e : 1e-1f) : 1e-5f;
+}
+
+static const float kInfF = std::numeric_limits<float>::infinity();
+
+static void ClearNode(WideNode *w) {
+	memset(w, 0, sizeof(*w));
+	for (uint32_t k = 0; k < kWideSlots; ++k) {
+		w->lox[k] = w->loy[k] = w->loz[k] = kInfF;      // the empty box: no ray passes it
+		w->hix[k] = w->hiy[k] = w->hiz[k] = -kInfF;
+		w->child[k] = kNullIndex;
+	}
+	w->next = kNullIndex;
+}
+
+static void SetSlotBox(WideNode *w, uint32_t k, const float lo[3], const float hi[3]) {
+	w->lox[k] = lo[0]; w->loy[k] = lo[1]; w->loz[k] = lo[2];
+	w->hix[k] = hi[0]; w->hiy[k] = hi[1]; w->hiz[k] = hi[2];
+}
+
+// The box BVHAccel::Init gives the builders for one triangle (bvhaccel.cpp:116-122): bounds of the
+// three vertices, grown by MachineEpsilon::E of the bounds.
+static void TriBuildBox(const TriRecord &tr, float lo[3], float hi[3]) {
+	float e = 0.f;
+	for (int k = 0; k < 3; ++k) {
+		lo[k] = std::min(std::min(tr.p0[k], tr.p1[k]), tr.p2[k]);
+		hi[k] = std::max(std::max(tr.p0[k], tr.p1[k]), tr.p2[k]);
+		e = std::max(e, std::max(EpsOf(lo[k]), EpsOf(hi[k])));
+	}
+	for (int k = 0; k < 3; ++k) {
+		lo[k] -= e;
+		hi[k] += e;
+	}
+}
+
+// Fills slot k of `w` with reference child `c` (inner node, triangle leaf or MBVH root leaf).
+static void FillSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, WideNode *w, uint32_t k, WideScene *out) {
+	const lrb_bvh_node &ch = in.nodes[c];
+	if (!IsLeaf(ch.nodeData)) {
+		SetSlotBox(w, k, ch.bvhNode.bboxMin, ch.bvhNode.bboxMax);
+		w->child[k] = wideOf[c];
+	} else if (in.instLeaves) {
+		const float lo[3] = { -kInfF, -kInfF, -kInfF }, hi[3] = { kInfF, kInfF, kInfF };
+		SetSlotBox(w, k, lo, hi);
+		InstRecord ir;
+		FillInst(in, c, &ir);
+		w->child[k] = kTagInstance | (uint32_t)out->insts.size();
+		out->insts.push_back(ir);
+	} else {
+		TriRecord tr;
+		FillTri(in, c, &tr);
+		float lo[3], hi[3];
+		TriBuildBox(tr, lo, hi);
+		SetSlotBox(w, k, lo, hi);
+		w->child[k] = kTagTri | (uint32_t)out->tris.size();
+		out->tris.push_back(tr);
+	}
+	w->nChild = k + 1;
+}
+
 // Appends the wide form of one reference tree to `out`.  Returns the wide index of its root
 // (kNullIndex for an empty tree) and the tree's worst-case stack need.
 static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stackNeed) {
@@ -113,25 +181,15 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 
 	const uint32_t wideStart = (uint32_t)out->wide.size();
 	const lrb_bvh_node *nodes = in.nodes;
+	std::vector<uint32_t> wideOf(in.n, kNullIndex);
 
 	// The root itself is a leaf (one-triangle mesh / one-mesh dataset): wrap it in a node.
 	if (IsLeaf(nodes[0].nodeData)) {
 		WideNode w;
-		memset(&w, 0, sizeof(w));
-		w.next = kNullIndex;
-		w.counts = (1u << 8);
-		if (in.instLeaves) {
-			w.leafBase = (uint32_t)out->insts.size();
-			InstRecord ir;
-			FillInst(in, 0, &ir);
-			out->insts.push_back(ir);
+		ClearNode(&w);
+		FillSlot(in, wideOf, 0, &w, 0, out);
+		if (in.instLeaves)
 			*stackNeed = 1 + (*in.leafStackNeed)[nodes[0].bvhLeaf.leafIndex];
-		} else {
-			w.leafBase = (uint32_t)out->tris.size();
-			TriRecord tr;
-			FillTri(in, 0, &tr);
-			out->tris.push_back(tr);
-		}
 		out->wide.push_back(w);
 		return wideStart;
 	}
@@ -139,23 +197,24 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	// The reference tests the root's own box first (bvhaccel.cpp:245-255 with currentNode == 0);
 	// no parent holds that box, so a one-child entry node carries it.
 	// Pass 1: wide index of every inner reference node, in array order.
-	std::vector<uint32_t> wideOf(in.n, kNullIndex);
 	uint32_t nWide = 1;
 	uint64_t nLeafTotal = 0;
 	for (uint32_t i = 0; i < in.n; ++i) {
 		if (IsLeaf(nodes[i].nodeData))
 			continue;
 		const uint32_t end = Skip(nodes[i].nodeData);
-		uint32_t nInner = 0;
+		uint32_t nKids = 0;
 		for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData)) {
 			if (IsLeaf(nodes[c].nodeData)) ++nLeafTotal;
-			else ++nInner;
+			++nKids;
 		}
 		wideOf[i] = wideStart + nWide;
-		nWide += std::max<uint32_t>(1u, (nInner + kWideSlots - 1) / kWideSlots);
+		nWide += std::max<uint32_t>(1u, (nKids + kWideSlots - 1) / kWideSlots);
 	}
-	if ((uint64_t)wideStart + nWide >= 0x7fffffffu)
+	if ((uint64_t)wideStart + nWide >= kMaxRefIndex)
 		throw std::runtime_error("too many wide nodes");
+	if ((in.instLeaves ? out->insts.size() : out->tris.size()) + nLeafTotal >= kMaxRefIndex)
+		throw std::runtime_error("too many leaves");
 	out->wide.resize((size_t)wideStart + nWide);
 	if (in.instLeaves)
 		out->insts.reserve(out->insts.size() + nLeafTotal);
@@ -164,83 +223,52 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 
 	{
 		WideNode &e = out->wide[wideStart];
-		memset(&e, 0, sizeof(e));
-		const lrb_bvh_node &r = nodes[0];
-		e.bminx[0] = r.bvhNode.bboxMin[0]; e.bminy[0] = r.bvhNode.bboxMin[1]; e.bminz[0] = r.bvhNode.bboxMin[2];
-		e.bmaxx[0] = r.bvhNode.bboxMax[0]; e.bmaxy[0] = r.bvhNode.bboxMax[1]; e.bmaxz[0] = r.bvhNode.bboxMax[2];
+		ClearNode(&e);
+		SetSlotBox(&e, 0, nodes[0].bvhNode.bboxMin, nodes[0].bvhNode.bboxMax);
 		e.child[0] = wideOf[0];
-		e.counts = 1;
-		e.next = kNullIndex;
+		e.nChild = 1;
+		e.flags = kNodeEntry;
 	}
 
-	// Pass 2: fill.
-	std::vector<uint32_t> innerKids, leafKids;
+	// Pass 2: fill, children in reference order.
+	std::vector<uint32_t> kids;
 	for (uint32_t i = 0; i < in.n; ++i) {
 		if (IsLeaf(nodes[i].nodeData))
 			continue;
-		innerKids.clear();
-		leafKids.clear();
+		kids.clear();
 		const uint32_t end = Skip(nodes[i].nodeData);
-		for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData)) {
-			if (IsLeaf(nodes[c].nodeData)) leafKids.push_back(c);
-			else innerKids.push_back(c);
-		}
-		const uint32_t nW = std::max<uint32_t>(1u, ((uint32_t)innerKids.size() + kWideSlots - 1) / kWideSlots);
+		for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData))
+			kids.push_back(c);
+		const uint32_t nW = std::max<uint32_t>(1u, ((uint32_t)kids.size() + kWideSlots - 1) / kWideSlots);
 		for (uint32_t j = 0; j < nW; ++j) {
 			WideNode &w = out->wide[wideOf[i] + j];
-			memset(&w, 0, sizeof(w));
+			ClearNode(&w);
 			const uint32_t first = j * kWideSlots;
-			const uint32_t cnt = std::min<uint32_t>(kWideSlots, (uint32_t)innerKids.size() - std::min<uint32_t>((uint32_t)innerKids.size(), first));
-			for (uint32_t k = 0; k < cnt; ++k) {
-				const lrb_bvh_node &ch = nodes[innerKids[first + k]];
-				w.bminx[k] = ch.bvhNode.bboxMin[0]; w.bminy[k] = ch.bvhNode.bboxMin[1]; w.bminz[k] = ch.bvhNode.bboxMin[2];
-				w.bmaxx[k] = ch.bvhNode.bboxMax[0]; w.bmaxy[k] = ch.bvhNode.bboxMax[1]; w.bmaxz[k] = ch.bvhNode.bboxMax[2];
-				w.child[k] = wideOf[innerKids[first + k]];
-			}
-			w.counts = cnt;
+			const uint32_t cnt = std::min<uint32_t>(kWideSlots, (uint32_t)kids.size() - std::min<uint32_t>((uint32_t)kids.size(), first));
+			for (uint32_t k = 0; k < cnt; ++k)
+				FillSlot(in, wideOf, kids[first + k], &w, k, out);
 			w.next = (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex;
-			if (j == 0) {
-				w.counts |= ((uint32_t)leafKids.size() << 8);
-				if (in.instLeaves) {
-					w.leafBase = (uint32_t)out->insts.size();
-					for (size_t k = 0; k < leafKids.size(); ++k) {
-						InstRecord ir;
-						FillInst(in, leafKids[k], &ir);
-						out->insts.push_back(ir);
-					}
-				} else {
-					w.leafBase = (uint32_t)out->tris.size();
-					for (size_t k = 0; k < leafKids.size(); ++k) {
-						TriRecord tr;
-						FillTri(in, leafKids[k], &tr);
-						out->tris.push_back(tr);
-					}
-				}
-			}
 		}
 	}
 
 	// Worst-case live stack entries.  Children always have larger wide indices than their parent
-	// (depth-first pre-order), so one reverse sweep suffices.
-	//   D[w] = (entries pushed at w) - 1 + max over entries D[entry]
+	// (depth-first pre-order), so one reverse sweep suffices.  Visiting w pushes every entry but the
+	// one it continues with:  D[w] = (entries of w) - 1 + max over entries D[entry];  entering an
+	// instance first pushes the sentinel.
 	std::vector<uint32_t> D(nWide, 0);
 	for (uint32_t r = nWide; r-- > 0;) {
 		const WideNode &w = out->wide[wideStart + r];
-		const uint32_t nInner = w.counts & 0xffu;
-		const uint32_t nLeaf = w.counts >> 8;
-		uint32_t k = nInner + (w.next != kNullIndex ? 1u : 0u);
+		uint32_t k = w.nChild + (w.next != kNullIndex ? 1u : 0u);
 		uint32_t below = 0;
-		for (uint32_t c = 0; c < nInner; ++c)
-			below = std::max(below, D[w.child[c] - wideStart]);
+		for (uint32_t c = 0; c < w.nChild; ++c) {
+			const uint32_t ref = w.child[c];
+			if (ref & kTagInstance)
+				below = std::max(below, 1u + out->insts[ref & kRefIndexMask].pad[0]);
+			else if (!(ref & kTagTri))
+				below = std::max(below, D[ref - wideStart]);
+		}
 		if (w.next != kNullIndex)
 			below = std::max(below, D[w.next - wideStart]);
-		if (in.instLeaves) {
-			k += nLeaf;
-			for (uint32_t c = 0; c < nLeaf; ++c) {
-				const InstRecord &ir = out->insts[w.leafBase + c];
-				below = std::max(below, 1u + ir.pad[0]);
-			}
-		}
 		D[r] = (k > 0 ? k - 1 : 0) + below;
 	}
 	*stackNeed = D[0];
@@ -279,11 +307,11 @@ void FillRootOfView(const WideScene &w, SceneView *v) {
 		return;
 	const WideNode &e = w.wide[w.rootWide];
 	// the one-child entry node ConvertTree puts in front of a tree whose root is an inner node
-	if (e.counts == 1u && e.next == kNullIndex) {
+	if (e.flags & kNodeEntry) {
 		v->rootHasBox = 1;
 		v->rootChild = e.child[0];
-		v->rootBox[0] = e.bminx[0]; v->rootBox[1] = e.bminy[0]; v->rootBox[2] = e.bminz[0];
-		v->rootBox[3] = e.bmaxx[0]; v->rootBox[4] = e.bmaxy[0]; v->rootBox[5] = e.bmaxz[0];
+		v->rootBox[0] = e.lox[0]; v->rootBox[1] = e.loy[0]; v->rootBox[2] = e.loz[0];
+		v->rootBox[3] = e.hix[0]; v->rootBox[4] = e.hiy[0]; v->rootBox[5] = e.hiz[0];
 	}
 }
 

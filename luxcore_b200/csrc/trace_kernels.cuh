@@ -5,9 +5,11 @@
 // atomic counter; lanes whose ray finished are re-filled in bulk (one atomicAdd per warp, the
 // lanes' slots assigned with a ballot + popc prefix) as soon as the number of live lanes drops
 // under a threshold, so incoherent bounce rays do not leave a warp running with a handful of
-// lanes.  The traversal stack is a per-lane column in shared memory (bank = lane, conflict-free
-// at any mix of depths); entries beyond the shared depth spill to a global scratch column.
-// Nodes/triangles are fetched with 128-bit read-only loads (ld.global.nc.v4).
+// lanes.  Finished lanes keep their result in registers until that re-fill, where all of them
+// store their RayHit together.  The traversal stack is a per-lane column in shared memory
+// (bank = lane, conflict-free at any mix of depths); entries beyond the shared depth spill to a
+// global scratch column.  Nodes/triangles are fetched with 256-bit read-only loads
+// (ld.global.nc.v8.f32).
 //
 // TraceStatic: same per-ray code, static grid-stride assignment, stack in local memory.  Kept as
 // the "simple" variant for A/B measurements and as the instrumented (STATS) kernel.
@@ -20,43 +22,62 @@
 
 namespace lrb {
 
+static const int kTraceBlock = 128;     // threads per block of every trace kernel
+
 // ---- stacks ---------------------------------------------------------------------------------
 
 // Shared-memory column per thread + global spill (compiled out when the scene's worst-case stack
-// fits the shared depth, which the host knows at launch).
+// fits the shared depth, which the host knows at launch).  Entry i of thread t lives in words
+// [2 i * kTraceBlock + t] (reference) and [(2 i + 1) * kTraceBlock + t] (entry distance): both
+// stores of a push use one address register and every access is bank-conflict-free.
 template <bool SPILL> struct SmemStack {
-	uint32_t *sNode;        // &smemNodes[threadIdx.x], stride = blockDim.x
-	float *sT;
-	uint32_t *gNode;        // &spillNodes[globalThread], stride = totalThreads (may be NULL when no spill is needed)
+	uint32_t *base;         // &smem[threadIdx.x]
+	uint32_t *top;          // next free shared entry (== base + sp * 2 * kTraceBlock while sp <= depthSmem)
+	uint32_t *limit;        // base + depthSmem * 2 * kTraceBlock
+	uint32_t *gNode;        // &spillNodes[globalThread], stride = totalThreads (NULL when no spill is needed)
 	float *gT;
-	uint32_t stride, gStride;
-	int depthSmem;
-	int sp;
+	uint32_t gStride;
+	int over;               // SPILL: entries currently held in the global column
 
-	__device__ __forceinline__ void push(uint32_t n, float t) {
-		if (!SPILL || sp < depthSmem) {
-			sNode[sp * stride] = n;
-			sT[sp * stride] = t;
-		} else {
-			const size_t o = (size_t)(sp - depthSmem) * gStride;
-			gNode[o] = n;
-			gT[o] = t;
+	__device__ __forceinline__ void init(uint32_t *b, int depthSmem) { base = top = b; limit = b + depthSmem * (2 * kTraceBlock); over = 0; }
+	__device__ __forceinline__ void reset() { top = base; over = 0; }
+	__device__ __forceinline__ bool room(int n) const { return !SPILL || top + n * (2 * kTraceBlock) <= limit; }
+	__device__ __forceinline__ void pushFast(uint32_t n, float t) {
+		top[0] = n;
+		top[kTraceBlock] = __float_as_uint(t);
+		top += 2 * kTraceBlock;
+	}
+	__device__ __forceinline__ void pushFastIf(bool p, uint32_t n, float t) {
+		if (p) {
+			top[0] = n;
+			top[kTraceBlock] = __float_as_uint(t);
 		}
-		++sp;
+		top += p ? 2 * kTraceBlock : 0;
+	}
+	__device__ __forceinline__ void push(uint32_t n, float t) {
+		if (!SPILL || top < limit) {
+			pushFast(n, t);
+			return;
+		}
+		const size_t o = (size_t)over * gStride;
+		gNode[o] = n;
+		gT[o] = t;
+		++over;
 	}
 	__device__ __forceinline__ void pop(uint32_t &n, float &t) {
-		--sp;
-		if (!SPILL || sp < depthSmem) {
-			n = sNode[sp * stride];
-			t = sT[sp * stride];
-		} else {
-			const size_t o = (size_t)(sp - depthSmem) * gStride;
+		if (SPILL && over > 0) {
+			--over;
+			const size_t o = (size_t)over * gStride;
 			n = gNode[o];
 			t = gT[o];
+			return;
 		}
+		top -= 2 * kTraceBlock;
+		n = top[0];
+		t = __uint_as_float(top[kTraceBlock]);
 	}
-	__device__ __forceinline__ bool empty() const { return sp == 0; }
-	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
+	__device__ __forceinline__ bool empty() const { return top == base; }
+	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)((top - base) / (2 * kTraceBlock) + over); }
 };
 
 // Local-memory stack + global spill.
@@ -68,6 +89,9 @@ template <int CAP> struct LocalStack {
 	uint32_t gStride;
 	int sp;
 
+	__device__ __forceinline__ bool room(int) const { return false; }
+	__device__ __forceinline__ void pushFast(uint32_t n, float t) { push(n, t); }
+	__device__ __forceinline__ void pushFastIf(bool p, uint32_t n, float t) { if (p) push(n, t); }
 	__device__ __forceinline__ void push(uint32_t n, float t) {
 		if (sp < CAP) {
 			node[sp] = n;
@@ -104,7 +128,6 @@ struct TraceArgs {
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
-	uint32_t triDrain;          // 1: a triangle phase tests every pending triangle of its lanes
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	TraceStats *stats;          // STATS kernels only
 	// fused RayHit push (PUSH kernels): see TracePersistent
@@ -219,7 +242,7 @@ __device__ __forceinline__ void CopierLoop(const TraceArgs &a, const uint32_t co
 }
 
 template <bool TWO_LEVEL, bool SPILL, bool PUSH>
-__global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
 	if (PUSH) {
@@ -228,29 +251,33 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 			return;
 		}
 	}
-	const uint32_t totalThreads = gridDim.x * blockDim.x;
-	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t totalThreads = gridDim.x * kTraceBlock;
+	const uint32_t gtid = blockIdx.x * kTraceBlock + threadIdx.x;
 
 	SmemStack<SPILL> stk;
-	stk.sNode = smem + threadIdx.x;
-	stk.sT = reinterpret_cast<float *>(smem + a.smemDepth * blockDim.x) + threadIdx.x;
-	stk.stride = blockDim.x;
+	stk.init(smem + threadIdx.x, (int)a.smemDepth);
 	stk.gNode = a.spillNode ? a.spillNode + gtid : nullptr;
 	stk.gT = a.spillT ? a.spillT + gtid : nullptr;
 	stk.gStride = totalThreads;
-	stk.depthSmem = (int)a.smemDepth;
-	stk.sp = 0;
 
 	RayState s;
 	uint32_t rayIdx = 0;
 	float rayMaxt = 0.f;
-	bool active = false;
+	bool active = false;            // the lane holds a ray that is still being traversed
+	bool unsaved = false;           // the lane holds a finished ray whose RayHit is not stored yet
 	bool exhausted = false;
 	RetireState rs;                 // PUSH: rays this lane retired since the last publication
 	rs.chunk = 0; rs.count = 0;
 	uint32_t round = 0;
 
 	for (;;) {
+		// ---- finished lanes store their RayHit (all of them in the same instructions) ----
+		if (unsaved) {
+			StoreHit(a.hits, rayIdx, s, rayMaxt);
+			if (PUSH)
+				RetireRay(a, rs, rayIdx);
+			unsaved = false;
+		}
 		if (PUSH) {
 			if (exhausted || (++round & 3u) == 0)
 				PublishRetired(a, lane, rs);
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 						rayIdx = idx;
 						rayMaxt = r.maxt;
 						if (InitRay(a.sc, r, s)) {
-							stk.sp = 0;
+							stk.reset();
 							active = true;
 						} else
 							StoreHit(a.hits, idx, s, rayMaxt);  // empty scene: miss
@@ -286,8 +313,7 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 			if (base + (uint32_t)nIdle >= a.rayCount)
 				exhausted = true;
 		}
-		unsigned live = __ballot_sync(0xffffffffu, active);
-		if (live == 0) {
+		if (__ballot_sync(0xffffffffu, active) == 0) {
 			if (exhausted) {
 				if (PUSH)
 					PublishRetired(a, lane, rs);    // e.g. trailing masked rays
@@ -297,45 +323,41 @@ __global__ void __launch_bounds__(128) TracePersistent(const TraceArgs a) {
 		}
 
 		// ---- traverse until too few lanes are alive ----
-		// Every iteration the warp runs ONE of two branch-free phases, whichever has more lanes
-		// ready: a node phase (pop / fetch a 128-B node / four box tests / ordered push) or a
-		// triangle phase (one pending leaf triangle per lane).  A lane holding pending triangles
-		// waits for a triangle phase; batching the two kinds of work keeps lanes converged on
-		// incoherent rays instead of serialising "my node had leaves" against "mine had not".
+		// Every iteration first lets the lanes that ran out of work pop their stack (Resolve), then the
+		// warp runs ONE of two branch-free phases, whichever has more lanes ready: a node phase (fetch
+		// a 128-B node / four box tests / ordered push) or a triangle phase (one triangle per lane).
+		// A lane holding a triangle reference waits for a triangle phase; batching the two kinds of
+		// work keeps lanes converged on incoherent rays instead of serialising them against each other.
 		const int floorLanes = exhausted ? 1 : (int)a.refillBelow;
+		int nLive;
 		do {
-			const bool wantTri = active && s.pendCount != 0;
-			const bool wantNode = active && s.pendCount == 0;
-			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
-			const unsigned nodeMask = __ballot_sync(0xffffffffu, wantNode);
-			const int nNode = __popc(nodeMask);
-			if (nTri * (int)a.triBias >= nNode * 4) {
-				if (wantTri) {
-					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
-					if (a.triDrain) {
-						while (s.pendCount)
-							TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
-					}
-				}
-			} else {
-				if (wantNode) {
-					if (!NodeStep<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr, nodeMask)) {
-						StoreHit(a.hits, rayIdx, s, rayMaxt);
-						if (PUSH)
-							RetireRay(a, rs, rayIdx);
-						active = false;
-					}
+			if (active && NeedsResolve<TWO_LEVEL>(s.cur)) {
+				if (!Resolve<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
+					active = false;
+					unsaved = true;
 				}
 			}
-			live = __ballot_sync(0xffffffffu, active);
-		} while (__popc(live) >= floorLanes);
+			__syncwarp();
+			const bool wantTri = active && (s.cur & kTagTri) != 0;
+			const bool wantNode = active && (s.cur & kTagTri) == 0;
+			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
+			const int nNode = __popc(__ballot_sync(0xffffffffu, wantNode));
+			if (nTri * (int)a.triBias >= nNode * 4) {
+				if (wantTri)
+					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+			} else {
+				if (wantNode)
+					NodeStep<TWO_LEVEL, false>(a.sc, s, stk, nullptr);
+			}
+			nLive = nTri + nNode;
+		} while (nLive >= floorLanes);
 	}
 }
 
 // ---- static grid-stride kernel (simple variant + instrumented variant) -----------------------
 
 template <bool TWO_LEVEL, bool STATS>
-__global__ void __launch_bounds__(128) TraceStatic(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 	const uint32_t totalThreads = gridDim.x * blockDim.x;
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	LocalStack<32> stk;

@@ -114,8 +114,9 @@ struct RayState {
 	uint32_t hitMesh, hitTri;
 	uint32_t bestInst, bestTri;     // reference array order of the current best hit
 	uint32_t curInstOrder, curMeshOffset;
-	uint32_t cur;           // wide node to visit next, or kNullIndex when the stack must be popped
-	uint32_t pendBase, pendCount;   // leaf triangles of the last visited node still to be tested
+	// What to process next: a wide-node index, kTagTri | triangle, kTagInstance | instance,
+	// kStackSentinel, or kNullIndex when the stack must be popped (Resolve).
+	uint32_t cur;
 	bool inInstance;
 };
 
@@ -154,26 +155,29 @@ LRB_HD bool TriangleTest(const RayState &r, const float p0x, const float p0y, co
 	return hit;
 }
 
-// One slab of BBox::IntersectP (bbox.cpp:152-161).  The swap keeps the reference's exact semantics
-// (no swap when either value is NaN); the interval updates use max/min that ignore a NaN operand,
-// which is what the reference's `tNear > t0 ? tNear : t0` does for a non-NaN t0.
-LRB_HD void Slab(float lo, float hi, float o, float inv, float &t0, float &t1) {
-	const float a = LRB_MUL(LRB_SUB(lo, o), inv);
-	const float b = LRB_MUL(LRB_SUB(hi, o), inv);
-	const bool sw = a > b;
-	const float tNear = sw ? b : a;
-	const float tFar = sw ? a : b;
-	t0 = LRB_FMAX(t0, tNear);
-	t1 = LRB_FMIN(t1, tFar);
-}
-
-// Entry distance of one child box, or +inf when the ray misses it / the slot is unused.
-LRB_HD float ChildEntry(const RayState &s, bool used, float lox, float loy, float loz, float hix, float hiy, float hiz) {
-	float t0 = s.mint, t1 = s.maxt;
-	Slab(lox, hix, s.ox, s.ix, t0, t1);
-	Slab(loy, hiy, s.oy, s.iy, t0, t1);
-	Slab(loz, hiz, s.oz, s.iz, t0, t1);
-	return (used & !(t0 > t1)) ? t0 : LRB_INF;
+// BBox::IntersectP (bbox.cpp:147-165) for one child box, returning its entry distance, or +inf
+// when the ray misses it / the slot is unused.
+// The reference computes a = (lo - o) * inv, b = (hi - o) * inv and swaps when a > b.  lo <= hi, so
+// for finite values the swap happens exactly when inv < 0: picking the near / far plane by the sign
+// of inv yields the same two numbers with a select per plane instead of a compare + two selects.
+// When a product is NaN (0 * inf: origin on a slab plane, direction parallel to it) the reference
+// does not swap and its `>` / `<` updates ignore the NaN; here fmaxf / fminf ignore it as well, and
+// in the sub-cases where the two differ this form only ever PASSES a box the reference rejects
+// (never the opposite), which cannot change a result.
+// Unused slots hold the empty box (+inf, -inf): a ray with finite origin and at least one finite,
+// non-zero-reciprocal direction component gets t0 = +inf there.  Only rays made of NaN / inf can
+// "pass" an empty box; their kNullIndex reference is dropped by Resolve.
+LRB_HD float ChildEntry(const RayState &s, const bool nx, const bool ny, const bool nz,
+		const float lox, const float loy, const float loz, const float hix, const float hiy, const float hiz) {
+	const float tnx = LRB_MUL(LRB_SUB(nx ? hix : lox, s.ox), s.ix);
+	const float tny = LRB_MUL(LRB_SUB(ny ? hiy : loy, s.oy), s.iy);
+	const float tnz = LRB_MUL(LRB_SUB(nz ? hiz : loz, s.oz), s.iz);
+	const float tfx = LRB_MUL(LRB_SUB(nx ? lox : hix, s.ox), s.ix);
+	const float tfy = LRB_MUL(LRB_SUB(ny ? loy : hiy, s.oy), s.iy);
+	const float tfz = LRB_MUL(LRB_SUB(nz ? loz : hiz, s.oz), s.iz);
+	const float t0 = LRB_FMAX(LRB_FMAX(LRB_FMAX(tnx, tny), tnz), s.mint);
+	const float t1 = LRB_FMIN(LRB_FMIN(LRB_FMIN(tfx, tfy), tfz), s.maxt);
+	return !(t0 > t1) ? t0 : LRB_INF;
 }
 
 LRB_HD void SetRay(RayState &s, float ox, float oy, float oz, float dx, float dy, float dz) {
@@ -319,7 +323,6 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	s.hitMesh = kNullIndex; s.hitTri = kNullIndex;
 	s.bestInst = 0; s.bestTri = 0;
 	s.curInstOrder = 0; s.curMeshOffset = 0;
-	s.pendBase = 0; s.pendCount = 0;
 	s.inInstance = false;
 	if (!sc.nWide) {
 		s.cur = kNullIndex;
@@ -327,21 +330,99 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	}
 	if (sc.rootHasBox) {
 		// root box test (bvhaccel.cpp:245-255 at currentNode == 0) straight from the parameters
-		const float d = ChildEntry(s, true, sc.rootBox[0], sc.rootBox[1], sc.rootBox[2], sc.rootBox[3], sc.rootBox[4], sc.rootBox[5]);
-		s.cur = (d < LRB_INF) ? sc.rootChild : kNullIndex;     // kNullIndex + empty stack => finished at the first step
+		const float d = ChildEntry(s, s.ix < 0.f, s.iy < 0.f, s.iz < 0.f,
+				sc.rootBox[0], sc.rootBox[1], sc.rootBox[2], sc.rootBox[3], sc.rootBox[4], sc.rootBox[5]);
+		s.cur = (d < LRB_INF) ? sc.rootChild : kNullIndex;     // kNullIndex + empty stack => finished at the first Resolve
 	} else
 		s.cur = sc.rootWide;
 	return true;
 }
 
-// Tests ONE pending leaf triangle of the last visited node.
+// True when s.cur is neither a wide node nor a triangle: the ray needs Resolve before its next step.
+template <bool TWO_LEVEL>
+LRB_HD bool NeedsResolve(const uint32_t cur) {
+	return TWO_LEVEL ? (cur >= kTagInstance) : (cur == kNullIndex);
+}
+
+// Turns s.cur into a wide-node or triangle reference: pops the stack while there is nothing to do
+// or the popped entry lies behind the best hit, leaves (sentinel) and enters (instance reference)
+// leaf trees.  Returns false when the ray is finished.
+// STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n).
+template <bool TWO_LEVEL, bool STATS, class STACK>
+LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+	uint32_t cur = s.cur;
+	bool alive = true;
+	// single exit: lanes that finish and lanes that found work leave the loop together
+	for (;;) {
+		if (cur == kNullIndex) {
+			if (stk.empty()) {
+				alive = false;
+				break;
+			}
+			float t0;
+			stk.pop(cur, t0);
+			// entry distance recorded at push time; a closer hit found since then culls the entry
+			// (same effect as running the box test now: t0 > min(maxt, tFar)).  The sentinel is
+			// pushed with -inf and never culled.
+			if (t0 > s.maxt) {
+				cur = kNullIndex;
+				continue;
+			}
+		}
+		if (!TWO_LEVEL || cur < kTagInstance) {
+			if (!TWO_LEVEL && cur == kNullIndex)
+				continue;       // the reference of an empty slot (NaN / inf rays only)
+			break;
+		}
+		if (TWO_LEVEL) {
+			if (cur == kStackSentinel) {
+				// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283)
+				SetRay(s, worldRay.o[0], worldRay.o[1], worldRay.o[2], worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+				s.inInstance = false;
+				cur = kNullIndex;
+				continue;
+			}
+			if (cur == kNullIndex)
+				continue;           // the reference of an empty slot (NaN / inf rays only)
+			// enter a leaf tree (mbvhaccel.cpp:312-333)
+			const char *ip = reinterpret_cast<const char *>(&sc.insts[cur & kRefIndexMask]);
+			const uint4 ir = LRB_LDGU4(ip);
+			const uint4 ir2 = LRB_LDGU4(ip + 16);
+			if (STATS) stats->instances++;
+			if (ir.x == kNullIndex) {
+				cur = kNullIndex;       // empty leaf tree
+				continue;
+			}
+			if (ir.y != kNullIndex) {
+				TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
+						worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+			} else if (ir.z != kNullIndex) {
+				float m[16];
+				MotionSample(sc, ir.z, s.time, m);
+				if (STATS) stats->motionSamples++;
+				TransformRayLocal(s, m, worldRay.o[0], worldRay.o[1], worldRay.o[2],
+						worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+			}
+			s.curMeshOffset = ir.w;
+			s.curInstOrder = ir2.x;
+			s.inInstance = true;
+			stk.push(kStackSentinel, -LRB_INF);
+			cur = ir.x;
+			break;
+		}
+	}
+	s.cur = cur;
+	return alive;
+}
+
+// Tests the triangle s.cur refers to.
 //   accept: strictly closer, or exactly as close as the current hit but earlier in the reference's
 //   depth-first array (so a hit at exactly t == ray.maxt is rejected while nothing was hit yet,
 //   like the reference's `t < rayHit->t` against the initial rayHit->t = maxt).
 template <bool TWO_LEVEL, bool STATS>
 LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
-	s.pendCount -= 1;
-	const char *tp = reinterpret_cast<const char *>(sc.tris + (s.pendBase + s.pendCount));
+	const char *tp = reinterpret_cast<const char *>(sc.tris + (s.cur & kRefIndexMask));
+	s.cur = kNullIndex;
 	const F8 a = Ld256(tp), b = Ld256(tp + 32);    // p0 p1 p2.xy | p2.z mesh tri order pad
 	if (STATS) stats->triangles++;
 	float t, b1, b2;
@@ -361,107 +442,30 @@ LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
 	}
 }
 
-// Visits one wide node (popping the stack first when needed): box-tests its inner children,
-// orders them near-to-far, pushes all but the nearest, and records the node's leaf triangles as
-// pending work for TriStep.  Returns false when the ray is finished.
-// STACK provides push(uint32_t node, float t0) / pop(uint32_t&, float&) / empty() / depth().
+// Visits the wide node s.cur refers to: box-tests its four child slots (no branches), orders the
+// children near-to-far, continues with the nearest and pushes the others with their entry
+// distances.
 template <bool TWO_LEVEL, bool STATS, class STACK>
-LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats,
-		const uint32_t convergeMask = 0) {
-	uint32_t cur = s.cur;
-	bool alive = true;
-	if (cur == kNullIndex) {
-		// pop until something is still worth visiting.  No early return from inside this region:
-		// its only exit is the end of the loop, so the lanes that had nothing to pop and the lanes
-		// that popped meet again BEFORE the node fetch instead of running it one group at a time.
-		for (;;) {
-			if (stk.empty()) {
-				alive = false;
-				break;
-			}
-			float t0;
-			stk.pop(cur, t0);
-			if (TWO_LEVEL) {
-				if (cur == kStackSentinel) {
-					// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283)
-					SetRay(s, worldRay.o[0], worldRay.o[1], worldRay.o[2], worldRay.d[0], worldRay.d[1], worldRay.d[2]);
-					s.inInstance = false;
-					continue;
-				}
-				if (cur & kTagInstance) {
-					// enter a leaf tree (mbvhaccel.cpp:312-333)
-					const char *ip = reinterpret_cast<const char *>(&sc.insts[cur & ~kTagInstance]);
-					const uint4 ir = LRB_LDGU4(ip);
-					const uint4 ir2 = LRB_LDGU4(ip + 16);
-					if (STATS) stats->instances++;
-					if (ir.x == kNullIndex)
-						continue;       // empty leaf tree
-					if (ir.y != kNullIndex) {
-						TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-								worldRay.d[0], worldRay.d[1], worldRay.d[2]);
-					} else if (ir.z != kNullIndex) {
-						float m[16];
-						MotionSample(sc, ir.z, s.time, m);
-						if (STATS) stats->motionSamples++;
-						TransformRayLocal(s, m, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-								worldRay.d[0], worldRay.d[1], worldRay.d[2]);
-					}
-					s.curMeshOffset = ir.w;
-					s.curInstOrder = ir2.x;
-					s.inInstance = true;
-					stk.push(kStackSentinel, 0.f);
-					cur = ir.x;
-					break;
-				}
-			}
-			// entry distance recorded at push time; a closer hit found since then culls the node
-			// (same effect as running the box test now: t0 > min(maxt, tFar))
-			if (t0 > s.maxt)
-				continue;
-			break;
-		}
-	}
-#if defined(__CUDA_ARCH__)
-	if (convergeMask)
-		__syncwarp(convergeMask);
-#endif
-	if (!alive)
-		return false;
-	// a finished lane must not fetch: point it at a valid node? -- not needed, it returned above.
-
+LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	// ---- fetch the 128-byte node with four 256-bit loads ----
-	const char *np = reinterpret_cast<const char *>(sc.nodes + cur);
+	const char *np = reinterpret_cast<const char *>(sc.nodes + s.cur);
 	if (STATS) stats->wideNodes++;
-	const F8 A = Ld256(np);          // bminx[4] bminy[4]
-	const F8 B = Ld256(np + 32);     // bminz[4] bmaxx[4]
-	const F8 C = Ld256(np + 64);     // bmaxy[4] bmaxz[4]
-	const F8 D = Ld256(np + 96);     // child[4] leafBase counts next pad
-	const uint32_t counts = LRB_F2U(D.v[5]);
-	const uint32_t nInner = counts & 0xffu;
-	const uint32_t nLeaf = counts >> 8;
-	const uint32_t leafBase = LRB_F2U(D.v[4]);
-	const uint32_t next = LRB_F2U(D.v[6]);
+	const F8 A = Ld256(np);          // lox[4] loy[4]
+	const F8 B = Ld256(np + 32);     // loz[4] hix[4]
+	const F8 C = Ld256(np + 64);     // hiy[4] hiz[4]
+	const F8 D = Ld256(np + 96);     // child[4] next nChild flags pad
+	uint32_t c0 = LRB_F2U(D.v[0]), c1 = LRB_F2U(D.v[1]), c2 = LRB_F2U(D.v[2]), c3 = LRB_F2U(D.v[3]);
+	const uint32_t next = LRB_F2U(D.v[4]);
 
-	// ---- leaf children ----
-	if (TWO_LEVEL && !s.inInstance) {
-		// root tree: leaves are instances; they have no box of their own in the reference, so each
-		// one is entered (mbvhaccel.cpp:312).  Defer them through the stack.
-		for (uint32_t j = 0; j < nLeaf; ++j)
-			stk.push(kTagInstance | (leafBase + j), 0.f);
-	} else {
-		s.pendBase = leafBase;
-		s.pendCount = nLeaf;
-	}
-
-	// ---- inner children: box tests (all four slots, no branches), near-to-far ordering ----
-	const float kInf = LRB_INF;
-	float d0 = ChildEntry(s, nInner > 0, A.v[0], A.v[4], B.v[0], B.v[4], C.v[0], C.v[4]);
-	float d1 = ChildEntry(s, nInner > 1, A.v[1], A.v[5], B.v[1], B.v[5], C.v[1], C.v[5]);
-	float d2 = ChildEntry(s, nInner > 2, A.v[2], A.v[6], B.v[2], B.v[6], C.v[2], C.v[6]);
-	float d3 = ChildEntry(s, nInner > 3, A.v[3], A.v[7], B.v[3], B.v[7], C.v[3], C.v[7]);
+	// ---- box tests of all four slots, near-to-far ordering ----
 	// A box that passes with entry distance +inf (mint = maxt = +inf) cannot hold an acceptable hit:
 	// the triangle test rejects t > maxt and a tie at +inf never wins; "not hit" is exact.
-	uint32_t c0 = LRB_F2U(D.v[0]), c1 = LRB_F2U(D.v[1]), c2 = LRB_F2U(D.v[2]), c3 = LRB_F2U(D.v[3]);
+	const float kInf = LRB_INF;
+	const bool nx = s.ix < 0.f, ny = s.iy < 0.f, nz = s.iz < 0.f;
+	float d0 = ChildEntry(s, nx, ny, nz, A.v[0], A.v[4], B.v[0], B.v[4], C.v[0], C.v[4]);
+	float d1 = ChildEntry(s, nx, ny, nz, A.v[1], A.v[5], B.v[1], B.v[5], C.v[1], C.v[5]);
+	float d2 = ChildEntry(s, nx, ny, nz, A.v[2], A.v[6], B.v[2], B.v[6], C.v[2], C.v[6]);
+	float d3 = ChildEntry(s, nx, ny, nz, A.v[3], A.v[7], B.v[3], B.v[7], C.v[3], C.v[7]);
 
 	// sorting network on (distance, child), ascending, written with selects
 #define LRB_CSWAP(da, ca, db, cb) { const bool sw_ = db < da; const float lo_ = sw_ ? db : da, hi_ = sw_ ? da : db; \
@@ -473,25 +477,36 @@ LRB_HD bool NodeStep(const SceneView &sc, const lrb_ray &worldRay, RayState &s, 
 	LRB_CSWAP(d1, c1, d2, c2)
 #undef LRB_CSWAP
 
-	// continuation node (reference nodes with more than four inner children): always visited
-	if (next != kNullIndex)
-		stk.push(next, -kInf);
-	// push far-to-near, keep the nearest
-	if (d3 < kInf) stk.push(c3, d3);
-	if (d2 < kInf) stk.push(c2, d2);
-	if (d1 < kInf) stk.push(c1, d1);
+	// push far-to-near, continue with the nearest.  A continuation node (reference nodes with more
+	// than four children) is always visited.
+	const bool h1 = d1 < kInf, h2 = d2 < kInf, h3 = d3 < kInf;
+	if (stk.room(4)) {
+		if (next != kNullIndex) stk.pushFast(next, -kInf);
+		stk.pushFastIf(h3, c3, d3);
+		stk.pushFastIf(h2, c2, d2);
+		stk.pushFastIf(h1, c1, d1);
+	} else {
+		if (next != kNullIndex) stk.push(next, -kInf);
+		if (h3) stk.push(c3, d3);
+		if (h2) stk.push(c2, d2);
+		if (h1) stk.push(c1, d1);
+	}
 	s.cur = (d0 < kInf) ? c0 : kNullIndex;
 	if (STATS) { const unsigned long long d = stk.depth(); if (d > stats->maxStack) stats->maxStack = d; }
-	return true;
 }
 
-// One node visit followed by all of its triangle tests (static kernel, host emulation).
+// One unit of work for one ray: Resolve, then a node visit or a triangle test (static kernel, host
+// emulation).  Returns false when the ray is finished.
 template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
-	if (!NodeStep<TWO_LEVEL, STATS>(sc, worldRay, s, stk, stats))
-		return false;
-	while (s.pendCount)
+	if (NeedsResolve<TWO_LEVEL>(s.cur)) {
+		if (!Resolve<TWO_LEVEL, STATS>(sc, worldRay, s, stk, stats))
+			return false;
+	}
+	if (s.cur & kTagTri)
 		TriStep<TWO_LEVEL, STATS>(sc, s, stats);
+	else
+		NodeStep<TWO_LEVEL, STATS>(sc, s, stk, stats);
 	return true;
 }
 

@@ -20,6 +20,9 @@ struct HostStack {
 	std::vector<uint32_t> n;
 	std::vector<float> t;
 	void push(uint32_t a, float b) { n.push_back(a); t.push_back(b); }
+	bool room(int) const { return (n.size() & 1) == 0; }    // exercise both push paths
+	void pushFast(uint32_t a, float b) { push(a, b); }
+	void pushFastIf(bool p, uint32_t a, float b) { if (p) push(a, b); }
 	void pop(uint32_t &a, float &b) { a = n.back(); b = t.back(); n.pop_back(); t.pop_back(); }
 	bool empty() const { return n.empty(); }
 	unsigned long long depth() const { return n.size(); }
