@@ -6,6 +6,7 @@
 // (bvhaccelhw.cpp:259-268, mbvhaccelhw.cpp:468-507).  No NVRTC, no cuew, no OptiX.
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -58,6 +59,13 @@ struct lrb_device {
 	int refillBelow;
 	int triBias;
 	int pushCopiers;                // copier warps of the fused trace + gather kernel
+	int sortRays;                   // 1 = order the rays of a batch for coherence before tracing them
+	int sortBitsPerAxis;            // origin-cell resolution of the sort key
+	int sortMinRays;                // batches smaller than this are traced in index order
+	// scratch of the ray-ordering pre-pass (keys / indices, double-buffered, + CUB temp storage)
+	uint32_t *sortKeys[2], *sortVals[2];
+	void *sortTemp;
+	size_t sortCap, sortTempBytes;
 	int hostChunk;                  // rays per chunk in lrb_trace_host
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
@@ -150,10 +158,16 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->stream = dev->ownStream;
 	dev->blocksPerSM = 0;
 	dev->persistent = 1;
-	dev->smemDepth = 12;
-	dev->refillBelow = 20;
+	dev->smemDepth = 16;
+	dev->refillBelow = 24;
 	dev->triBias = 8;
 	dev->pushCopiers = 32;
+	dev->sortRays = 0;
+	dev->sortBitsPerAxis = 5;
+	dev->sortMinRays = 1 << 18;
+	dev->sortKeys[0] = dev->sortKeys[1] = dev->sortVals[0] = dev->sortVals[1] = nullptr;
+	dev->sortTemp = nullptr;
+	dev->sortCap = dev->sortTempBytes = 0;
 	dev->hostChunk = 1 << 20;
 	*out = dev;
 	return LRB_OK;
@@ -167,6 +181,8 @@ int lrb_device_destroy(lrb_device *dev) {
 	for (size_t i = 0; i < dev->events.size(); ++i) cudaEventDestroy(dev->events[i]);
 	if (dev->stageRays) cudaFree(dev->stageRays);
 	if (dev->stageHits) cudaFree(dev->stageHits);
+	cudaFree(dev->sortKeys[0]); cudaFree(dev->sortKeys[1]); cudaFree(dev->sortVals[0]); cudaFree(dev->sortVals[1]);
+	cudaFree(dev->sortTemp);
 	cudaStreamDestroy(dev->copyInStream);
 	cudaStreamDestroy(dev->copyOutStream);
 	cudaStreamDestroy(dev->ownStream);
@@ -228,6 +244,14 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "push_copiers") {
 		if (iv < 1 || iv > 1024) return Fail(LRB_ERR_INVALID, "push_copiers out of range");
 		dev->pushCopiers = iv;
+	} else if (k == "sort_rays") {
+		dev->sortRays = iv ? 1 : 0;
+	} else if (k == "sort_bits") {
+		if (iv < 1 || iv > 9) return Fail(LRB_ERR_INVALID, "sort_bits (per axis) must be 1..9");
+		dev->sortBitsPerAxis = iv;
+	} else if (k == "sort_min_rays") {
+		if (iv < 0) return Fail(LRB_ERR_INVALID, "sort_min_rays out of range");
+		dev->sortMinRays = iv;
 	} else if (k == "host_chunk") {
 		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
 		dev->hostChunk = iv;
@@ -612,6 +636,53 @@ static int EnsureSpill(lrb_scene *s, uint32_t residentDepth, int totalThreads) {
 
 typedef void (*PersistentKernel)(const TraceArgs);
 
+// Ray-ordering pre-pass: keys from origin cell + direction octant, LSD radix sort of (key, index).
+// Leaves the processing order in *perm (device memory owned by the device object).
+static int SortRays(lrb_scene *s, const void *rays, uint32_t n, cudaStream_t stream, const uint32_t **perm) {
+	lrb_device *dev = s->dev;
+	const int bits = dev->sortBitsPerAxis;
+	const int keyBits = 3 * bits + 3;
+	cub::DoubleBuffer<uint32_t> keys(dev->sortKeys[0], dev->sortKeys[1]), vals(dev->sortVals[0], dev->sortVals[1]);
+	if (dev->sortCap < n) {
+		LRB_CUDA(cudaStreamSynchronize(stream));
+		for (int i = 0; i < 2; ++i) {
+			cudaFree(dev->sortKeys[i]); cudaFree(dev->sortVals[i]);
+			dev->sortKeys[i] = dev->sortVals[i] = nullptr;
+		}
+		dev->sortCap = 0;
+		for (int i = 0; i < 2; ++i) {
+			LRB_CUDA(cudaMalloc((void **)&dev->sortKeys[i], (size_t)n * sizeof(uint32_t)));
+			LRB_CUDA(cudaMalloc((void **)&dev->sortVals[i], (size_t)n * sizeof(uint32_t)));
+		}
+		dev->sortCap = n;
+		keys = cub::DoubleBuffer<uint32_t>(dev->sortKeys[0], dev->sortKeys[1]);
+		vals = cub::DoubleBuffer<uint32_t>(dev->sortVals[0], dev->sortVals[1]);
+	}
+	size_t tempBytes = 0;
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, vals, (int)n, 0, keyBits, stream));
+	if (dev->sortTempBytes < tempBytes) {
+		LRB_CUDA(cudaStreamSynchronize(stream));
+		cudaFree(dev->sortTemp);
+		dev->sortTemp = nullptr; dev->sortTempBytes = 0;
+		LRB_CUDA(cudaMalloc(&dev->sortTemp, tempBytes));
+		dev->sortTempBytes = tempBytes;
+	}
+	const float *rb = s->view.rootBox;
+	const float cells = (float)(1u << bits);
+	float sc[3];
+	for (int k = 0; k < 3; ++k) {
+		const float ext = rb[3 + k] - rb[k];
+		sc[k] = (ext > 0.f && ext < 3e38f) ? cells / ext : 0.f;
+	}
+	RayKeyKernel<<<(n + 255) / 256, 256, 0, stream>>>((const lrb_ray *)rays, n, rb[0], rb[1], rb[2], sc[0], sc[1], sc[2],
+			(uint32_t)bits, keys.Current(), vals.Current());
+	LRB_CUDA(cudaGetLastError());
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(dev->sortTemp, tempBytes, keys, vals, (int)n, 0, keyBits, stream));
+	*perm = vals.Current();
+	dev->counters.kernel_launches += 1 + (keyBits + 7) / 8 + 1;
+	return LRB_OK;
+}
+
 static PersistentKernel PickPersistent(bool two, bool spill, bool push) {
 	if (two) {
 		if (spill) return push ? TracePersistent<true, true, true> : TracePersistent<true, true, false>;
@@ -668,6 +739,10 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
+		// optional coherence pre-pass (not with the fused push, whose chunks must complete in index order)
+		if (dev->sortRays && !push && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
+			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
+		}
 		if (push) {
 			dev->pushWatch = s->dCounter + 1;
 			// the copier warps must be co-resident with the tracers they wait for: the grid never

@@ -5,21 +5,22 @@
 // (include/luxrays/accelerators/bvh.cl:136-217).  On upload we keep every reference box VALUE
 // and every triangle, but re-lay them out for 256-bit vector loads:
 //
-//   WideNode  (128 B, 128-B aligned = one L2 line / four 32-B sectors)
+//   WideNode  (64 B, 64-B aligned = two 32-B sectors, two 256-bit loads)
 //     one per reference inner node (plus continuation nodes when a reference node has more than
-//     four children, i.e. accelerator.bvh.treetype = 8).  Holds, in struct-of-arrays form, one box
-//     and one reference per child:
-//       * inner child    : its own box, copied bit-for-bit from its BVHArrayNode record; the
-//                          reference is the child's wide-node index;
+//     four children, i.e. accelerator.bvh.treetype = 8).  Holds one box and one reference per child:
+//       * inner child    : its own box from its BVHArrayNode record; reference = wide-node index;
 //       * triangle leaf  : the triangle's build box -- bounds of the three vertices grown by
 //                          MachineEpsilon::E(bbox), the box BVHAccel::Init hands to the builders
-//                          (bvhaccel.cpp:116-122) and therefore a subset of the parent's box; the
-//                          reference is kTagTri | TriRecord index;
-//       * MBVH root leaf : an unbounded box (the reference enters every instance of a visited root
-//                          node, mbvhaccel.cpp:312); the reference is kTagInstance | InstRecord index;
-//       * unused slot    : the empty box (+inf, -inf) and kNullIndex.
-//     One fetch replaces up to five dependent 32-B fetches of the reference walk, and every child
-//     (node or triangle) is ordered near-to-far and culled by its entry distance.
+//                          (bvhaccel.cpp:116-122); reference = kTagTri | TriRecord index;
+//       * MBVH root leaf : the whole grid of the node (the reference enters every instance of a
+//                          visited root node, mbvhaccel.cpp:312); reference = kTagInstance | index;
+//       * unused slot    : an inverted box (lo = 255, hi = 0) and kNullIndex.
+//     The four boxes are stored on a per-node grid: origin = min corner of the union of the slot
+//     boxes, one power-of-two step per axis, 8 bits per plane, lo rounded down and hi rounded up,
+//     so every stored box CONTAINS the reference's float box (a box test here passes whenever the
+//     reference's passes, up to the rounding discussed in traverse.h; boxes only cull, they never
+//     decide a result).  One 64-B fetch replaces up to five dependent 32-B fetches of the reference
+//     walk, and every child (node or triangle) is ordered near-to-far and culled by entry distance.
 //   TriRecord (64 B, 64-B aligned = two 256-bit loads): the three vertices pre-gathered next to
 //     meshIndex / triangleIndex, one per reference triangle leaf.
 //   InstRecord (32 B): one per MBVH root leaf (bvhLeaf payload, bvhbuild_types.cl:33-37).
@@ -52,15 +53,16 @@ static const uint32_t kMaxRefIndex = 0x3ffffff0u;   // node / triangle / instanc
 
 enum { kNodeEntry = 1 };    // WideNode::flags: one-child entry node carrying a tree's root box
 
-struct __attribute__((aligned(128))) WideNode {
-	float lox[4], loy[4], loz[4];
-	float hix[4], hiy[4], hiz[4];
+struct __attribute__((aligned(64))) WideNode {
+	float org[3];           // grid origin
+	uint32_t exps;          // bytes 0-2: biased exponent byte of (step_axis * 2^15); byte 3: used slots
 	uint32_t child[4];      // reference of slot k (wide index, kTagTri|i, kTagInstance|i) or kNullIndex
+	uint32_t qlo[3];        // x, y, z: byte k = lower plane of slot k in grid steps
+	uint32_t qhi[3];        // x, y, z: byte k = upper plane of slot k in grid steps
 	uint32_t next;          // continuation node holding further children, or kNullIndex
-	uint32_t nChild;        // used slots (host-side bookkeeping; the kernels test child != kNullIndex)
 	uint32_t flags;
-	uint32_t pad;
 };
+static const int kGridShift = 15;   // plane byte q sits in bits 8-15 of a float mantissa: 1 + q * 2^-15
 
 struct __attribute__((aligned(64))) TriRecord {
 	float p0[3], p1[3], p2[3];
@@ -94,7 +96,7 @@ enum {
 	kItTX = 16, kItTY = 32, kItTZ = 64
 };
 
-static_assert(sizeof(WideNode) == 128, "WideNode");
+static_assert(sizeof(WideNode) == 64, "WideNode");
 static_assert(sizeof(TriRecord) == 64, "TriRecord");
 static_assert(sizeof(InstRecord) == 32, "InstRecord");
 static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
@@ -117,6 +119,9 @@ struct SceneView {
 	uint32_t rootHasBox;
 	uint32_t rootChild;             // wide index of the real root node
 	float rootBox[6];               // min xyz, max xyz of the reference's node 0
+	// 0x3f800000 (1.0f).  Read from the parameter bank so that the plane decode's PRMT keeps its byte
+	// selector as the immediate operand (with a literal constant ptxas moves the selectors to registers).
+	uint32_t oneBits;
 };
 
 }   // namespace lrb

@@ -114,19 +114,109 @@ static inline float EpsOf(float v) {
 
 static const float kInfF = std::numeric_limits<float>::infinity();
 
-static void ClearNode(WideNode *w) {
-	memset(w, 0, sizeof(*w));
-	for (uint32_t k = 0; k < kWideSlots; ++k) {
-		w->lox[k] = w->loy[k] = w->loz[k] = kInfF;      // the empty box: no ray passes it
-		w->hix[k] = w->hiy[k] = w->hiz[k] = -kInfF;
-		w->child[k] = kNullIndex;
-	}
-	w->next = kNullIndex;
-}
+// Float boxes of the slots of one wide node, before they are put on the node's grid.
+struct SlotBoxes {
+	float lo[kWideSlots][3], hi[kWideSlots][3];
+	bool whole[kWideSlots];         // MBVH root leaf: the slot covers the whole grid
+	uint32_t child[kWideSlots];
+	uint32_t n;
+	bool hasOwn;                    // the node's own reference box (bounds every child, instances included)
+	float ownLo[3], ownHi[3];
+	SlotBoxes() : n(0), hasOwn(false) {}
+};
 
-static void SetSlotBox(WideNode *w, uint32_t k, const float lo[3], const float hi[3]) {
-	w->lox[k] = lo[0]; w->loy[k] = lo[1]; w->loz[k] = lo[2];
-	w->hix[k] = hi[0]; w->hiy[k] = hi[1]; w->hiz[k] = hi[2];
+static inline uint32_t NodeSlots(const WideNode &w) { return w.exps >> 24; }
+
+// Puts the slot boxes on the node's grid (layout.h): origin = min corner of everything the node
+// bounds, power-of-two step per axis, lower planes rounded down and upper planes rounded up with a
+// 1/64-step margin (the kernel's decode error is below 2^-9 step, traverse.h).
+static void QuantizeNode(const SlotBoxes &b, uint32_t next, uint32_t flags, WideNode *w) {
+	memset(w, 0, sizeof(*w));
+	w->next = next;
+	w->flags = flags;
+	for (uint32_t k = 0; k < kWideSlots; ++k)
+		w->child[k] = k < b.n ? b.child[k] : kNullIndex;
+	uint32_t exps = b.n << 24;
+	for (int a = 0; a < 3; ++a) {
+		double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+		if (b.hasOwn) { lo = b.ownLo[a]; hi = b.ownHi[a]; }
+		for (uint32_t k = 0; k < b.n; ++k) {
+			if (b.whole[k]) continue;
+			lo = std::min(lo, (double)b.lo[k][a]);
+			hi = std::max(hi, (double)b.hi[k][a]);
+		}
+		int eb;             // biased exponent byte of step * 2^kGridShift
+		float org;
+		uint32_t qlo = 0, qhi = 0;
+		if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {
+			// nothing finite to bound (a lone MBVH root leaf, or non-finite input): a grid that spans
+			// (practically) everything, so that every ray passes
+			org = -ldexpf(1.f, 126);
+			eb = 119 + kGridShift + 127;
+			for (uint32_t k = 0; k < kWideSlots; ++k) {
+				qlo |= (k < b.n ? 0u : 255u) << (8 * k);
+				qhi |= (k < b.n ? 255u : 0u) << (8 * k);
+			}
+		} else {
+			// smallest power-of-two step with 250 steps >= extent, but never finer than 4 ulp of the
+			// largest coordinate (the grid origin is a float)
+			const double ext = hi - lo;
+			int E = -140, e2;
+			if (ext > 0.0) {
+				const double m = frexp(ext / 250.0, &e2);      // ext / 250 = m * 2^e2, m in [0.5, 1)
+				E = (m == 0.5) ? e2 - 1 : e2;
+			}
+			const double mag = std::max(fabs(lo), fabs(hi));
+			if (mag > 0.0) {
+				frexp(mag, &e2);
+				E = std::max(E, e2 - 24 + 2);
+			}
+			E = std::max(E, 1 - kGridShift - 127);
+			for (;; ++E) {
+				eb = E + kGridShift + 127;
+				if (eb > 254)
+					throw std::runtime_error("BVH box coordinates are too large for the node grid");
+				const double step = ldexp(1.0, E);
+				// the origin sits 1.5 steps below the lowest plane: every plane keeps its outward margin
+				// (no plane is clamped at 0 or 255), whole-grid slots extend past the node's own box
+				org = (float)(lo - 1.5 * step);
+				bool ok = std::isfinite(org);
+				qlo = qhi = 0;
+				for (uint32_t k = 0; k < kWideSlots && ok; ++k) {
+					uint32_t l = 255, h = 0;        // unused slot: inverted
+					if (k < b.n) {
+						if (b.whole[k]) {
+							l = 0; h = 255;
+						} else {
+							const double xl = ((double)b.lo[k][a] - (double)org) / step, xh = ((double)b.hi[k][a] - (double)org) / step;
+							const double fl = floor(xl - 1.0 / 64.0), ch = ceil(xh + 1.0 / 64.0);
+							if (!(fl >= 0.0) || !(ch <= 255.0) || !(fl <= ch)) {
+								ok = false;     // needs a coarser grid (or the child box is not finite)
+								break;
+							}
+							l = (uint32_t)fl;
+							h = (uint32_t)ch;
+						}
+					}
+					qlo |= l << (8 * k);
+					qhi |= h << (8 * k);
+				}
+				if (ok)
+					break;
+				bool finite = true;
+				for (uint32_t k = 0; k < b.n; ++k)
+					if (!b.whole[k] && (!std::isfinite(b.lo[k][a]) || !std::isfinite(b.hi[k][a]) || !(b.lo[k][a] <= b.hi[k][a])))
+						finite = false;
+				if (!finite)
+					throw std::runtime_error("BVH node with a non-finite or inverted box");
+			}
+		}
+		w->org[a] = org;
+		w->qlo[a] = qlo;
+		w->qhi[a] = qhi;
+		exps |= (uint32_t)eb << (8 * a);
+	}
+	w->exps = exps;
 }
 
 // The box BVHAccel::Init gives the builders for one triangle (bvhaccel.cpp:116-122): bounds of the
@@ -144,29 +234,27 @@ static void TriBuildBox(const TriRecord &tr, float lo[3], float hi[3]) {
 	}
 }
 
-// Fills slot k of `w` with reference child `c` (inner node, triangle leaf or MBVH root leaf).
-static void FillSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, WideNode *w, uint32_t k, WideScene *out) {
+// Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.
+static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, SlotBoxes *b, WideScene *out) {
 	const lrb_bvh_node &ch = in.nodes[c];
+	const uint32_t k = b->n++;
+	b->whole[k] = false;
 	if (!IsLeaf(ch.nodeData)) {
-		SetSlotBox(w, k, ch.bvhNode.bboxMin, ch.bvhNode.bboxMax);
-		w->child[k] = wideOf[c];
+		for (int a = 0; a < 3; ++a) { b->lo[k][a] = ch.bvhNode.bboxMin[a]; b->hi[k][a] = ch.bvhNode.bboxMax[a]; }
+		b->child[k] = wideOf[c];
 	} else if (in.instLeaves) {
-		const float lo[3] = { -kInfF, -kInfF, -kInfF }, hi[3] = { kInfF, kInfF, kInfF };
-		SetSlotBox(w, k, lo, hi);
+		b->whole[k] = true;
 		InstRecord ir;
 		FillInst(in, c, &ir);
-		w->child[k] = kTagInstance | (uint32_t)out->insts.size();
+		b->child[k] = kTagInstance | (uint32_t)out->insts.size();
 		out->insts.push_back(ir);
 	} else {
 		TriRecord tr;
 		FillTri(in, c, &tr);
-		float lo[3], hi[3];
-		TriBuildBox(tr, lo, hi);
-		SetSlotBox(w, k, lo, hi);
-		w->child[k] = kTagTri | (uint32_t)out->tris.size();
+		TriBuildBox(tr, b->lo[k], b->hi[k]);
+		b->child[k] = kTagTri | (uint32_t)out->tris.size();
 		out->tris.push_back(tr);
 	}
-	w->nChild = k + 1;
 }
 
 // Appends the wide form of one reference tree to `out`.  Returns the wide index of its root
@@ -185,9 +273,10 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 
 	// The root itself is a leaf (one-triangle mesh / one-mesh dataset): wrap it in a node.
 	if (IsLeaf(nodes[0].nodeData)) {
+		SlotBoxes b;
+		AddSlot(in, wideOf, 0, &b, out);
 		WideNode w;
-		ClearNode(&w);
-		FillSlot(in, wideOf, 0, &w, 0, out);
+		QuantizeNode(b, kNullIndex, 0, &w);
 		if (in.instLeaves)
 			*stackNeed = 1 + (*in.leafStackNeed)[nodes[0].bvhLeaf.leafIndex];
 		out->wide.push_back(w);
@@ -222,12 +311,15 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		out->tris.reserve(out->tris.size() + nLeafTotal);
 
 	{
-		WideNode &e = out->wide[wideStart];
-		ClearNode(&e);
-		SetSlotBox(&e, 0, nodes[0].bvhNode.bboxMin, nodes[0].bvhNode.bboxMax);
-		e.child[0] = wideOf[0];
-		e.nChild = 1;
-		e.flags = kNodeEntry;
+		SlotBoxes b;
+		b.n = 1;
+		b.whole[0] = false;
+		for (int a = 0; a < 3; ++a) { b.lo[0][a] = nodes[0].bvhNode.bboxMin[a]; b.hi[0][a] = nodes[0].bvhNode.bboxMax[a]; }
+		b.child[0] = wideOf[0];
+		QuantizeNode(b, kNullIndex, kNodeEntry, &out->wide[wideStart]);
+		if (in.instLeaves || !out->twoLevel) {
+			for (int a = 0; a < 3; ++a) { out->entryBox[a] = nodes[0].bvhNode.bboxMin[a]; out->entryBox[3 + a] = nodes[0].bvhNode.bboxMax[a]; }
+		}
 	}
 
 	// Pass 2: fill, children in reference order.
@@ -241,13 +333,15 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 			kids.push_back(c);
 		const uint32_t nW = std::max<uint32_t>(1u, ((uint32_t)kids.size() + kWideSlots - 1) / kWideSlots);
 		for (uint32_t j = 0; j < nW; ++j) {
-			WideNode &w = out->wide[wideOf[i] + j];
-			ClearNode(&w);
 			const uint32_t first = j * kWideSlots;
 			const uint32_t cnt = std::min<uint32_t>(kWideSlots, (uint32_t)kids.size() - std::min<uint32_t>((uint32_t)kids.size(), first));
+			SlotBoxes b;
+			// the node's own box bounds every child; MBVH root leaves (no box of their own) take it whole
+			b.hasOwn = true;
+			for (int a = 0; a < 3; ++a) { b.ownLo[a] = nodes[i].bvhNode.bboxMin[a]; b.ownHi[a] = nodes[i].bvhNode.bboxMax[a]; }
 			for (uint32_t k = 0; k < cnt; ++k)
-				FillSlot(in, wideOf, kids[first + k], &w, k, out);
-			w.next = (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex;
+				AddSlot(in, wideOf, kids[first + k], &b, out);
+			QuantizeNode(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
 		}
 	}
 
@@ -258,9 +352,10 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	std::vector<uint32_t> D(nWide, 0);
 	for (uint32_t r = nWide; r-- > 0;) {
 		const WideNode &w = out->wide[wideStart + r];
-		uint32_t k = w.nChild + (w.next != kNullIndex ? 1u : 0u);
+		const uint32_t nChild = NodeSlots(w);
+		uint32_t k = nChild + (w.next != kNullIndex ? 1u : 0u);
 		uint32_t below = 0;
-		for (uint32_t c = 0; c < w.nChild; ++c) {
+		for (uint32_t c = 0; c < nChild; ++c) {
 			const uint32_t ref = w.child[c];
 			if (ref & kTagInstance)
 				below = std::max(below, 1u + out->insts[ref & kRefIndexMask].pad[0]);
@@ -302,16 +397,17 @@ void FillRootOfView(const WideScene &w, SceneView *v) {
 	v->twoLevel = w.twoLevel ? 1u : 0u;
 	v->rootHasBox = 0;
 	v->rootChild = 0;
+	v->oneBits = 0x3f800000u;
 	for (int i = 0; i < 6; ++i) v->rootBox[i] = 0.f;
 	if (w.wide.empty() || w.rootWide == kNullIndex)
 		return;
 	const WideNode &e = w.wide[w.rootWide];
-	// the one-child entry node ConvertTree puts in front of a tree whose root is an inner node
+	// the one-child entry node ConvertTree puts in front of a tree whose root is an inner node: its
+	// box (the reference's node 0, exact floats) is tested from the kernel parameters
 	if (e.flags & kNodeEntry) {
 		v->rootHasBox = 1;
 		v->rootChild = e.child[0];
-		v->rootBox[0] = e.lox[0]; v->rootBox[1] = e.loy[0]; v->rootBox[2] = e.loz[0];
-		v->rootBox[3] = e.hix[0]; v->rootBox[4] = e.hiy[0]; v->rootBox[5] = e.hiz[0];
+		for (int i = 0; i < 6; ++i) v->rootBox[i] = w.entryBox[i];
 	}
 }
 

@@ -25,10 +25,11 @@ struct WideScene {
 	uint32_t stackNeed;     // worst-case number of live stack entries
 	uint32_t nRefNodes;
 	bool twoLevel;
+	float entryBox[6];      // exact box of the top-level tree's root (reference node 0): min xyz, max xyz
 	std::vector<uint32_t> leafRootWide;   // per unique leaf: wide index of its root
 	std::vector<uint32_t> leafStackNeed;
 
-	WideScene() : rootWide(0), nRootWide(0), stackNeed(0), nRefNodes(0), twoLevel(false) {}
+	WideScene() : rootWide(0), nRootWide(0), stackNeed(0), nRefNodes(0), twoLevel(false) { for (int i = 0; i < 6; ++i) entryBox[i] = 0.f; }
 };
 
 // Validates a reference array (skip indices in range and properly nested).  Returns false and

@@ -124,6 +124,7 @@ struct TraceArgs {
 	lrb_rayhit *hits;
 	uint32_t rayCount;
 	uint32_t *counter;          // persistent kernel: next unassigned ray (zeroed before launch)
+	const uint32_t *perm;       // optional processing order (ray indices sorted for coherence), or NULL
 	uint32_t *spillNode;        // global stack spill, [spillDepth][totalThreads]
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
@@ -292,8 +293,9 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 				base = atomicAdd(a.counter, (uint32_t)nIdle);
 			base = __shfl_sync(0xffffffffu, base, leader);
 			if (!active) {
-				const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-				if (idx < a.rayCount) {
+				const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
+				if (slot < a.rayCount) {
+					const uint32_t idx = a.perm ? __ldg(a.perm + slot) : slot;
 					lrb_ray r;
 					LoadRay(a.rays, idx, r);
 					// masked rays are skipped and their RayHit is left untouched (bvh.cl:242-244)
@@ -352,6 +354,41 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 			nLive = nTri + nNode;
 		} while (nLive >= floorLanes);
 	}
+}
+
+// ---- ray ordering ----------------------------------------------------------------------------
+
+// Sort key of a ray for the optional coherence pre-pass: direction octant in the top bits, Morton
+// code of the origin cell (bitsPerAxis bits per axis inside the scene's root box) below.  Rays with
+// the same key start in the same cell and order the children of every node the same way.  Masked
+// rays get the largest key.
+__device__ __forceinline__ uint32_t SpreadBits3(uint32_t v) {      // 10 bits -> every third bit
+	v = (v | (v << 16)) & 0x030000ffu;
+	v = (v | (v << 8)) & 0x0300f00fu;
+	v = (v | (v << 4)) & 0x030c30c3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+__global__ void __launch_bounds__(256) RayKeyKernel(const lrb_ray *__restrict__ rays, const uint32_t n,
+		const float lox, const float loy, const float loz, const float sx, const float sy, const float sz,
+		const uint32_t bitsPerAxis, uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const float4 *p = reinterpret_cast<const float4 *>(rays + i);
+	const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+	const float cells = (float)((1u << bitsPerAxis) - 1u);
+	const uint32_t qx = (uint32_t)fminf(fmaxf((a.x - lox) * sx, 0.f), cells);
+	const uint32_t qy = (uint32_t)fminf(fmaxf((a.y - loy) * sy, 0.f), cells);
+	const uint32_t qz = (uint32_t)fminf(fmaxf((a.z - loz) * sz, 0.f), cells);
+	const uint32_t morton = SpreadBits3(qx) | (SpreadBits3(qy) << 1) | (SpreadBits3(qz) << 2);
+	const uint32_t octant = (a.w < 0.f ? 1u : 0u) | (b.x < 0.f ? 2u : 0u) | (b.y < 0.f ? 4u : 0u);
+	uint32_t key = (octant << (3u * bitsPerAxis)) | morton;
+	if (__float_as_uint(c.y) & LRB_RAY_FLAGS_MASKED)
+		key = (8u << (3u * bitsPerAxis)) - 1u;
+	keys[i] = key;
+	idx[i] = i;
 }
 
 // ---- static grid-stride kernel (simple variant + instrumented variant) -----------------------

@@ -45,6 +45,10 @@
 #define LRB_FMAX(a, b) fmaxf((a), (b))
 #define LRB_FMIN(a, b) fminf((a), (b))
 #define LRB_F2U(x) __float_as_uint(x)
+#define LRB_U2F(x) __uint_as_float(x)
+#define LRB_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+/* byte k of w placed in mantissa bits 8-15 of 1.0f: the float 1 + q * 2^-15 (one PRMT) */
+#define LRB_QBYTE(w, k, one) lrb::QByte<(k)>((w), (one))
 /* Slerp's sinf/acosf (quaternion.cpp:150-156): the reference gets glibc's results, which are the
  * correctly rounded float in all but vanishingly rare cases.  CUDA's sinf/acosf are 1-2 ulp
  * functions, enough to move b1/b2 of distant triangles past the 1e-5 tolerance, so the device
@@ -57,6 +61,9 @@
 #define LRB_FMAX(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) > (b) ? (a) : (b))))
 #define LRB_FMIN(a, b) ((a) != (a) ? (b) : ((b) != (b) ? (a) : ((a) < (b) ? (a) : (b))))
 #define LRB_F2U(x) lrb::HostF2U(x)
+#define LRB_U2F(x) lrb::HostU2F(x)
+#define LRB_FMA(a, b, c) fmaf((a), (b), (c))
+#define LRB_QBYTE(w, k, one) lrb::HostU2F((one) | ((((w) >> (8 * (k))) & 0xffu) << 8))
 #define LRB_SINF(x) sinf(x)
 #define LRB_ACOSF(x) acosf(x)
 #define LRB_MUL(a, b) ((a) * (b))
@@ -78,6 +85,12 @@ struct uint4 { uint32_t x, y, z, w; };
 struct F8 { float v[8]; };
 
 #if defined(__CUDA_ARCH__)
+// The selector is the immediate and 1.0f sits in a register (a PRMT takes one immediate).
+template <int K> __device__ __forceinline__ float QByte(const uint32_t w, const uint32_t one) {
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "n"(0x7604 | (K << 4)));
+	return __uint_as_float(r);
+}
 __device__ __forceinline__ F8 Ld256(const void *p) {
 	F8 r;
 	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -88,6 +101,7 @@ __device__ __forceinline__ F8 Ld256(const void *p) {
 #else
 static inline F8 Ld256(const void *p) { F8 r; __builtin_memcpy(&r, p, 32); return r; }
 static inline uint32_t HostF2U(float x) { uint32_t u; __builtin_memcpy(&u, &x, 4); return u; }
+static inline float HostU2F(uint32_t u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
 #endif
 
 #if !defined(__CUDA_ARCH__)
@@ -164,9 +178,9 @@ LRB_HD bool TriangleTest(const RayState &r, const float p0x, const float p0y, co
 // does not swap and its `>` / `<` updates ignore the NaN; here fmaxf / fminf ignore it as well, and
 // in the sub-cases where the two differ this form only ever PASSES a box the reference rejects
 // (never the opposite), which cannot change a result.
-// Unused slots hold the empty box (+inf, -inf): a ray with finite origin and at least one finite,
-// non-zero-reciprocal direction component gets t0 = +inf there.  Only rays made of NaN / inf can
-// "pass" an empty box; their kNullIndex reference is dropped by Resolve.
+// (Used for the root box, which travels as exact floats in the kernel parameters.  Unused slots of a
+// node hold an inverted box; a degenerate ray that "passes" one gets a kNullIndex reference, which
+// Resolve drops.)
 LRB_HD float ChildEntry(const RayState &s, const bool nx, const bool ny, const bool nz,
 		const float lox, const float loy, const float loz, const float hix, const float hiy, const float hiz) {
 	const float tnx = LRB_MUL(LRB_SUB(nx ? hix : lox, s.ox), s.ix);
@@ -442,30 +456,66 @@ LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
 	}
 }
 
+// Entry distance of one slot box of a quantized node, or +inf when the ray misses it.
+//   plane position = org + q * step  =>  t = (org + q * step - o) * inv = fma(1 + q * 2^-15, A, B)
+//   with A = step * 2^15 * inv and B = (org - o) * inv - A  (per node and axis, see NodeStep);
+//   `1 + q * 2^-15` is the float whose mantissa bits 8-15 hold the byte q (one PRMT).
+// Rounding: B carries an error below ulp(A) = 2^-9 step, covered by the 1/64-step margin the
+// planes were rounded outward with (relayout.cpp QuantizeNode); the remaining error is the same
+// few ulp of |plane - o| * |inv| that the reference's own (p - o) * inv test has, far inside the
+// >= 128 ulp / 1e-5 by which every build box is grown around its triangle (bvhaccel.cpp:116-122).
+// Degenerate products (0 * inf, inf - inf) give NaN, which fmaxf / fminf ignore: the box passes.
+template <int k>
+LRB_HD float SlotEntry(const RayState &s, const uint32_t one, const uint32_t nqx, const uint32_t nqy, const uint32_t nqz,
+		const uint32_t fqx, const uint32_t fqy, const uint32_t fqz,
+		const float ax, const float ay, const float az, const float bx, const float by, const float bz) {
+	const float tnx = LRB_FMA(LRB_QBYTE(nqx, k, one), ax, bx);
+	const float tny = LRB_FMA(LRB_QBYTE(nqy, k, one), ay, by);
+	const float tnz = LRB_FMA(LRB_QBYTE(nqz, k, one), az, bz);
+	const float tfx = LRB_FMA(LRB_QBYTE(fqx, k, one), ax, bx);
+	const float tfy = LRB_FMA(LRB_QBYTE(fqy, k, one), ay, by);
+	const float tfz = LRB_FMA(LRB_QBYTE(fqz, k, one), az, bz);
+	const float t0 = LRB_FMAX(LRB_FMAX(LRB_FMAX(tnx, tny), tnz), s.mint);
+	const float t1 = LRB_FMIN(LRB_FMIN(LRB_FMIN(tfx, tfy), tfz), s.maxt);
+	return !(t0 > t1) ? t0 : LRB_INF;
+}
+
 // Visits the wide node s.cur refers to: box-tests its four child slots (no branches), orders the
 // children near-to-far, continues with the nearest and pushes the others with their entry
 // distances.
 template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
-	// ---- fetch the 128-byte node with four 256-bit loads ----
+	// ---- fetch the 64-byte node with two 256-bit loads ----
 	const char *np = reinterpret_cast<const char *>(sc.nodes + s.cur);
 	if (STATS) stats->wideNodes++;
-	const F8 A = Ld256(np);          // lox[4] loy[4]
-	const F8 B = Ld256(np + 32);     // loz[4] hix[4]
-	const F8 C = Ld256(np + 64);     // hiy[4] hiz[4]
-	const F8 D = Ld256(np + 96);     // child[4] next nChild flags pad
-	uint32_t c0 = LRB_F2U(D.v[0]), c1 = LRB_F2U(D.v[1]), c2 = LRB_F2U(D.v[2]), c3 = LRB_F2U(D.v[3]);
-	const uint32_t next = LRB_F2U(D.v[4]);
+	const F8 A = Ld256(np);          // org[3] exps child[4]
+	const F8 B = Ld256(np + 32);     // qlo[3] qhi[3] next flags
+	uint32_t c0 = LRB_F2U(A.v[4]), c1 = LRB_F2U(A.v[5]), c2 = LRB_F2U(A.v[6]), c3 = LRB_F2U(A.v[7]);
+	const uint32_t exps = LRB_F2U(A.v[3]);
+	const uint32_t next = LRB_F2U(B.v[6]);
+
+	// per-axis decode constants
+	const float ax = LRB_MUL(LRB_U2F((exps << 23) & 0x7f800000u), s.ix);
+	const float ay = LRB_MUL(LRB_U2F((exps << 15) & 0x7f800000u), s.iy);
+	const float az = LRB_MUL(LRB_U2F((exps << 7) & 0x7f800000u), s.iz);
+	const float bx = LRB_SUB(LRB_MUL(LRB_SUB(A.v[0], s.ox), s.ix), ax);
+	const float by = LRB_SUB(LRB_MUL(LRB_SUB(A.v[1], s.oy), s.iy), ay);
+	const float bz = LRB_SUB(LRB_MUL(LRB_SUB(A.v[2], s.oz), s.iz), az);
+	// near / far plane words by direction sign (see ChildEntry)
+	const bool nx = s.ix < 0.f, ny = s.iy < 0.f, nz = s.iz < 0.f;
+	const uint32_t qlx = LRB_F2U(B.v[0]), qly = LRB_F2U(B.v[1]), qlz = LRB_F2U(B.v[2]);
+	const uint32_t qhx = LRB_F2U(B.v[3]), qhy = LRB_F2U(B.v[4]), qhz = LRB_F2U(B.v[5]);
+	const uint32_t nqx = nx ? qhx : qlx, nqy = ny ? qhy : qly, nqz = nz ? qhz : qlz;
+	const uint32_t fqx = nx ? qlx : qhx, fqy = ny ? qly : qhy, fqz = nz ? qlz : qhz;
 
 	// ---- box tests of all four slots, near-to-far ordering ----
 	// A box that passes with entry distance +inf (mint = maxt = +inf) cannot hold an acceptable hit:
 	// the triangle test rejects t > maxt and a tie at +inf never wins; "not hit" is exact.
 	const float kInf = LRB_INF;
-	const bool nx = s.ix < 0.f, ny = s.iy < 0.f, nz = s.iz < 0.f;
-	float d0 = ChildEntry(s, nx, ny, nz, A.v[0], A.v[4], B.v[0], B.v[4], C.v[0], C.v[4]);
-	float d1 = ChildEntry(s, nx, ny, nz, A.v[1], A.v[5], B.v[1], B.v[5], C.v[1], C.v[5]);
-	float d2 = ChildEntry(s, nx, ny, nz, A.v[2], A.v[6], B.v[2], B.v[6], C.v[2], C.v[6]);
-	float d3 = ChildEntry(s, nx, ny, nz, A.v[3], A.v[7], B.v[3], B.v[7], C.v[3], C.v[7]);
+	float d0 = SlotEntry<0>(s, sc.oneBits, nqx, nqy, nqz, fqx, fqy, fqz, ax, ay, az, bx, by, bz);
+	float d1 = SlotEntry<1>(s, sc.oneBits, nqx, nqy, nqz, fqx, fqy, fqz, ax, ay, az, bx, by, bz);
+	float d2 = SlotEntry<2>(s, sc.oneBits, nqx, nqy, nqz, fqx, fqy, fqz, ax, ay, az, bx, by, bz);
+	float d3 = SlotEntry<3>(s, sc.oneBits, nqx, nqy, nqz, fqx, fqy, fqz, ax, ay, az, bx, by, bz);
 
 	// sorting network on (distance, child), ascending, written with selects
 #define LRB_CSWAP(da, ca, db, cb) { const bool sw_ = db < da; const float lo_ = sw_ ? db : da, hi_ = sw_ ? da : db; \

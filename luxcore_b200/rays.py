@@ -158,6 +158,40 @@ def bounce_rays(rays_u8, hits_u8, tri_p0, tri_e1, tri_e2, seed=2):
     return pack_rays(no, nd, time=time), idx
 
 
+def surface_rays(tri_p0, tri_e1, tri_e2, n, seed=7, device="cpu", axis_fraction=0.1):
+    """Grazing stress batch: origins ON random triangles, moved along the geometric normal by
+    k * E(p) with k uniform in [-2, 2] (exactly 0 for a quarter of them), directions uniform on the
+    sphere; `axis_fraction` of the rays get an exactly axis-parallel direction (zero components ->
+    infinite reciprocals).  These are the rays whose hits sit right at the planes of the boxes that
+    bound the triangles they start from."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    p0 = torch.as_tensor(tri_p0, dtype=torch.float32, device=device)
+    e1 = torch.as_tensor(tri_e1, dtype=torch.float32, device=device)
+    e2 = torch.as_tensor(tri_e2, dtype=torch.float32, device=device)
+    t = torch.randint(0, p0.shape[0], (n,), generator=g, device=device)
+    u = torch.rand((n, 2), generator=g, device=device, dtype=torch.float32)
+    su = torch.sqrt(u[:, 0])
+    b1 = 1.0 - su
+    b2 = u[:, 1] * su
+    p = p0[t] + b1[:, None] * e1[t] + b2[:, None] * e2[t]
+    nrm = torch.linalg.cross(e1[t], e2[t])
+    ln = nrm.norm(dim=-1, keepdim=True)
+    nrm = torch.where(ln > 0, nrm / torch.where(ln > 0, ln, torch.ones_like(ln)), torch.zeros_like(nrm))
+    k = 4.0 * torch.rand(n, generator=g, device=device, dtype=torch.float32) - 2.0
+    k = torch.where(torch.rand(n, generator=g, device=device) < 0.25, torch.zeros_like(k), k)
+    o = p + nrm * (k * machine_epsilon_point(p))[:, None]
+    z = 1.0 - 2.0 * torch.rand(n, generator=g, device=device, dtype=torch.float32)
+    phi = 2.0 * math.pi * torch.rand(n, generator=g, device=device, dtype=torch.float32)
+    r = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
+    d = torch.stack([r * torch.cos(phi), r * torch.sin(phi), z], dim=1)
+    ax = torch.rand(n, generator=g, device=device) < axis_fraction
+    which = torch.randint(0, 6, (n,), generator=g, device=device)
+    axes = torch.tensor([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=torch.float32, device=device)
+    d = torch.where(ax[:, None], axes[which], d)
+    return pack_rays(o, d)
+
+
 def to_numpy_rays(rays_u8):
     from_dtype = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("mint", "<f4"), ("maxt", "<f4"), ("time", "<f4"),
                            ("flags", "<u4"), ("pad", "<f4", 2)])

@@ -37,3 +37,28 @@ def test_bvh_emulation_matches_oracle(name, tree_type):
     # single-level BVH: identical arithmetic => identical floats
     assert rep["bit_exact_hits"] == rep["hits"]
     assert st["max_stack"] <= emu.info()["stack_need"]
+
+
+@pytest.mark.parametrize("name,tree_type,n", [("cornell", 4, 60000), ("bigmonkey", 4, 60000), ("kitchen", 4, 120000), ("kitchen", 8, 40000),
+                                              ("luxball", 2, 40000)])
+def test_bvh_emulation_grazing_rays(name, tree_type, n):
+    """Rays that start on (or a few epsilons off) the surfaces, axis-parallel ones included: their
+    hits lie at the very planes of the leaf boxes and of the quantized node grids."""
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=tree_type)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(bvh.nodes(), verts, offs)
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = R.to_numpy_rays(R.surface_rays(p0, e1, e2, n, seed=17))
+    # also from far outside the scene (large |o| against small boxes)
+    lo, hi = desc.bbox()
+    far = R.to_numpy_rays(R.uniform_rays(lo - 40 * (hi - lo), hi + 40 * (hi - lo), n // 4, seed=19))
+    c = 0.5 * (lo + hi)
+    far["d"] = (c[None, :] + 0.3 * (hi - lo)[None, :] * (np.random.default_rng(5).random((far.shape[0], 3)).astype(np.float32) - 0.5)) - far["o"]
+    rays = np.concatenate([rays, far])
+    ref = bvh.intersect(rays)
+    got = emu.trace(rays)
+    rep = H.compare_hits(got, ref, rays, what="grazing %s k=%d" % (name, tree_type))
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]

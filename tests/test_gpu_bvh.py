@@ -113,3 +113,59 @@ def test_trace_gather_pushes_every_hit(dev, chunks, n):
     for p in (d_rays, d_hits, d_dst):
         dev.free(p)
     scene.free()
+
+
+@pytest.mark.parametrize("name,n,bits", [("kitchen", 600000, 5), ("cornell", 300000, 3), ("bigmonkey", 400000, 9)])
+def test_sorted_ray_order_gives_identical_hits(dev, name, n, bits):
+    """The coherence pre-pass (sort_rays) only changes the order rays are processed in: the RayHit
+    buffer must be byte-identical to the unsorted trace, masked rays included."""
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    rays = _rays_for(desc, n, seed=41)
+    m = rays.shape[0]
+    mask = np.random.default_rng(2).random(m) < 0.15
+    rays["flags"][mask] = capi.RAY_FLAGS_MASKED
+    base = np.zeros(m, dtype=capi.HIT_DTYPE)
+    base["t"] = 5.0
+    plain = base.copy()
+    scene.trace_host(rays, plain)
+    dev.set_option("sort_rays", "1")
+    dev.set_option("sort_bits", str(bits))
+    dev.set_option("sort_min_rays", "1024")
+    try:
+        srt = base.copy()
+        scene.trace_host(rays, srt)
+    finally:
+        dev.set_option("sort_rays", "0")
+        dev.set_option("sort_bits", "5")
+    assert srt.tobytes() == plain.tobytes()
+    ref = bvh.intersect(rays)
+    H.compare_hits(srt[~mask], ref[~mask], rays[~mask], what="sorted " + name)
+    scene.free()
+
+
+@pytest.mark.parametrize("name,tree_type,n", [("cornell", 4, 300000), ("bigmonkey", 4, 300000), ("kitchen", 4, 1000000), ("classroom", 8, 300000)])
+def test_bvh_grazing_rays_match_oracle(dev, name, tree_type, n):
+    """Rays starting on / a few epsilons off the surfaces (axis-parallel ones included) and rays from
+    far outside the scene: hits at the very planes of the leaf boxes and quantized node grids."""
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=tree_type)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = R.to_numpy_rays(R.surface_rays(p0, e1, e2, n, seed=23))
+    lo, hi = desc.bbox()
+    far = R.to_numpy_rays(R.uniform_rays(lo - 40 * (hi - lo), hi + 40 * (hi - lo), n // 4, seed=29))
+    c = 0.5 * (lo + hi)
+    far["d"] = (c[None, :] + 0.3 * (hi - lo)[None, :] * (np.random.default_rng(6).random((far.shape[0], 3)).astype(np.float32) - 0.5)) - far["o"]
+    rays = np.concatenate([rays, far])
+    ref = bvh.intersect(rays)
+    got = scene.trace_host(rays)
+    rep = H.compare_hits(got, ref, rays, what="grazing %s k=%d" % (name, tree_type))
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
