@@ -211,15 +211,16 @@ LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_d
 LRB_API int lrb_ipc_get_handle(lrb_device *dev, void *devptr, unsigned char handle[LRB_IPC_HANDLE_BYTES]);
 LRB_API int lrb_ipc_open_handle(lrb_device *dev, const unsigned char handle[LRB_IPC_HANDLE_BYTES], void **devptr);
 LRB_API int lrb_ipc_close_handle(lrb_device *dev, void *devptr);
-/* Trace + gather, overlapped.  gather_dst_dev is this rank's slice of the gather buffer (local or
- * peer-mapped memory); hits_dev keeps the local copy; gather_dst_dev == hits_dev skips the push.
- *   n_chunks == 0 (default): FUSED -- one persistent kernel traces and, as each run of 32 768 ray
- *     indices is retired (release/acquire counters), a few copier warps of the same kernel stream
- *     that RayHit range to gather_dst_dev with 16-byte stores over NVLink while the other warps keep
- *     tracing.  No second launch, no copy engine, no NCCL.
+/* Trace + gather, fused.  gather_dst_dev is this rank's slice of the gather buffer (local or
+ * peer-mapped memory); hits_dev keeps the local copy (may be NULL with n_chunks == 0 when only the
+ * gathered copy is wanted); gather_dst_dev == hits_dev is a plain trace.
+ *   n_chunks == 0 (default): ONE kernel -- every lane stores its finished RayHit record into hits_dev
+ *     and into gather_dst_dev (posted 4-byte stores over NVLink that ride along with the traversal;
+ *     measured: no change in kernel time).  The records of masked rays are forwarded from hits_dev.
+ *     No second launch, no copy engine, no NCCL.
  *   n_chunks >= 1: the batch is cut into n_chunks launches; each traced piece is pushed by the copy
  *     engine on a second stream while the next piece is traced.
- * Asynchronous: later work on the device's stream is ordered after the last push. */
+ * Asynchronous: later work on the device's stream is ordered after the last store / push. */
 LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
 		void *gather_dst_dev, uint32_t n_chunks);
 

@@ -58,7 +58,6 @@ struct lrb_device {
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
 	int triBias;
-	int pushCopiers;                // copier warps of the fused trace + gather kernel
 	int sortRays;                   // 1 = order the rays of a batch for coherence before tracing them
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
 	int sortMinRays;                // batches smaller than this are traced in index order
@@ -71,7 +70,6 @@ struct lrb_device {
 	void *stageRays, *stageHits;
 	size_t stageRaysBytes, stageHitsBytes;
 	std::vector<cudaEvent_t> events;
-	uint32_t *pushWatch;            // watchdog word of the last fused push launch (checked by lrb_sync)
 };
 
 struct lrb_scene {
@@ -79,6 +77,7 @@ struct lrb_scene {
 	WideScene host;                 // kept for MBVH (Update); cleared for single-level scenes
 	WideNode *dNodes;
 	TriRecord *dTris;
+	TriGate *dGates;
 	InstRecord *dInsts;
 	float *dMinv;
 	uint32_t *dMotionFirst, *dMotionLast;
@@ -89,8 +88,6 @@ struct lrb_scene {
 	float *dSpillT;
 	size_t spillEntries;
 	TraceStats *dStats;
-	uint32_t *dChunkDone;           // fused push: retired-ray counters per chunk
-	size_t chunkDoneCap;
 	SceneView view;
 	lrb_scene_info info;
 };
@@ -146,7 +143,6 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	memset(&dev->counters, 0, sizeof(dev->counters));
 	dev->stageRays = dev->stageHits = nullptr;
 	dev->stageRaysBytes = dev->stageHitsBytes = 0;
-	dev->pushWatch = nullptr;
 	cudaError_t e = cudaGetDeviceProperties(&dev->prop, ordinal);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->ownStream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dev->copyInStream, cudaStreamNonBlocking);
@@ -161,7 +157,6 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->smemDepth = 16;
 	dev->refillBelow = 24;
 	dev->triBias = 8;
-	dev->pushCopiers = 32;
 	dev->sortRays = 0;
 	dev->sortBitsPerAxis = 5;
 	dev->sortMinRays = 1 << 18;
@@ -241,9 +236,6 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "tri_bias") {
 		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
 		dev->triBias = iv;
-	} else if (k == "push_copiers") {
-		if (iv < 1 || iv > 1024) return Fail(LRB_ERR_INVALID, "push_copiers out of range");
-		dev->pushCopiers = iv;
 	} else if (k == "sort_rays") {
 		dev->sortRays = iv ? 1 : 0;
 	} else if (k == "sort_bits") {
@@ -330,14 +322,6 @@ int lrb_flush(lrb_device *dev) {
 int lrb_sync(lrb_device *dev) {
 	LRB_SETDEV(dev);
 	LRB_CUDA(cudaStreamSynchronize(dev->stream));
-	// watchdog of the fused trace + gather kernel (see CopierLoop)
-	if (dev->pushWatch) {
-		uint32_t w = 0;
-		LRB_CUDA(cudaMemcpy(&w, dev->pushWatch, sizeof(w), cudaMemcpyDeviceToHost));
-		dev->pushWatch = nullptr;
-		if (w != 0)
-			return Fail(LRB_ERR_INTERNAL, "fused trace+gather kernel: a RayHit chunk never completed (watchdog)");
-	}
 	return LRB_OK;
 }
 
@@ -437,6 +421,7 @@ static void FillView(lrb_scene *s) {
 	SceneView &v = s->view;
 	v.nodes = s->dNodes;
 	v.tris = s->dTris;
+	v.gates = s->dGates;
 	v.insts = s->dInsts;
 	v.minv = s->dMinv;
 	v.motionFirst = s->dMotionFirst;
@@ -457,6 +442,7 @@ static int UploadScene(lrb_scene *s) {
 	int rc;
 	if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.tris, &s->dTris, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.gates, &s->dGates, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.insts, &s->dInsts, &s->capInsts, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.minv, &s->dMinv, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.motionFirst, &s->dMotionFirst, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
@@ -481,12 +467,11 @@ static int UploadScene(lrb_scene *s) {
 static lrb_scene *NewScene(lrb_device *dev) {
 	lrb_scene *s = new lrb_scene();
 	s->dev = dev;
-	s->dNodes = nullptr; s->dTris = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
+	s->dNodes = nullptr; s->dTris = nullptr; s->dGates = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
 	s->dMotionFirst = s->dMotionLast = nullptr; s->dInterps = nullptr;
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
 	s->dStats = nullptr;
-	s->dChunkDone = nullptr; s->chunkDoneCap = 0;
 	memset(&s->view, 0, sizeof(s->view));
 	memset(&s->info, 0, sizeof(s->info));
 	return s;
@@ -500,11 +485,9 @@ int lrb_scene_free(lrb_scene *s) {
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
 	cudaStreamSynchronize(dev->stream);
-	if (s->dCounter && dev->pushWatch == s->dCounter + 1)
-		dev->pushWatch = nullptr;
-	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dInsts); cudaFree(s->dMinv);
+	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dGates); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
-	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dChunkDone);
+	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats);
 	{
 		std::lock_guard<std::mutex> g(dev->mtx);
 		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, s->info.device_bytes);
@@ -537,6 +520,7 @@ int lrb_bvh_upload(lrb_device *dev, const lrb_bvh_node *nodes, uint32_t nNodes, 
 	// single-level scenes never change: drop the host copy (the view / info keep the bookkeeping)
 	std::vector<WideNode>().swap(s->host.wide);
 	std::vector<TriRecord>().swap(s->host.tris);
+	std::vector<TriGate>().swap(s->host.gates);
 	*out = s;
 	return LRB_OK;
 }
@@ -563,6 +547,7 @@ int lrb_mbvh_upload(lrb_device *dev, const lrb_mbvh_desc *desc, lrb_scene **out)
 	}
 	// triangles are immutable under Update; the wide nodes / instances stay on the host
 	std::vector<TriRecord>().swap(s->host.tris);
+	std::vector<TriGate>().swap(s->host.gates);
 	s->host.tris.resize(0);
 	*out = s;
 	return LRB_OK;
@@ -683,23 +668,18 @@ static int SortRays(lrb_scene *s, const void *rays, uint32_t n, cudaStream_t str
 	return LRB_OK;
 }
 
-static PersistentKernel PickPersistent(bool two, bool spill, bool push) {
-	if (two) {
-		if (spill) return push ? TracePersistent<true, true, true> : TracePersistent<true, true, false>;
-		return push ? TracePersistent<true, false, true> : TracePersistent<true, false, false>;
-	}
-	if (spill) return push ? TracePersistent<false, true, true> : TracePersistent<false, true, false>;
-	return push ? TracePersistent<false, false, true> : TracePersistent<false, false, false>;
+static PersistentKernel PickPersistent(bool two, bool spill) {
+	if (two)
+		return spill ? TracePersistent<true, true> : TracePersistent<true, false>;
+	return spill ? TracePersistent<false, true> : TracePersistent<false, false>;
 }
 
-static const uint32_t kPushChunkShift = 15;     // 32 768 rays = 640 KiB of RayHit per pushed chunk
-
 static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream,
-		lrb_rayhit *pushDst = nullptr) {
+		lrb_rayhit *hitsPeer = nullptr) {
 	lrb_device *dev = s->dev;
 	if (n == 0)
 		return LRB_OK;
-	if (!rays || (!hits && !stats))
+	if (!rays || (!hits && !hitsPeer && !stats))
 		return Fail(LRB_ERR_INVALID, "null ray/hit buffer");
 	if ((reinterpret_cast<uintptr_t>(rays) & 15u) != 0)
 		return Fail(LRB_ERR_INVALID, "ray buffer must be 16-byte aligned");
@@ -709,6 +689,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.sc = s->view;
 	a.rays = (const lrb_ray *)rays;
 	a.hits = (lrb_rayhit *)hits;
+	a.hitsPeer = hitsPeer;
 	a.rayCount = n;
 	a.counter = s->dCounter;
 	a.stats = s->dStats;
@@ -724,8 +705,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
-		const bool push = pushDst != nullptr;
-		PersistentKernel kernel = PickPersistent(two, spill, push);
+		PersistentKernel kernel = PickPersistent(two, spill);
 		if ((rc = Occupancy(kernel, block, smemBytes, &bps)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
@@ -739,30 +719,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
-		// optional coherence pre-pass (not with the fused push, whose chunks must complete in index order)
-		if (dev->sortRays && !push && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
+		// optional coherence pre-pass
+		if (dev->sortRays && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
-		}
-		if (push) {
-			dev->pushWatch = s->dCounter + 1;
-			// the copier warps must be co-resident with the tracers they wait for: the grid never
-			// exceeds sm * bps resident blocks, and a block needs at least two warps
-			if (block < 64 || grid < 2)
-				return Fail(LRB_ERR_INVALID, "fused push needs block_threads >= 64 and at least two blocks");
-			const size_t nChunks = ((size_t)n >> kPushChunkShift) + 1;
-			if (s->chunkDoneCap < nChunks) {
-				LRB_CUDA(cudaStreamSynchronize(stream));
-				cudaFree(s->dChunkDone);
-				s->dChunkDone = nullptr; s->chunkDoneCap = 0;
-				LRB_CUDA(cudaMalloc((void **)&s->dChunkDone, nChunks * sizeof(uint32_t)));
-				s->chunkDoneCap = nChunks;
-			}
-			LRB_CUDA(cudaMemsetAsync(s->dChunkDone, 0, nChunks * sizeof(uint32_t), stream));
-			a.pushDst = pushDst;
-			a.chunkDone = s->dChunkDone;
-			a.chunkShift = kPushChunkShift;
-			a.nCopiers = (uint32_t)std::min<long long>(dev->pushCopiers, grid / 2);
-			if (a.nCopiers < 1) a.nCopiers = 1;
 		}
 		kernel<<<(unsigned)grid, block, smemBytes, stream>>>(a);
 	} else {
@@ -869,16 +828,12 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 	LRB_SETDEV(dev);
 	if (n == 0)
 		return LRB_OK;
-	if (!rays || !hits || !dst)
+	if (!rays || !dst || (!hits && nChunks != 0))
 		return Fail(LRB_ERR_INVALID, "null buffer");
 	if (nChunks == 0) {
-		// fused: ONE kernel traces and pushes completed 32 768-ray chunks to the gather buffer itself
+		// fused: ONE kernel; every lane stores its RayHit into the local buffer (if any) and into the gather slice
 		if (dst == hits)
 			return LaunchTrace(s, rays, hits, n, false, dev->stream);
-		if (!dev->persistent)
-			return Fail(LRB_ERR_INVALID, "the fused trace + gather kernel is the persistent kernel");
-		if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0 || (reinterpret_cast<uintptr_t>(hits) & 15u) != 0)
-			return Fail(LRB_ERR_INVALID, "hit buffers must be 16-byte aligned for the fused push");
 		return LaunchTrace(s, rays, hits, n, false, dev->stream, (lrb_rayhit *)dst);
 	}
 	if (nChunks > 1024) nChunks = 1024;

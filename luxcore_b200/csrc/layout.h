@@ -71,6 +71,18 @@ struct __attribute__((aligned(64))) TriRecord {
 	uint32_t pad[4];        // 64 B: two 256-bit loads, never straddles a 128-B line
 };
 
+// The reference tests a leaf triangle exactly when the boxes of all its inner ancestors pass, and
+// its Triangle::Intersect can report a "hit" on a triangle the ray does not touch when the ray lies
+// in the triangle's plane (divisor = rounding noise).  The traversal here uses boxes that CONTAIN
+// the reference's, so it may reach such a triangle where the reference never does.  TriGate holds
+// the exact box of the triangle's parent node (the last, and tightest, of the reference's gates --
+// ancestor boxes are unions of their children's, so they pass whenever it does); a hit is accepted
+// only if the reference's own box arithmetic passes it.  Read once per ACCEPTED hit, not per test.
+struct __attribute__((aligned(32))) TriGate {
+	float lo[3], hi[3];
+	uint32_t pad[2];
+};
+
 struct __attribute__((aligned(16))) InstRecord {
 	uint32_t rootWide;      // wide-node index of the leaf tree's root (absolute)
 	uint32_t transformIndex, motionIndex;   // at most one != kNullIndex
@@ -98,6 +110,7 @@ enum {
 
 static_assert(sizeof(WideNode) == 64, "WideNode");
 static_assert(sizeof(TriRecord) == 64, "TriRecord");
+static_assert(sizeof(TriGate) == 32, "TriGate");
 static_assert(sizeof(InstRecord) == 32, "InstRecord");
 static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
 
@@ -105,6 +118,7 @@ static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
 struct SceneView {
 	const WideNode *nodes;
 	const TriRecord *tris;
+	const TriGate *gates;           // one per TriRecord
 	const InstRecord *insts;
 	const float *minv;              // 16 floats per instance transform, row-major
 	const uint32_t *motionFirst;    // per motion system: first / last DevInterp index

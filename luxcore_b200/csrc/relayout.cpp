@@ -235,7 +235,8 @@ static void TriBuildBox(const TriRecord &tr, float lo[3], float hi[3]) {
 }
 
 // Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.
-static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, SlotBoxes *b, WideScene *out) {
+static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, const lrb_bvh_node *parent,
+		SlotBoxes *b, WideScene *out) {
 	const lrb_bvh_node &ch = in.nodes[c];
 	const uint32_t k = b->n++;
 	b->whole[k] = false;
@@ -254,6 +255,14 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 		TriBuildBox(tr, b->lo[k], b->hi[k]);
 		b->child[k] = kTagTri | (uint32_t)out->tris.size();
 		out->tris.push_back(tr);
+		// the reference's gate for this triangle: its parent's exact box (none for a root that is a leaf)
+		TriGate g;
+		memset(&g, 0, sizeof(g));
+		for (int a = 0; a < 3; ++a) {
+			g.lo[a] = parent ? parent->bvhNode.bboxMin[a] : -kInfF;
+			g.hi[a] = parent ? parent->bvhNode.bboxMax[a] : kInfF;
+		}
+		out->gates.push_back(g);
 	}
 }
 
@@ -274,7 +283,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	// The root itself is a leaf (one-triangle mesh / one-mesh dataset): wrap it in a node.
 	if (IsLeaf(nodes[0].nodeData)) {
 		SlotBoxes b;
-		AddSlot(in, wideOf, 0, &b, out);
+		AddSlot(in, wideOf, 0, nullptr, &b, out);
 		WideNode w;
 		QuantizeNode(b, kNullIndex, 0, &w);
 		if (in.instLeaves)
@@ -307,8 +316,10 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	out->wide.resize((size_t)wideStart + nWide);
 	if (in.instLeaves)
 		out->insts.reserve(out->insts.size() + nLeafTotal);
-	else
+	else {
 		out->tris.reserve(out->tris.size() + nLeafTotal);
+		out->gates.reserve(out->gates.size() + nLeafTotal);
+	}
 
 	{
 		SlotBoxes b;
@@ -340,7 +351,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 			b.hasOwn = true;
 			for (int a = 0; a < 3; ++a) { b.ownLo[a] = nodes[i].bvhNode.bboxMin[a]; b.ownHi[a] = nodes[i].bvhNode.bboxMax[a]; }
 			for (uint32_t k = 0; k < cnt; ++k)
-				AddSlot(in, wideOf, kids[first + k], &b, out);
+				AddSlot(in, wideOf, kids[first + k], &nodes[i], &b, out);
 			QuantizeNode(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
 		}
 	}

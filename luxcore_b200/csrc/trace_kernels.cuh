@@ -131,11 +131,11 @@ struct TraceArgs {
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	TraceStats *stats;          // STATS kernels only
-	// fused RayHit push (PUSH kernels): see TracePersistent
-	lrb_rayhit *pushDst;        // this rank's slice of the gather buffer (peer-mapped over NVLink)
-	uint32_t *chunkDone;        // retired-ray counters, one per chunk of (1 << chunkShift) rays (zeroed before launch)
-	uint32_t chunkShift;
-	uint32_t nCopiers;          // warp 0 of blocks [0, nCopiers) pushes completed chunks instead of tracing
+	// Multi-GPU gather fused into the trace: when set, every RayHit record is ALSO stored here -- this
+	// rank's slice of the gather buffer on the destination GPU, peer-mapped over NVLink.  The five
+	// 4-byte stores per ray are posted writes that ride along with the traversal (measured: no change
+	// in kernel time at 57 GB/s of RayHit payload), so no copy pass / collective follows the kernel.
+	lrb_rayhit *hitsPeer;
 };
 
 __device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray &r) {
@@ -147,9 +147,7 @@ __device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray
 	r.time = c.x; r.flags = __float_as_uint(c.y);
 }
 
-__device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const RayState &s, float rayMaxt) {
-	lrb_rayhit h;
-	WriteHit(s, rayMaxt, &h);
+__device__ __forceinline__ void StoreHitTo(lrb_rayhit *hits, uint32_t i, const lrb_rayhit &h) {
 	// 20-B records are only 4-B aligned: five scalar stores
 	float *p = reinterpret_cast<float *>(hits + i);
 	p[0] = h.t; p[1] = h.b1; p[2] = h.b2;
@@ -157,101 +155,33 @@ __device__ __forceinline__ void StoreHit(lrb_rayhit *hits, uint32_t i, const Ray
 	reinterpret_cast<uint32_t *>(p)[4] = h.triangleIndex;
 }
 
+__device__ __forceinline__ void StoreHit(const TraceArgs &a, uint32_t i, const RayState &s, float rayMaxt) {
+	lrb_rayhit h;
+	WriteHit(s, rayMaxt, &h);
+	if (a.hits)
+		StoreHitTo(a.hits, i, h);
+	if (a.hitsPeer)
+		StoreHitTo(a.hitsPeer, i, h);
+}
+
+// A masked ray's RayHit is left untouched (bvh.cl:242-244); the gather slice must still end up equal
+// to the local buffer, so the record is forwarded as it is.
+__device__ __forceinline__ void ForwardMaskedHit(const TraceArgs &a, uint32_t i) {
+	if (a.hits && a.hitsPeer) {
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(a.hits + i);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(a.hitsPeer + i);
+#pragma unroll
+		for (int k = 0; k < 5; ++k)
+			dst[k] = src[k];
+	}
+}
+
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-// Retired rays (hit written, or masked) are counted into their chunk of the local RayHit buffer.
-// Each lane accumulates (chunk, count) locally; the counts are published once per warp every few
-// re-fill rounds with RELEASE semantics (one MEMBAR.GPU for many rays: __syncwarp orders every
-// lane's RayHit stores before the leader's release), so a copier warp that ACQUIRES the full count
-// sees every RayHit of the chunk.
-struct RetireState {
-	uint32_t chunk, count;
-};
-
-__device__ __forceinline__ void RetireRay(const TraceArgs &a, RetireState &rs, const uint32_t idx) {
-	const uint32_t c = idx >> a.chunkShift;
-	if (rs.count && c != rs.chunk) {
-		// crossed a chunk boundary before the warp published: release this lane's own count now
-		asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.chunkDone + rs.chunk), "r"(rs.count) : "memory");
-		rs.count = 0;
-	}
-	rs.chunk = c;
-	rs.count += 1;
-}
-
-__device__ __forceinline__ void PublishRetired(const TraceArgs &a, const uint32_t lane, RetireState &rs) {
-	__syncwarp();
-	unsigned todo = __ballot_sync(0xffffffffu, rs.count != 0);
-	while (todo) {
-		const int src = __ffs(todo) - 1;
-		const uint32_t c = __shfl_sync(0xffffffffu, rs.chunk, src);
-		const bool mine = rs.count != 0 && rs.chunk == c;
-		const unsigned same = __ballot_sync(0xffffffffu, mine);
-		const uint32_t cnt = __reduce_add_sync(0xffffffffu, mine ? rs.count : 0u);
-		if ((int)lane == src)
-			asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.chunkDone + c), "r"(cnt) : "memory");
-		if (mine)
-			rs.count = 0;
-		todo &= ~same;
-	}
-}
-
-// Copier warp of the fused trace + gather kernel: waits for chunks of the local RayHit buffer to
-// complete and streams them into the gather buffer on the destination GPU with 16-byte stores over
-// NVLink, while the other warps keep tracing.  Chunks complete roughly in index order because ray
-// indices are handed out in increasing order.
-__device__ __forceinline__ void CopierLoop(const TraceArgs &a, const uint32_t copier, const uint32_t lane) {
-	const uint32_t chunkRays = 1u << a.chunkShift;
-	const uint32_t nChunks = (a.rayCount + chunkRays - 1) >> a.chunkShift;
-	for (uint32_t c = copier; c < nChunks; c += a.nCopiers) {
-		const uint32_t first = c << a.chunkShift;
-		const uint32_t cnt = min(chunkRays, a.rayCount - first);
-		// bounded wait (~8 s): a chunk that never completes is a bug, not a reason to hang the GPU;
-		// the watchdog word is checked by the host at the next lrb_sync
-		bool ok = false;
-		for (uint32_t spin = 0; spin < (1u << 21); ++spin) {
-			uint32_t done;
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.chunkDone + c) : "memory");
-			if (done >= cnt) { ok = true; break; }
-			__nanosleep(4096);
-		}
-		if (!ok) {
-			if (lane == 0)
-				atomicExch(a.counter + 1, 0xdeadu);
-			return;
-		}
-		// 20-B records, chunk starts are multiples of 4 rays => 16-B aligned byte ranges
-		const size_t bytes = (size_t)cnt * sizeof(lrb_rayhit);
-		const uint4 *src = reinterpret_cast<const uint4 *>(a.hits + first);
-		uint4 *dst = reinterpret_cast<uint4 *>(a.pushDst + first);
-		const uint32_t nVec = (uint32_t)(bytes / 16);
-		uint32_t i = lane;
-		for (; i + 7 * 32 < nVec; i += 8 * 32) {
-			uint4 v[8];
-#pragma unroll
-			for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + i + k * 32);    // L2 (written by other SMs)
-#pragma unroll
-			for (int k = 0; k < 8; ++k) dst[i + k * 32] = v[k];
-		}
-		for (; i < nVec; i += 32)
-			dst[i] = __ldcg(src + i);
-		// tail of a last chunk whose ray count is not a multiple of 4
-		const uint32_t tailWords = (uint32_t)((bytes - (size_t)nVec * 16) / 4);
-		if (lane < tailWords)
-			reinterpret_cast<uint32_t *>(dst + nVec)[lane] = __ldcg(reinterpret_cast<const uint32_t *>(src + nVec) + lane);
-	}
-}
-
-template <bool TWO_LEVEL, bool SPILL, bool PUSH>
+template <bool TWO_LEVEL, bool SPILL>
 __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
-	if (PUSH) {
-		if ((threadIdx.x >> 5) == 0 && blockIdx.x < a.nCopiers) {
-			CopierLoop(a, blockIdx.x, lane);
-			return;
-		}
-	}
 	const uint32_t totalThreads = gridDim.x * kTraceBlock;
 	const uint32_t gtid = blockIdx.x * kTraceBlock + threadIdx.x;
 
@@ -264,27 +194,19 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 	RayState s;
 	uint32_t rayIdx = 0;
 	float rayMaxt = 0.f;
-	bool active = false;            // the lane holds a ray that is still being traversed
-	bool unsaved = false;           // the lane holds a finished ray whose RayHit is not stored yet
-	bool exhausted = false;
-	RetireState rs;                 // PUSH: rays this lane retired since the last publication
-	rs.chunk = 0; rs.count = 0;
-	uint32_t round = 0;
+	// lane state: kIdle (nothing), kActive (traversing), kUnsaved (finished, RayHit not stored yet)
+	enum { kIdle = 0, kActive = 1, kUnsaved = 2 };
+	int state = kIdle;
+	int exhausted = 0;
 
 	for (;;) {
 		// ---- finished lanes store their RayHit (all of them in the same instructions) ----
-		if (unsaved) {
-			StoreHit(a.hits, rayIdx, s, rayMaxt);
-			if (PUSH)
-				RetireRay(a, rs, rayIdx);
-			unsaved = false;
-		}
-		if (PUSH) {
-			if (exhausted || (++round & 3u) == 0)
-				PublishRetired(a, lane, rs);
+		if (state == kUnsaved) {
+			StoreHit(a, rayIdx, s, rayMaxt);
+			state = kIdle;
 		}
 		// ---- re-fill idle lanes ----
-		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		const unsigned idle = __ballot_sync(0xffffffffu, state == kIdle);
 		if (!exhausted && idle) {
 			const int nIdle = __popc(idle);
 			const int leader = __ffs(idle) - 1;
@@ -292,7 +214,7 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 			if ((int)lane == leader)
 				base = atomicAdd(a.counter, (uint32_t)nIdle);
 			base = __shfl_sync(0xffffffffu, base, leader);
-			if (!active) {
+			if (state == kIdle) {
 				const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
 				if (slot < a.rayCount) {
 					const uint32_t idx = a.perm ? __ldg(a.perm + slot) : slot;
@@ -304,44 +226,42 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 						rayMaxt = r.maxt;
 						if (InitRay(a.sc, r, s)) {
 							stk.reset();
-							active = true;
+							state = kActive;
 						} else
-							StoreHit(a.hits, idx, s, rayMaxt);  // empty scene: miss
-					}
-					if (PUSH && !active)        // masked ray, or answered without traversal
-						RetireRay(a, rs, idx);
+							StoreHit(a, idx, s, rayMaxt);   // empty scene: miss
+					} else
+						ForwardMaskedHit(a, idx);
 				}
 			}
 			if (base + (uint32_t)nIdle >= a.rayCount)
-				exhausted = true;
+				exhausted = 1;
 		}
-		if (__ballot_sync(0xffffffffu, active) == 0) {
-			if (exhausted) {
-				if (PUSH)
-					PublishRetired(a, lane, rs);    // e.g. trailing masked rays
+		if (__ballot_sync(0xffffffffu, state == kActive) == 0) {
+			if (exhausted)
 				break;
-			}
 			continue;
 		}
 
 		// ---- traverse until too few lanes are alive ----
-		// Every iteration first lets the lanes that ran out of work pop their stack (Resolve), then the
-		// warp runs ONE of two branch-free phases, whichever has more lanes ready: a node phase (fetch
-		// a 128-B node / four box tests / ordered push) or a triangle phase (one triangle per lane).
-		// A lane holding a triangle reference waits for a triangle phase; batching the two kinds of
-		// work keeps lanes converged on incoherent rays instead of serialising them against each other.
+		// Every iteration first lets the lanes that ran out of work pop their stack until they hold an
+		// entry that is still worth visiting (Resolve; an empty stack finishes the ray), then the warp
+		// runs ONE of two branch-free phases, whichever has more lanes ready: a node phase (fetch a 64-B
+		// node / four box tests / ordered push) or a triangle phase (one triangle per lane).  A lane
+		// holding a triangle reference waits for a triangle phase; batching the two kinds of work keeps
+		// lanes converged on incoherent rays instead of serialising them against each other.
+		// (Measured alternatives, both slower on incoherent rays: one converged pop attempt per
+		// iteration, and pops inside the phases -- lanes whose popped entry is culled then idle a phase.)
 		const int floorLanes = exhausted ? 1 : (int)a.refillBelow;
 		int nLive;
 		do {
-			if (active && NeedsResolve<TWO_LEVEL>(s.cur)) {
-				if (!Resolve<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr)) {
-					active = false;
-					unsaved = true;
-				}
+			if (state == kActive && NeedsResolve<TWO_LEVEL>(s.cur)) {
+				if (!Resolve<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr))
+					state = kUnsaved;
 			}
 			__syncwarp();
-			const bool wantTri = active && (s.cur & kTagTri) != 0;
-			const bool wantNode = active && (s.cur & kTagTri) == 0;
+			const bool ready = state == kActive;
+			const bool wantTri = ready && (s.cur & kTagTri) != 0;
+			const bool wantNode = ready && (s.cur & kTagTri) == 0;
 			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
 			const int nNode = __popc(__ballot_sync(0xffffffffu, wantNode));
 			if (nTri * (int)a.triBias >= nNode * 4) {
@@ -416,8 +336,7 @@ __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 		if (InitRay(a.sc, r, s)) {
 			while (Step<TWO_LEVEL, STATS>(a.sc, a.rays[i], s, stk, &local)) { }
 		}
-		if (a.hits)
-			StoreHit(a.hits, i, s, r.maxt);
+		StoreHit(a, i, s, r.maxt);
 	}
 	if (STATS) {
 		atomicAdd(&a.stats->wideNodes, local.wideNodes);

@@ -429,13 +429,28 @@ LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, S
 	return alive;
 }
 
+// One pop attempt (warp-converged form of Resolve's inner loop for the persistent kernel): takes the
+// top entry; an entry behind the best hit leaves s.cur empty (the lane tries again at the next
+// attempt).  Returns false when the stack was empty, i.e. the ray is finished.
+template <class STACK>
+LRB_HD bool PopOnce(RayState &s, STACK &stk) {
+	if (stk.empty())
+		return false;
+	uint32_t c;
+	float t0;
+	stk.pop(c, t0);
+	s.cur = (t0 > s.maxt) ? kNullIndex : c;
+	return true;
+}
+
 // Tests the triangle s.cur refers to.
 //   accept: strictly closer, or exactly as close as the current hit but earlier in the reference's
 //   depth-first array (so a hit at exactly t == ray.maxt is rejected while nothing was hit yet,
 //   like the reference's `t < rayHit->t` against the initial rayHit->t = maxt).
 template <bool TWO_LEVEL, bool STATS>
 LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
-	const char *tp = reinterpret_cast<const char *>(sc.tris + (s.cur & kRefIndexMask));
+	const uint32_t triIndex = s.cur & kRefIndexMask;
+	const char *tp = reinterpret_cast<const char *>(sc.tris + triIndex);
 	s.cur = kNullIndex;
 	const F8 a = Ld256(tp), b = Ld256(tp + 32);    // p0 p1 p2.xy | p2.z mesh tri order pad
 	if (STATS) stats->triangles++;
@@ -447,6 +462,12 @@ LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
 	const bool tieWin = (t == s.maxt) & (s.hitMesh != kNullIndex) &
 			((instOrder < s.bestInst) | ((instOrder == s.bestInst) & (order < s.bestTri)));
 	if (hit & (closer | tieWin)) {
+		// the reference's gate (layout.h TriGate): its parent's exact box with the reference's own
+		// arithmetic.  A genuine hit always passes (the hit point is inside the triangle's grown box).
+		const F8 g = Ld256(sc.gates + triIndex);
+		const float ge = ChildEntry(s, s.ix < 0.f, s.iy < 0.f, s.iz < 0.f, g.v[0], g.v[1], g.v[2], g.v[3], g.v[4], g.v[5]);
+		if (!(ge < LRB_INF))
+			return;
 		s.maxt = t;
 		s.b1 = b1; s.b2 = b2;
 		s.hitMesh = TWO_LEVEL ? (mesh + s.curMeshOffset) : mesh;

@@ -35,6 +35,7 @@ static SceneView View(const WideScene &w) {
 	memset(&v, 0, sizeof(v));
 	v.nodes = w.wide.data();
 	v.tris = w.tris.data();
+	v.gates = w.gates.data();
 	v.insts = w.insts.data();
 	v.minv = w.minv.data();
 	v.motionFirst = w.motionFirst.data();
