@@ -5,6 +5,7 @@
 // (bvhaccelhw.cpp:38-237, mbvhaccelhw.cpp:41-306,308-466) and their kernel launches
 // (bvhaccelhw.cpp:259-268, mbvhaccelhw.cpp:468-507).  No NVRTC, no cuew, no OptiX.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -58,6 +59,9 @@ struct lrb_device {
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
 	int triBias;
+	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
+	int gatherChunkShift;           // log2(rays per signalled chunk)
+	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
 	int sortRays;                   // 1 = order the rays of a batch for coherence before tracing them
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
 	int sortMinRays;                // batches smaller than this are traced in index order
@@ -88,6 +92,9 @@ struct lrb_scene {
 	float *dSpillT;
 	size_t spillEntries;
 	TraceStats *dStats;
+	uint32_t *dChunkDone, *dChunkFlag;  // signalled gather: retired-ray counters / completion flags per chunk
+	size_t chunkCap;
+	uint32_t epoch;
 	SceneView view;
 	lrb_scene_info info;
 };
@@ -158,6 +165,9 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->refillBelow = 24;
 	dev->triBias = 8;
 	dev->sortRays = 0;
+	dev->wideStores = 2;
+	dev->gatherStores = 0;
+	dev->gatherChunkShift = 20;
 	dev->sortBitsPerAxis = 5;
 	dev->sortMinRays = 1 << 18;
 	dev->sortKeys[0] = dev->sortKeys[1] = dev->sortVals[0] = dev->sortVals[1] = nullptr;
@@ -236,6 +246,14 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "tri_bias") {
 		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
 		dev->triBias = iv;
+	} else if (k == "gather_stores") {
+		dev->gatherStores = iv ? 1 : 0;
+	} else if (k == "gather_chunk_shift") {
+		if (iv < 12 || iv > 28) return Fail(LRB_ERR_INVALID, "gather_chunk_shift must be 12..28");
+		dev->gatherChunkShift = iv;
+	} else if (k == "wide_stores") {
+		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
+		dev->wideStores = iv;
 	} else if (k == "sort_rays") {
 		dev->sortRays = iv ? 1 : 0;
 	} else if (k == "sort_bits") {
@@ -472,6 +490,7 @@ static lrb_scene *NewScene(lrb_device *dev) {
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
 	s->dStats = nullptr;
+	s->dChunkDone = s->dChunkFlag = nullptr; s->chunkCap = 0; s->epoch = 0;
 	memset(&s->view, 0, sizeof(s->view));
 	memset(&s->info, 0, sizeof(s->info));
 	return s;
@@ -487,7 +506,7 @@ int lrb_scene_free(lrb_scene *s) {
 	cudaStreamSynchronize(dev->stream);
 	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dGates); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
-	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats);
+	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dChunkDone); cudaFree(s->dChunkFlag);
 	{
 		std::lock_guard<std::mutex> g(dev->mtx);
 		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, s->info.device_bytes);
@@ -668,14 +687,38 @@ static int SortRays(lrb_scene *s, const void *rays, uint32_t n, cudaStream_t str
 	return LRB_OK;
 }
 
-static PersistentKernel PickPersistent(bool two, bool spill) {
-	if (two)
-		return spill ? TracePersistent<true, true> : TracePersistent<true, false>;
-	return spill ? TracePersistent<false, true> : TracePersistent<false, false>;
+static PersistentKernel PickPersistent(bool two, bool spill, bool signal) {
+	if (two) {
+		if (spill) return signal ? TracePersistent<true, true, true> : TracePersistent<true, true, false>;
+		return signal ? TracePersistent<true, false, true> : TracePersistent<true, false, false>;
+	}
+	if (spill) return signal ? TracePersistent<false, true, true> : TracePersistent<false, true, false>;
+	return signal ? TracePersistent<false, false, true> : TracePersistent<false, false, false>;
+}
+
+// Driver entry points for stream-ordered memory operations, resolved at run time (the library does
+// not link against libcuda, so that it also loads on a machine without a driver).
+typedef CUresult (*PFN_StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*PFN_MemsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstream);
+static PFN_StreamWaitValue32 g_streamWaitValue32 = nullptr;
+static PFN_MemsetD32Async g_memsetD32Async = nullptr;
+
+static int ResolveDriverEntryPoints() {
+	if (g_streamWaitValue32 && g_memsetD32Async)
+		return LRB_OK;
+	void *f0 = nullptr, *f1 = nullptr;
+	cudaDriverEntryPointQueryResult q0, q1;
+	LRB_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &f0, cudaEnableDefault, &q0));
+	LRB_CUDA(cudaGetDriverEntryPoint("cuMemsetD32Async", &f1, cudaEnableDefault, &q1));
+	if (!f0 || !f1 || q0 != cudaDriverEntryPointSuccess || q1 != cudaDriverEntryPointSuccess)
+		return Fail(LRB_ERR_CUDA, "driver entry points for stream memory operations are not available");
+	g_streamWaitValue32 = (PFN_StreamWaitValue32)f0;
+	g_memsetD32Async = (PFN_MemsetD32Async)f1;
+	return LRB_OK;
 }
 
 static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream,
-		lrb_rayhit *hitsPeer = nullptr) {
+		lrb_rayhit *hitsPeer = nullptr, bool signal = false) {
 	lrb_device *dev = s->dev;
 	if (n == 0)
 		return LRB_OK;
@@ -690,6 +733,10 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.rays = (const lrb_ray *)rays;
 	a.hits = (lrb_rayhit *)hits;
 	a.hitsPeer = hitsPeer;
+	// vector stores: off for the local buffer (the four-way switch costs more than it saves there),
+	// optional for the peer buffer
+	a.hitFlags = ((dev->wideStores & 1) && (reinterpret_cast<uintptr_t>(hits) & 15u) == 0 ? 1u : 0u) |
+			((dev->wideStores & 2) && (reinterpret_cast<uintptr_t>(hitsPeer) & 15u) == 0 ? 2u : 0u);
 	a.rayCount = n;
 	a.counter = s->dCounter;
 	a.stats = s->dStats;
@@ -705,7 +752,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
-		PersistentKernel kernel = PickPersistent(two, spill);
+		PersistentKernel kernel = PickPersistent(two, spill, signal);
 		if ((rc = Occupancy(kernel, block, smemBytes, &bps)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
@@ -722,6 +769,24 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		// optional coherence pre-pass
 		if (dev->sortRays && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
+		}
+		if (signal) {
+			const size_t nChunks = ((size_t)n >> dev->gatherChunkShift) + 1;
+			if (s->chunkCap < nChunks) {
+				LRB_CUDA(cudaStreamSynchronize(stream));
+				cudaFree(s->dChunkDone); cudaFree(s->dChunkFlag);
+				s->dChunkDone = s->dChunkFlag = nullptr; s->chunkCap = 0;
+				LRB_CUDA(cudaMalloc((void **)&s->dChunkDone, nChunks * sizeof(uint32_t)));
+				LRB_CUDA(cudaMalloc((void **)&s->dChunkFlag, nChunks * sizeof(uint32_t)));
+				LRB_CUDA(cudaMemset(s->dChunkFlag, 0, nChunks * sizeof(uint32_t)));
+				s->chunkCap = nChunks;
+				s->epoch = 0;
+			}
+			LRB_CUDA(cudaMemsetAsync(s->dChunkDone, 0, nChunks * sizeof(uint32_t), stream));
+			a.chunkDone = s->dChunkDone;
+			a.chunkFlag = s->dChunkFlag;
+			a.chunkShift = (uint32_t)dev->gatherChunkShift;
+			a.epoch = ++s->epoch;
 		}
 		kernel<<<(unsigned)grid, block, smemBytes, stream>>>(a);
 	} else {
@@ -831,10 +896,44 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 	if (!rays || !dst || (!hits && nChunks != 0))
 		return Fail(LRB_ERR_INVALID, "null buffer");
 	if (nChunks == 0) {
-		// fused: ONE kernel; every lane stores its RayHit into the local buffer (if any) and into the gather slice
 		if (dst == hits)
 			return LaunchTrace(s, rays, hits, n, false, dev->stream);
-		return LaunchTrace(s, rays, hits, n, false, dev->stream, (lrb_rayhit *)dst);
+		if (dev->gatherStores || !hits || !dev->persistent) {
+			// ONE kernel; every lane stores its RayHit into the local buffer (if any) and into the gather slice
+			return LaunchTrace(s, rays, hits, n, false, dev->stream, (lrb_rayhit *)dst);
+		}
+		// ONE kernel + signalled pushes: the kernel raises a flag per completed chunk of ray indices; the
+		// copy stream waits on each flag (stream-ordered, no host involvement) and pushes that chunk of
+		// the RayHit buffer with the copy engine while the kernel keeps tracing.
+		int rc = ResolveDriverEntryPoints();
+		if (rc != LRB_OK)
+			return rc;
+		while (dev->events.size() < 2) {
+			cudaEvent_t e;
+			LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			dev->events.push_back(e);
+		}
+		// the copy stream starts after everything queued so far (previous readers of dst / hits)
+		LRB_CUDA(cudaEventRecord(dev->events[0], dev->stream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, dev->events[0], 0));
+		if ((rc = LaunchTrace(s, rays, hits, n, false, dev->stream, nullptr, true)) != LRB_OK)
+			return rc;
+		const uint32_t epoch = s->epoch;
+		const uint32_t chunkRays = 1u << dev->gatherChunkShift;
+		const uint32_t nC = (n + chunkRays - 1) >> dev->gatherChunkShift;
+		// safety net: once the kernel has finished every flag is raised, whatever happened inside it
+		if (g_memsetD32Async((CUdeviceptr)(uintptr_t)s->dChunkFlag, epoch, nC, (CUstream)dev->stream) != CUDA_SUCCESS)
+			return Fail(LRB_ERR_CUDA, "cuMemsetD32Async failed");
+		for (uint32_t c = 0; c < nC; ++c) {
+			const uint32_t first = c << dev->gatherChunkShift, cnt = std::min(chunkRays, n - first);
+			if (g_streamWaitValue32((CUstream)dev->copyOutStream, (CUdeviceptr)(uintptr_t)(s->dChunkFlag + c), epoch, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+				return Fail(LRB_ERR_CUDA, "cuStreamWaitValue32 failed");
+			LRB_CUDA(cudaMemcpyAsync((lrb_rayhit *)dst + first, (lrb_rayhit *)hits + first, (size_t)cnt * sizeof(lrb_rayhit),
+					cudaMemcpyDefault, dev->copyOutStream));
+		}
+		LRB_CUDA(cudaEventRecord(dev->events[1], dev->copyOutStream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, dev->events[1], 0));
+		return LRB_OK;
 	}
 	if (nChunks > 1024) nChunks = 1024;
 	// chunk boundaries on multiples of 4 rays keep every RayHit range 16-byte aligned (4 x 20 B)

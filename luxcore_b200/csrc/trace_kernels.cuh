@@ -136,6 +136,15 @@ struct TraceArgs {
 	// 4-byte stores per ray are posted writes that ride along with the traversal (measured: no change
 	// in kernel time at 57 GB/s of RayHit payload), so no copy pass / collective follows the kernel.
 	lrb_rayhit *hitsPeer;
+	uint32_t hitFlags;          // bit 0: hits is 16-byte aligned, bit 1: hitsPeer is 16-byte aligned
+	// Chunk-completion signalling (SIGNAL kernels): rays retired per chunk of (1 << chunkShift) ray
+	// indices; the warp that completes a chunk publishes `epoch` in chunkFlag[chunk], on which a copy
+	// stream waits (cuStreamWaitValue32) before it pushes that chunk of the RayHit buffer with the
+	// copy engine -- the gather overlaps the rest of the traversal, in full-size NVLink packets.
+	uint32_t *chunkDone;        // zeroed before launch
+	uint32_t *chunkFlag;
+	uint32_t chunkShift;
+	uint32_t epoch;
 };
 
 __device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray &r) {
@@ -147,21 +156,46 @@ __device__ __forceinline__ void LoadRay(const lrb_ray *rays, uint32_t i, lrb_ray
 	r.time = c.x; r.flags = __float_as_uint(c.y);
 }
 
-__device__ __forceinline__ void StoreHitTo(lrb_rayhit *hits, uint32_t i, const lrb_rayhit &h) {
-	// 20-B records are only 4-B aligned: five scalar stores
-	float *p = reinterpret_cast<float *>(hits + i);
-	p[0] = h.t; p[1] = h.b1; p[2] = h.b2;
-	reinterpret_cast<uint32_t *>(p)[3] = h.meshIndex;
-	reinterpret_cast<uint32_t *>(p)[4] = h.triangleIndex;
+// 20-byte records are only 4-byte aligned, but with a 16-byte aligned buffer the alignment of record
+// i is known from i & 3: two or three vector stores cover it instead of five scalar ones (fewer
+// store instructions, and fewer, larger write packets when the buffer is peer memory over NVLink).
+__device__ __forceinline__ void StoreHitTo(lrb_rayhit *hits, uint32_t i, const lrb_rayhit &h, const bool aligned16) {
+	char *p = reinterpret_cast<char *>(hits + i);
+	const uint32_t w0 = __float_as_uint(h.t), w1 = __float_as_uint(h.b1), w2 = __float_as_uint(h.b2), w3 = h.meshIndex, w4 = h.triangleIndex;
+	if (!aligned16) {
+		uint32_t *q = reinterpret_cast<uint32_t *>(p);
+		q[0] = w0; q[1] = w1; q[2] = w2; q[3] = w3; q[4] = w4;
+		return;
+	}
+	switch (i & 3u) {
+	case 0:     // offset 0 mod 16
+		*reinterpret_cast<uint4 *>(p) = make_uint4(w0, w1, w2, w3);
+		*reinterpret_cast<uint32_t *>(p + 16) = w4;
+		break;
+	case 1:     // offset 4 mod 16
+		*reinterpret_cast<uint32_t *>(p) = w0;
+		*reinterpret_cast<uint2 *>(p + 4) = make_uint2(w1, w2);
+		*reinterpret_cast<uint2 *>(p + 12) = make_uint2(w3, w4);
+		break;
+	case 2:     // offset 8 mod 16
+		*reinterpret_cast<uint2 *>(p) = make_uint2(w0, w1);
+		*reinterpret_cast<uint2 *>(p + 8) = make_uint2(w2, w3);
+		*reinterpret_cast<uint32_t *>(p + 16) = w4;
+		break;
+	default:    // offset 12 mod 16
+		*reinterpret_cast<uint32_t *>(p) = w0;
+		*reinterpret_cast<uint4 *>(p + 4) = make_uint4(w1, w2, w3, w4);
+		break;
+	}
 }
 
 __device__ __forceinline__ void StoreHit(const TraceArgs &a, uint32_t i, const RayState &s, float rayMaxt) {
 	lrb_rayhit h;
 	WriteHit(s, rayMaxt, &h);
 	if (a.hits)
-		StoreHitTo(a.hits, i, h);
+		StoreHitTo(a.hits, i, h, (a.hitFlags & 1u) != 0);
 	if (a.hitsPeer)
-		StoreHitTo(a.hitsPeer, i, h);
+		StoreHitTo(a.hitsPeer, i, h, (a.hitFlags & 2u) != 0);
 }
 
 // A masked ray's RayHit is left untouched (bvh.cl:242-244); the gather slice must still end up equal
@@ -178,7 +212,54 @@ __device__ __forceinline__ void ForwardMaskedHit(const TraceArgs &a, uint32_t i)
 
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-template <bool TWO_LEVEL, bool SPILL>
+// SIGNAL kernels count retired rays (RayHit stored, or masked) per chunk.  Each lane accumulates
+// (chunk, count); a warp publishes its counts every few re-fill rounds: __syncwarp orders every
+// lane's RayHit stores before the leader's fence, the fence makes them visible device-wide before
+// the counter moves, and whoever brings a counter to the chunk's size raises the chunk's flag.
+struct RetireState {
+	uint32_t chunk, count;
+};
+
+__device__ __forceinline__ void SignalChunk(const TraceArgs &a, const uint32_t c, const uint32_t cnt) {
+	__threadfence();
+	const uint32_t old = atomicAdd(a.chunkDone + c, cnt);
+	const uint32_t first = c << a.chunkShift;
+	const uint32_t size = min(1u << a.chunkShift, a.rayCount - first);
+	if (old + cnt == size) {
+		__threadfence();
+		atomicExch(a.chunkFlag + c, a.epoch);
+	}
+}
+
+__device__ __forceinline__ void RetireRay(const TraceArgs &a, RetireState &rs, const uint32_t idx) {
+	const uint32_t c = idx >> a.chunkShift;
+	if (rs.count && c != rs.chunk) {
+		// crossed a chunk boundary before the warp published: this lane's own stores are ordered by its own fence
+		SignalChunk(a, rs.chunk, rs.count);
+		rs.count = 0;
+	}
+	rs.chunk = c;
+	rs.count += 1;
+}
+
+__device__ __forceinline__ void PublishRetired(const TraceArgs &a, const uint32_t lane, RetireState &rs) {
+	__syncwarp();
+	unsigned todo = __ballot_sync(0xffffffffu, rs.count != 0);
+	while (todo) {
+		const int src = __ffs(todo) - 1;
+		const uint32_t c = __shfl_sync(0xffffffffu, rs.chunk, src);
+		const bool mine = rs.count != 0 && rs.chunk == c;
+		const unsigned same = __ballot_sync(0xffffffffu, mine);
+		const uint32_t cnt = __reduce_add_sync(0xffffffffu, mine ? rs.count : 0u);
+		if ((int)lane == src)
+			SignalChunk(a, c, cnt);
+		if (mine)
+			rs.count = 0;
+		todo &= ~same;
+	}
+}
+
+template <bool TWO_LEVEL, bool SPILL, bool SIGNAL>
 __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
@@ -198,12 +279,21 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 	enum { kIdle = 0, kActive = 1, kUnsaved = 2 };
 	int state = kIdle;
 	int exhausted = 0;
+	RetireState rs;                 // SIGNAL: rays this lane retired since the last publication
+	rs.chunk = 0; rs.count = 0;
+	uint32_t round = 0;
 
 	for (;;) {
 		// ---- finished lanes store their RayHit (all of them in the same instructions) ----
 		if (state == kUnsaved) {
 			StoreHit(a, rayIdx, s, rayMaxt);
+			if (SIGNAL)
+				RetireRay(a, rs, rayIdx);
 			state = kIdle;
+		}
+		if (SIGNAL) {
+			if (exhausted || (++round & 15u) == 0)
+				PublishRetired(a, lane, rs);
 		}
 		// ---- re-fill idle lanes ----
 		const unsigned idle = __ballot_sync(0xffffffffu, state == kIdle);
@@ -231,14 +321,19 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 							StoreHit(a, idx, s, rayMaxt);   // empty scene: miss
 					} else
 						ForwardMaskedHit(a, idx);
+					if (SIGNAL && state != kActive)     // masked ray, or answered without traversal
+						RetireRay(a, rs, idx);
 				}
 			}
 			if (base + (uint32_t)nIdle >= a.rayCount)
 				exhausted = 1;
 		}
 		if (__ballot_sync(0xffffffffu, state == kActive) == 0) {
-			if (exhausted)
+			if (exhausted) {
+				if (SIGNAL)
+					PublishRetired(a, lane, rs);    // e.g. trailing masked rays
 				break;
+			}
 			continue;
 		}
 

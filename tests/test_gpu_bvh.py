@@ -79,11 +79,16 @@ def test_masked_rays_leave_hits_untouched(dev):
     scene.free()
 
 
-@pytest.mark.parametrize("chunks", [0, 1, 5])
+@pytest.mark.parametrize("chunks", [0, -1, 1, 5])
 @pytest.mark.parametrize("n", [1000, 32768 * 3 + 1234, 500000])
 def test_trace_gather_pushes_every_hit(dev, chunks, n):
-    """lrb_trace_gather (fused in-kernel push for chunks == 0, copy-engine push otherwise): the gather
-    slice must end up byte-identical to the local RayHit buffer, including masked rays' records."""
+    """lrb_trace_gather: chunks == 0 -> one kernel + copy-engine pushes triggered by the kernel's
+    chunk-completion flags (here with 16 Ki-ray chunks so that several are in flight); chunks == -1 ->
+    one kernel with dual-destination RayHit stores; chunks >= 1 -> chunked launches + copy engine.
+    The gather slice must end up byte-identical to the local RayHit buffer, masked rays' records included."""
+    dev.set_option("gather_stores", "1" if chunks < 0 else "0")
+    dev.set_option("gather_chunk_shift", "14")
+    chunks = max(chunks, 0)
     desc = S.load_fixture("kitchen")
     osc = H.oracle_scene(desc)
     bvh = O.BVH(osc)
@@ -113,6 +118,8 @@ def test_trace_gather_pushes_every_hit(dev, chunks, n):
     for p in (d_rays, d_hits, d_dst):
         dev.free(p)
     scene.free()
+    dev.set_option("gather_stores", "0")
+    dev.set_option("gather_chunk_shift", "20")
 
 
 @pytest.mark.parametrize("name,n,bits", [("kitchen", 600000, 5), ("cornell", 300000, 3), ("bigmonkey", 400000, 9)])
@@ -168,4 +175,37 @@ def test_bvh_grazing_rays_match_oracle(dev, name, tree_type, n):
     rep = H.compare_hits(got, ref, rays, what="grazing %s k=%d" % (name, tree_type))
     assert rep["hits"] > 0.3 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
+
+
+@pytest.mark.parametrize("offset", [0, 4, 8, 12])
+def test_hit_buffer_alignment(dev, offset):
+    """RayHit records are written with alignment-dependent vector stores when the buffer is 16-byte
+    aligned and with scalar stores otherwise: every byte offset must give the same records."""
+    desc = S.load_fixture("bigmonkey")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    n = 50001
+    rays = _rays_for(desc, n, seed=51)[:n]
+    d_rays = dev.alloc(n * 48)
+    d_hits = dev.alloc(n * 20 + 64)
+    dev.h2d(d_rays, rays, blocking=True)
+    dev.h2d(d_hits, np.zeros(n * 20 + 64, np.uint8), blocking=True)
+    dev.set_option("wide_stores", "3")
+    try:
+        scene.trace(d_rays, d_hits + 16 + offset, n)
+        dev.sync()
+    finally:
+        dev.set_option("wide_stores", "2")
+    raw = np.zeros(n * 20 + 64, dtype=np.uint8)
+    dev.d2h(raw, d_hits)
+    assert (raw[:16 + offset] == 0).all() and (raw[16 + offset + n * 20:] == 0).all()
+    got = raw[16 + offset:16 + offset + n * 20].view(capi.HIT_DTYPE)
+    ref = bvh.intersect(rays)
+    rep = H.compare_hits(got, ref, rays, what="offset %d" % offset)
+    assert rep["bit_exact_hits"] == rep["hits"]
+    dev.free(d_rays)
+    dev.free(d_hits)
     scene.free()
