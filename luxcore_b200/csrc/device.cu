@@ -92,8 +92,8 @@ struct lrb_scene {
 	float *dSpillT;
 	size_t spillEntries;
 	TraceStats *dStats;
-	uint32_t *dChunkDone, *dChunkFlag;  // signalled gather: retired-ray counters / completion flags per chunk
-	size_t chunkCap;
+	uint32_t *dWatermark, *dChunkFlag;  // signalled gather: per-warp watermarks / completion flags per chunk
+	size_t chunkCap, watermarkCap;
 	uint32_t epoch;
 	SceneView view;
 	lrb_scene_info info;
@@ -167,7 +167,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortRays = 0;
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
-	dev->gatherChunkShift = 20;
+	dev->gatherChunkShift = 19;
 	dev->sortBitsPerAxis = 5;
 	dev->sortMinRays = 1 << 18;
 	dev->sortKeys[0] = dev->sortKeys[1] = dev->sortVals[0] = dev->sortVals[1] = nullptr;
@@ -490,7 +490,7 @@ static lrb_scene *NewScene(lrb_device *dev) {
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
 	s->dStats = nullptr;
-	s->dChunkDone = s->dChunkFlag = nullptr; s->chunkCap = 0; s->epoch = 0;
+	s->dWatermark = s->dChunkFlag = nullptr; s->chunkCap = 0; s->watermarkCap = 0; s->epoch = 0;
 	memset(&s->view, 0, sizeof(s->view));
 	memset(&s->info, 0, sizeof(s->info));
 	return s;
@@ -506,7 +506,7 @@ int lrb_scene_free(lrb_scene *s) {
 	cudaStreamSynchronize(dev->stream);
 	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dGates); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
-	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dChunkDone); cudaFree(s->dChunkFlag);
+	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dWatermark); cudaFree(s->dChunkFlag);
 	{
 		std::lock_guard<std::mutex> g(dev->mtx);
 		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, s->info.device_bytes);
@@ -767,23 +767,28 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
 		// optional coherence pre-pass
-		if (dev->sortRays && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
+		if (dev->sortRays && !signal && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
 		}
 		if (signal) {
 			const size_t nChunks = ((size_t)n >> dev->gatherChunkShift) + 1;
-			if (s->chunkCap < nChunks) {
+			const size_t nWarps = (size_t)grid * block / 32;
+			if (s->chunkCap < nChunks || s->watermarkCap < nWarps) {
 				LRB_CUDA(cudaStreamSynchronize(stream));
-				cudaFree(s->dChunkDone); cudaFree(s->dChunkFlag);
-				s->dChunkDone = s->dChunkFlag = nullptr; s->chunkCap = 0;
-				LRB_CUDA(cudaMalloc((void **)&s->dChunkDone, nChunks * sizeof(uint32_t)));
-				LRB_CUDA(cudaMalloc((void **)&s->dChunkFlag, nChunks * sizeof(uint32_t)));
-				LRB_CUDA(cudaMemset(s->dChunkFlag, 0, nChunks * sizeof(uint32_t)));
-				s->chunkCap = nChunks;
+				cudaFree(s->dWatermark); cudaFree(s->dChunkFlag);
+				s->dWatermark = s->dChunkFlag = nullptr; s->chunkCap = 0; s->watermarkCap = 0;
+				const size_t capC = std::max(nChunks, s->chunkCap), capW = std::max<size_t>(nWarps, 16384);
+				LRB_CUDA(cudaMalloc((void **)&s->dWatermark, capW * sizeof(uint32_t)));
+				LRB_CUDA(cudaMalloc((void **)&s->dChunkFlag, capC * sizeof(uint32_t)));
+				LRB_CUDA(cudaMemset(s->dChunkFlag, 0, capC * sizeof(uint32_t)));
+				s->chunkCap = capC;
+				s->watermarkCap = capW;
 				s->epoch = 0;
 			}
-			LRB_CUDA(cudaMemsetAsync(s->dChunkDone, 0, nChunks * sizeof(uint32_t), stream));
-			a.chunkDone = s->dChunkDone;
+			if (grid < 2)
+				return Fail(LRB_ERR_INVALID, "signalled gather needs at least two blocks");
+			LRB_CUDA(cudaMemsetAsync(s->dWatermark, 0, nWarps * sizeof(uint32_t), stream));
+			a.watermark = s->dWatermark;
 			a.chunkFlag = s->dChunkFlag;
 			a.chunkShift = (uint32_t)dev->gatherChunkShift;
 			a.epoch = ++s->epoch;

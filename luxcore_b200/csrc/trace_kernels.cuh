@@ -137,11 +137,15 @@ struct TraceArgs {
 	// in kernel time at 57 GB/s of RayHit payload), so no copy pass / collective follows the kernel.
 	lrb_rayhit *hitsPeer;
 	uint32_t hitFlags;          // bit 0: hits is 16-byte aligned, bit 1: hitsPeer is 16-byte aligned
-	// Chunk-completion signalling (SIGNAL kernels): rays retired per chunk of (1 << chunkShift) ray
-	// indices; the warp that completes a chunk publishes `epoch` in chunkFlag[chunk], on which a copy
-	// stream waits (cuStreamWaitValue32) before it pushes that chunk of the RayHit buffer with the
-	// copy engine -- the gather overlaps the rest of the traversal, in full-size NVLink packets.
-	uint32_t *chunkDone;        // zeroed before launch
+	// Chunk-completion signalling (SIGNAL kernels).  Ray indices are handed out in increasing order,
+	// so "everything below index p is finished" is a prefix property: every warp publishes a
+	// watermark -- the smallest ray index it still holds (or, holding none, the end of its last fetch,
+	// below which it will never fetch again) -- and one detector warp keeps the minimum over all
+	// watermarks.  When that prefix passes the end of a chunk of (1 << chunkShift) ray indices the
+	// detector writes `epoch` into chunkFlag[chunk]; a copy stream waits on the flag
+	// (cuStreamWaitValue32) and pushes that chunk of the RayHit buffer with the copy engine, in
+	// full-size NVLink packets, while the kernel keeps tracing.  No per-ray atomics.
+	uint32_t *watermark;        // one word per warp of the grid, zeroed before launch
 	uint32_t *chunkFlag;
 	uint32_t chunkShift;
 	uint32_t epoch;
@@ -212,57 +216,58 @@ __device__ __forceinline__ void ForwardMaskedHit(const TraceArgs &a, uint32_t i)
 
 // ---- persistent, warp-cooperative kernel ----------------------------------------------------
 
-// SIGNAL kernels count retired rays (RayHit stored, or masked) per chunk.  Each lane accumulates
-// (chunk, count); a warp publishes its counts every few re-fill rounds: __syncwarp orders every
-// lane's RayHit stores before the leader's fence, the fence makes them visible device-wide before
-// the counter moves, and whoever brings a counter to the chunk's size raises the chunk's flag.
-struct RetireState {
-	uint32_t chunk, count;
-};
-
-__device__ __forceinline__ void SignalChunk(const TraceArgs &a, const uint32_t c, const uint32_t cnt) {
-	__threadfence();
-	const uint32_t old = atomicAdd(a.chunkDone + c, cnt);
-	const uint32_t first = c << a.chunkShift;
-	const uint32_t size = min(1u << a.chunkShift, a.rayCount - first);
-	if (old + cnt == size) {
-		__threadfence();
-		atomicExch(a.chunkFlag + c, a.epoch);
-	}
-}
-
-__device__ __forceinline__ void RetireRay(const TraceArgs &a, RetireState &rs, const uint32_t idx) {
-	const uint32_t c = idx >> a.chunkShift;
-	if (rs.count && c != rs.chunk) {
-		// crossed a chunk boundary before the warp published: this lane's own stores are ordered by its own fence
-		SignalChunk(a, rs.chunk, rs.count);
-		rs.count = 0;
-	}
-	rs.chunk = c;
-	rs.count += 1;
-}
-
-__device__ __forceinline__ void PublishRetired(const TraceArgs &a, const uint32_t lane, RetireState &rs) {
+// Watermark of one warp (SIGNAL kernels).  __syncwarp orders every lane's RayHit stores before the
+// leader's fence; the fence makes them visible device-wide before the watermark moves.
+__device__ __forceinline__ void PublishWatermark(const TraceArgs &a, const uint32_t lane, const uint32_t warpId,
+		const bool holdsRay, const uint32_t rayIdx, const uint32_t lowBound, const bool exhausted) {
+	uint32_t v = __reduce_min_sync(0xffffffffu, holdsRay ? rayIdx : 0xffffffffu);
+	if (v == 0xffffffffu && !exhausted)
+		v = lowBound;
 	__syncwarp();
-	unsigned todo = __ballot_sync(0xffffffffu, rs.count != 0);
-	while (todo) {
-		const int src = __ffs(todo) - 1;
-		const uint32_t c = __shfl_sync(0xffffffffu, rs.chunk, src);
-		const bool mine = rs.count != 0 && rs.chunk == c;
-		const unsigned same = __ballot_sync(0xffffffffu, mine);
-		const uint32_t cnt = __reduce_add_sync(0xffffffffu, mine ? rs.count : 0u);
-		if ((int)lane == src)
-			SignalChunk(a, c, cnt);
-		if (mine)
-			rs.count = 0;
-		todo &= ~same;
+	if (lane == 0) {
+		__threadfence();
+		asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(a.watermark + warpId), "r"(v) : "memory");
+	}
+}
+
+// Detector warp: minimum over all watermarks -> finished prefix -> chunk flags.
+__device__ __forceinline__ void DetectorLoop(const TraceArgs &a, const uint32_t lane, const uint32_t nWarps) {
+	const uint32_t chunkRays = 1u << a.chunkShift;
+	const uint32_t nChunks = (a.rayCount + chunkRays - 1) >> a.chunkShift;
+	uint32_t next = 0;
+	// bounded (~10 s): the host raises every flag after the kernel anyway
+#pragma unroll 1
+	for (uint32_t spin = 0; spin < (1u << 20) && next < nChunks; ++spin) {
+		uint32_t m = 0xffffffffu;
+		for (uint32_t w = 1 + lane; w < nWarps; w += 32) {      // warp 0 is the detector itself
+			uint32_t v;
+			asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.watermark + w) : "memory");
+			m = min(m, v);
+		}
+		m = __reduce_min_sync(0xffffffffu, m);
+		bool raised = false;
+		while (next < nChunks && m >= min((next + 1) << a.chunkShift, a.rayCount)) {
+			if (lane == 0) {
+				__threadfence();
+				atomicExch(a.chunkFlag + next, a.epoch);
+			}
+			++next;
+			raised = true;
+		}
+		if (!raised)
+			__nanosleep(8192);
 	}
 }
 
 template <bool TWO_LEVEL, bool SPILL, bool SIGNAL>
-__global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warpId = (blockIdx.x * kTraceBlock + threadIdx.x) >> 5;
+	if (SIGNAL && warpId == 0) {
+		DetectorLoop(a, lane, (gridDim.x * kTraceBlock) >> 5);
+		return;
+	}
 	const uint32_t totalThreads = gridDim.x * kTraceBlock;
 	const uint32_t gtid = blockIdx.x * kTraceBlock + threadIdx.x;
 
@@ -279,21 +284,18 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 	enum { kIdle = 0, kActive = 1, kUnsaved = 2 };
 	int state = kIdle;
 	int exhausted = 0;
-	RetireState rs;                 // SIGNAL: rays this lane retired since the last publication
-	rs.chunk = 0; rs.count = 0;
+	uint32_t lowBound = 0;          // SIGNAL: this warp never fetches a ray index below this again
 	uint32_t round = 0;
 
 	for (;;) {
 		// ---- finished lanes store their RayHit (all of them in the same instructions) ----
 		if (state == kUnsaved) {
 			StoreHit(a, rayIdx, s, rayMaxt);
-			if (SIGNAL)
-				RetireRay(a, rs, rayIdx);
 			state = kIdle;
 		}
 		if (SIGNAL) {
 			if (exhausted || (++round & 15u) == 0)
-				PublishRetired(a, lane, rs);
+				PublishWatermark(a, lane, warpId, state == kActive, rayIdx, lowBound, exhausted != 0);
 		}
 		// ---- re-fill idle lanes ----
 		const unsigned idle = __ballot_sync(0xffffffffu, state == kIdle);
@@ -321,17 +323,17 @@ __global__ void __launch_bounds__(kTraceBlock) TracePersistent(const TraceArgs a
 							StoreHit(a, idx, s, rayMaxt);   // empty scene: miss
 					} else
 						ForwardMaskedHit(a, idx);
-					if (SIGNAL && state != kActive)     // masked ray, or answered without traversal
-						RetireRay(a, rs, idx);
 				}
 			}
+			if (SIGNAL)
+				lowBound = base + (uint32_t)nIdle;
 			if (base + (uint32_t)nIdle >= a.rayCount)
 				exhausted = 1;
 		}
 		if (__ballot_sync(0xffffffffu, state == kActive) == 0) {
 			if (exhausted) {
 				if (SIGNAL)
-					PublishRetired(a, lane, rs);    // e.g. trailing masked rays
+					PublishWatermark(a, lane, warpId, false, 0u, 0u, true);     // nothing left: +inf
 				break;
 			}
 			continue;

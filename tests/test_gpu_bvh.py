@@ -119,7 +119,7 @@ def test_trace_gather_pushes_every_hit(dev, chunks, n):
         dev.free(p)
     scene.free()
     dev.set_option("gather_stores", "0")
-    dev.set_option("gather_chunk_shift", "20")
+    dev.set_option("gather_chunk_shift", "19")
 
 
 @pytest.mark.parametrize("name,n,bits", [("kitchen", 600000, 5), ("cornell", 300000, 3), ("bigmonkey", 400000, 9)])
