@@ -116,10 +116,28 @@ class ClockSampler:
 # workload
 # ---------------------------------------------------------------------------------------------
 
+def is_soup(scene_name):
+    return scene_name.startswith("soup")
+
+
 def build_scene_arrays(scene_name):
+    """A committed fixture of one of the reference's scenes, or `soup[:NTRIS]` = BASELINE.json configs[4]:
+    the synthetic random triangle soup (50 M triangles by default, size scaled so
+    that the triangle density per unit volume stays the one of the 50 M / 0.002 soup)."""
     from luxcore_b200 import scenes as S
-    desc = S.load_fixture(scene_name)
-    return desc
+    if is_soup(scene_name):
+        n_tris = int(scene_name.split(":")[1]) if ":" in scene_name else 50000000
+        return S.random_soup(n_tris, seed=4, size=0.002 * (50e6 / n_tris) ** (1.0 / 3.0), name="soup")
+    return S.load_fixture(scene_name)
+
+
+def make_batch(trace_fn, desc, args, n_rays, seed, device):
+    """The ray batch of the workload: incoherent bounce rays for the reference's scenes, uniform
+    origins x uniform directions inside the unit cube for the soup."""
+    if is_soup(args.scene):
+        from luxcore_b200 import rays as R
+        return R.uniform_rays([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], n_rays, seed=5 + seed, device=device)
+    return make_bounce_batch(trace_fn, desc, n_rays, seed=seed, device=device, depth=args.depth)
 
 
 def make_bounce_batch(trace_fn, desc, n_rays, seed, device, depth=2):
@@ -192,10 +210,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = args.gpus
-    workload = "%s-%dM-bounce%d" % (args.scene, args.rays >> 20, args.depth) if args.rays >= (1 << 20) else "%s-%d-bounce%d" % (args.scene, args.rays, args.depth)
-    config = {"workload": workload, "scene": "scenes/%s (fixture tests/golden/scenes/%s.npz)" % (args.scene, args.scene),
+    kind = "uniform" if is_soup(args.scene) else "bounce%d" % args.depth
+    workload = "%s-%dM-%s" % (args.scene, args.rays >> 20, kind) if args.rays >= (1 << 20) else "%s-%d-%s" % (args.scene, args.rays, kind)
+    config = {"workload": workload,
+              "scene": ("synthetic random triangle soup, seed 4 (BASELINE.json configs[4])" if is_soup(args.scene)
+                        else "scenes/%s (fixture tests/golden/scenes/%s.npz)" % (args.scene, args.scene)),
               "accelerator": "BVH", "builder": args.builder, "treetype": 4, "rays_per_batch_per_gpu": args.rays,
-              "ray_kind": "incoherent diffuse bounce, path depth %d" % args.depth,
+              "ray_kind": ("incoherent: origins uniform in the unit cube, directions uniform on the sphere" if is_soup(args.scene)
+                           else "incoherent diffuse bounce, path depth %d" % args.depth),
               "parallelism": "replicated BVH, one %d-ray batch per GPU x%d, RayHit gathered on rank 0 (%s)" % (args.rays, n_gpus, args.gather if n_gpus > 1 else "n/a"),
               "l2_policy": "inputs larger than L2 (48 B x rays + 20 B x rays per step >> 126 MB)"}
 
@@ -231,7 +253,7 @@ def main():
         return hits
 
     n = args.rays
-    rays = make_bounce_batch(trace_fn, desc, n, seed=2 + rank, device=device, depth=args.depth)
+    rays = make_batch(trace_fn, desc, args, n, seed=2 + rank, device=device)
     torch.cuda.synchronize()
     hits = torch.empty((n, 20), dtype=torch.uint8, device=device)
 
@@ -368,7 +390,7 @@ def main():
 
     out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic rays (seeded, generated on the GPU) over the reference's kitchen scene geometry",
+           "dtype": "f32", "data": "synthetic rays (seeded, generated on the GPU) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": launches,
            "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "verified": gather_ok,
                       "bytes_per_step_into_rank0": (world - 1) * n * 20 if world > 1 else 0},
@@ -404,9 +426,11 @@ def main():
             l2_bw = None
         out["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                           "note": ("scene (nodes + triangles = %.1f MB) is L2-resident: the algorithmic bytes are served by L1/L2, DRAM only sees "
-                                    "the compulsory ray/hit streams (see traffic); frac is algorithmic bytes / HBM peak as the contract defines it "
-                                    "and can exceed 1" % (info.device_bytes / 1e6)),
+                           "note": (("scene (nodes + triangles = %.1f MB) is L2-resident: the algorithmic bytes are served by L1/L2, DRAM only sees "
+                                     "the compulsory ray/hit streams (see traffic); frac is algorithmic bytes / HBM peak as the contract defines it "
+                                     "and can exceed 1" % (info.device_bytes / 1e6)) if info.device_bytes < 100e6 else
+                                    ("scene (%.1f GB on the device) does not fit L2: node / triangle fetches of incoherent rays go to HBM"
+                                     % (info.device_bytes / 1e9))),
                            "algorithmic_bytes_per_ray": round(alg, 1),
                            "algorithmic_bytes_definition": ("A_ref = 68 + 32*N_inner + 68*N_leaf of the REFERENCE traversal on the same tree (SURVEY 8d)"
                                                             if a_ref is not None else "A_impl (reference visit counts unavailable at N>1)"),
@@ -458,7 +482,7 @@ def run_reference(args, rank, world, config):
         h = bvh.intersect(r, nthreads=threads)
         return torch.from_numpy(h.view(np.uint8).reshape(-1, 20).copy())
 
-    rays = make_bounce_batch(trace_fn, desc, sample, seed=2, device="cpu", depth=args.depth)
+    rays = make_batch(trace_fn, desc, args, sample, seed=2, device="cpu")
     rays_np = R.to_numpy_rays(rays)
     for _ in range(max(1, min(args.warmup, 2))):
         bvh.intersect(rays_np, nthreads=threads)
@@ -469,7 +493,7 @@ def run_reference(args, rank, world, config):
     v = round(sample / dt / 1e6, 3)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic rays (seeded) over the reference's kitchen scene geometry",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic rays (seeded) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": 0,
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": "%d rays of the same ray kind per step (bounded sample of the %d-ray batch), oracle restatement of BVHAccel::Intersect, %d threads"
