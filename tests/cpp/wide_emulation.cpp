@@ -116,6 +116,20 @@ void emu_info(void *wp, uint32_t *info6) {
 	info6[3] = w->stackNeed; info6[4] = w->rootWide; info6[5] = w->twoLevel ? 1 : 0;
 }
 
+// raw copies of the re-laid-out arrays (layout checks from Python)
+void emu_copy_nodes(void *wp, void *dst) {
+	const WideScene *w = (const WideScene *)wp;
+	memcpy(dst, w->wide.data(), w->wide.size() * sizeof(WideNode));
+}
+void emu_copy_tris(void *wp, void *dst) {
+	const WideScene *w = (const WideScene *)wp;
+	memcpy(dst, w->tris.data(), w->tris.size() * sizeof(TriRecord));
+}
+void emu_copy_gates(void *wp, void *dst) {
+	const WideScene *w = (const WideScene *)wp;
+	memcpy(dst, w->gates.data(), w->gates.size() * sizeof(TriGate));
+}
+
 void emu_trace(void *wp, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, unsigned long long *stats6) {
 	const WideScene *w = (const WideScene *)wp;
 	if (w->twoLevel) Run<true>(*w, rays, hits, n, stats6);

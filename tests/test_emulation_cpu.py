@@ -59,6 +59,102 @@ def test_bvh_emulation_grazing_rays(name, tree_type, n):
     rays = np.concatenate([rays, far])
     ref = bvh.intersect(rays)
     got = emu.trace(rays)
-    rep = H.compare_hits(got, ref, rays, what="grazing %s k=%d" % (name, tree_type))
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="grazing %s k=%d" % (name, tree_type))
     assert rep["hits"] > 0.3 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
+
+
+@pytest.mark.parametrize("name,tree_type", [("cornell", 4), ("kitchen", 4), ("kitchen", 8), ("bigmonkey", 2)])
+def test_quantized_nodes_contain_the_reference_boxes(name, tree_type):
+    """Layout invariants of the 64-byte nodes (layout.h): every slot box, decoded in exact arithmetic
+    as org + q * step, contains the reference box of that child (inner node: its BVHArrayNode box;
+    triangle: the bounds of its vertices) with a margin on both sides, unused slots are inverted, every
+    reference leaf appears exactly once, and every gate is the box of the leaf's parent."""
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=tree_type)
+    nodes = bvh.nodes()
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(nodes, verts, offs)
+    wide, tris, gates = emu.arrays()
+    raw = nodes.view(np.uint8).reshape(len(nodes), 32)
+    ref_box = raw[:, :24].copy().view(np.float32).reshape(-1, 6).astype(np.float64)
+    nd = nodes["nodeData"]
+    is_leaf = (nd >> 31) == 1
+    assert len(tris) == int(is_leaf.sum())
+    assert sorted(tris["order"].tolist()) == np.nonzero(is_leaf)[0].tolist()
+
+    # parent of every reference node (depth-first array, skip index = end of the subtree)
+    parent = np.full(len(nodes), -1, dtype=np.int64)
+    stack = []
+    for i in range(len(nodes)):
+        while stack and (nd[stack[-1]] & 0x7FFFFFFF) <= i:
+            stack.pop()
+        if stack:
+            parent[i] = stack[-1]
+        if not is_leaf[i]:
+            stack.append(i)
+    # gates: exact box of the parent
+    par = parent[tris["order"]]
+    assert (par >= 0).all()
+    assert np.array_equal(gates["lo"].astype(np.float64), ref_box[par, :3]) and np.array_equal(gates["hi"].astype(np.float64), ref_box[par, 3:])
+
+    org = wide["org"].astype(np.float64)
+    eb = np.stack([(wide["exps"] >> (8 * a)) & 0xFF for a in range(3)], axis=1).astype(np.int64)
+    step = np.ldexp(1.0, eb - 15 - 127)
+    n_slots = wide["exps"] >> 24
+    tri_lo = np.minimum(np.minimum(tris["p0"], tris["p1"]), tris["p2"]).astype(np.float64)
+    tri_hi = np.maximum(np.maximum(tris["p0"], tris["p1"]), tris["p2"]).astype(np.float64)
+    # wide index -> reference inner node: the k-th inner node in array order owns wide node 1 + (nodes before it)
+    checked_inner = checked_tri = 0
+    for k in range(4):
+        ql = np.stack([(wide["qlo"][:, a] >> (8 * k)) & 0xFF for a in range(3)], axis=1).astype(np.float64)
+        qh = np.stack([(wide["qhi"][:, a] >> (8 * k)) & 0xFF for a in range(3)], axis=1).astype(np.float64)
+        lo = org + ql * step
+        hi = org + qh * step
+        used = n_slots > k
+        ref = wide["child"][:, k]
+        assert (ref[~used] == 0xFFFFFFFF).all()
+        assert ((ql[~used] == 255) & (qh[~used] == 0)).all()         # inverted: nothing passes
+        is_tri = used & ((ref & 0xC0000000) == 0x40000000)
+        t = ref[is_tri] & 0x3FFFFFFF
+        m = step[is_tri] / 64.0
+        assert (lo[is_tri] <= tri_lo[t] - m).all() and (hi[is_tri] >= tri_hi[t] + m).all()
+        assert (ql[is_tri] >= 1).all() and (qh[is_tri] <= 254).all()
+        checked_tri += int(is_tri.sum())
+        is_inner = used & ((ref & 0xC0000000) == 0)
+        checked_inner += int(is_inner.sum())
+    assert checked_tri == len(tris)
+    # inner children: rebuild the reference-node -> wide-node map (one wide node per inner node, plus
+    # continuation nodes, in array order after the entry node) and check every inner child's own box
+    skip = (nd & 0x7FFFFFFF).astype(np.int64)
+    kids_of = {}
+    for i in np.nonzero(~is_leaf)[0]:
+        ks, c = [], i + 1
+        while c < skip[i]:
+            ks.append(c)
+            c = skip[c] if not is_leaf[c] else c + 1
+        kids_of[int(i)] = ks
+    wide_of, idx = {}, 1
+    for i in sorted(kids_of):
+        wide_of[i] = idx
+        idx += max(1, (len(kids_of[i]) + 3) // 4)
+    assert idx == len(wide)
+    assert wide["child"][0, 0] == wide_of[0] and (wide["flags"][0] & 1) == 1      # entry node -> root
+    n_checked = 0
+    for i, ks in kids_of.items():
+        for k, c in enumerate(ks):
+            w, slot = wide_of[i] + k // 4, k % 4
+            if is_leaf[c]:
+                assert (wide["child"][w, slot] & 0xC0000000) == 0x40000000
+                assert tris["order"][wide["child"][w, slot] & 0x3FFFFFFF] == c
+                continue
+            assert wide["child"][w, slot] == wide_of[int(c)]
+            ql = np.array([(wide["qlo"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
+            qh = np.array([(wide["qhi"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
+            lo, hi = org[w] + ql * step[w], org[w] + qh * step[w]
+            assert (lo <= ref_box[c, :3] - step[w] / 64.0).all() and (hi >= ref_box[c, 3:] + step[w] / 64.0).all()
+            n_checked += 1
+        for j in range((len(ks) + 3) // 4):
+            assert wide["next"][wide_of[i] + j] == (wide_of[i] + j + 1 if j + 1 < (len(ks) + 3) // 4 else 0xFFFFFFFF)
+    assert n_checked == int((~is_leaf).sum()) - 1

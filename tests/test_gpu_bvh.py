@@ -172,7 +172,7 @@ def test_bvh_grazing_rays_match_oracle(dev, name, tree_type, n):
     rays = np.concatenate([rays, far])
     ref = bvh.intersect(rays)
     got = scene.trace_host(rays)
-    rep = H.compare_hits(got, ref, rays, what="grazing %s k=%d" % (name, tree_type))
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="grazing %s k=%d" % (name, tree_type))
     assert rep["hits"] > 0.3 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
     scene.free()

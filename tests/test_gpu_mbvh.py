@@ -85,3 +85,21 @@ def test_update_root_and_transforms(dev):
         rep = H.compare_hits(scene.trace_host(rays), mb.intersect(rays), rays, what="after update %d" % step)
         assert rep["bit_exact_hits"] == rep["hits"]
     scene.free()
+
+
+@pytest.mark.parametrize("which", ["zoo-inst", "bigmonkey-instances", "lightinstances"])
+def test_instances_grazing_rays(dev, which):
+    """Rays starting on / a few epsilons off the instanced surfaces, a third of them axis-parallel."""
+    desc = {"zoo-inst": lambda: Z.instances_scene(), "bigmonkey-instances": lambda: S.load_fixture("bigmonkey-instances"),
+            "lightinstances": lambda: S.load_fixture("lightinstances", max_objects=300)}[which]()
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc)
+    scene = _upload(dev, desc, mb)
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = R.to_numpy_rays(R.surface_rays(p0, e1, e2, 200000, seed=73, axis_fraction=0.33))
+    ref = mb.intersect(rays)
+    got = scene.trace_host(rays)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="grazing " + which, two_level=True)
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()

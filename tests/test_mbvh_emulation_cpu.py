@@ -81,3 +81,22 @@ def test_mbvh_update_root_only():
     ref = mb.intersect(rays)
     rep = H.compare_hits(emu.trace(rays), ref, rays, what="after update")
     assert rep["bit_exact_hits"] == rep["hits"]
+
+
+@pytest.mark.parametrize("which", ["zoo-inst", "bigmonkey-instances", "lightinstances"])
+def test_instances_grazing_rays(which):
+    """Two-level scenes with rays that start on (or a few epsilons off) the instanced surfaces, a
+    third of them axis-parallel: hits at the planes of the quantized grids of leaf trees (in instance
+    space) and of the root tree (whole-grid instance slots)."""
+    desc = {"zoo-inst": lambda: Z.instances_scene(), "bigmonkey-instances": lambda: S.load_fixture("bigmonkey-instances"),
+            "lightinstances": lambda: S.load_fixture("lightinstances", max_objects=300)}[which]()
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = R.to_numpy_rays(R.surface_rays(p0, e1, e2, 40000, seed=71, axis_fraction=0.33))
+    ref = mb.intersect(rays)
+    got = emu.trace(rays)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="grazing " + which, two_level=True)
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
