@@ -177,6 +177,21 @@ def oracle_for(desc, nodes):
     return O, O.BVH(osc, nodes=nodes)
 
 
+def reference_for(desc, nodes):
+    """The reference's own BVHAccel (oracle/_ref: its C++ sources compiled from /root/reference) walking the
+    same BVHArrayNode array, or None where the prebuilt library is absent (then the oracle port is used)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import helpers as H
+        from oracle import refapi as RF
+        if not RF.available():
+            return None
+        return RF.BVH(H.reference_scene(desc), nodes=nodes)
+    except Exception as e:      # a broken checker must not take the benchmark down
+        log("reference library unavailable:", repr(e))
+        return None
+
+
 def cpu_time_sample(O, bvh, rays_np, target_s, threads):
     """Times the oracle (reference algorithm, CPU) on a bounded prefix of the batch."""
     probe = min(rays_np.shape[0], 200000)
@@ -405,19 +420,23 @@ def main():
             O, bvh = oracle_for(desc, sess.bvh_nodes())
             rays_np = R.to_numpy_rays(rays)
             threads = O.hardware_threads()
-            cn, cdt = cpu_time_sample(O, bvh, rays_np, args.cpu_seconds, threads)
-            cpu = {"value": round(cn / cdt / 1e6, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "first %d rays of the same batch, oracle BVHAccel::Intersect restatement walking the same BVHArrayNode array, %d threads, %.1f s" % (cn, threads, cdt)}
+            refbvh = reference_for(desc, sess.bvh_nodes())
+            cn, cdt = cpu_time_sample(O, refbvh or bvh, rays_np, args.cpu_seconds, threads)
+            cpu = {"value": round(cn / cdt / 1e6, 3), "unit": UNIT, "cores": threads, "kind": "reference" if refbvh else "port",
+                   "sample": "first %d rays of the same batch, %s walking the same BVHArrayNode array, %d threads, %.1f s" % (
+                       cn, "the reference's own BVHAccel::Intersect (oracle/_ref, compiled from the reference sources)" if refbvh
+                       else "oracle BVHAccel::Intersect restatement", threads, cdt)}
             # reference-traversal visit counts on the same tree (canonical algorithmic bytes)
             k = min(rays_np.shape[0], 200000)
             _, cnt = bvh.intersect(rays_np[:k], nthreads=threads, count=True)
             a_ref = 48 + 20 + 32.0 * cnt[0] / k + 68.0 * cnt[1] / k
             # spot parity of the timed batch (not timed): device hits == oracle hits on a slice
-            ref = bvh.intersect(rays_np[:k], nthreads=threads)
+            ref = (refbvh or bvh).intersect(rays_np[:k], nthreads=threads)
             got = hits[:k].cpu().numpy().reshape(-1).view(capi.HIT_DTYPE)
             same = (got["meshIndex"] == ref["meshIndex"]) & ((got["triangleIndex"] == ref["triangleIndex"]) | (ref["meshIndex"] == 0xFFFFFFFF))
             out["parity_check"] = {"rays": int(k), "index_mismatch": int((~same).sum()),
-                                   "t_bit_exact": bool((got["t"][same] == ref["t"][same]).all())}
+                                   "t_bit_exact": bool((got["t"][same] == ref["t"][same]).all()),
+                                   "against": "reference library (oracle/_ref)" if refbvh else "oracle port"}
         alg = a_ref if a_ref is not None else a_impl
         achieved = alg * n / (kern_ms * 1e-3) / 1e9
         try:
@@ -475,6 +494,9 @@ def run_reference(args, rank, world, config):
     nodes = sess.bvh_nodes()
     O, bvh = oracle_for(desc, nodes)
     threads = O.hardware_threads()
+    refbvh = reference_for(desc, nodes)
+    if refbvh is not None:
+        bvh = refbvh        # the reference's own code; same intersect(rays, nthreads=) call
     sample = int(os.environ.get("LRB_REF_SAMPLE", "1048576"))
 
     def trace_fn(rays_u8):
@@ -495,9 +517,10 @@ def run_reference(args, rank, world, config):
            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic rays (seeded) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": 0,
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": "%d rays of the same ray kind per step (bounded sample of the %d-ray batch), oracle restatement of BVHAccel::Intersect, %d threads"
-                                      % (sample, args.rays, threads)},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference" if refbvh is not None else "port",
+                            "sample": "%d rays of the same ray kind per step (bounded sample of the %d-ray batch), %s, %d threads"
+                                      % (sample, args.rays, "the reference's own BVHAccel::Intersect (oracle/_ref) on the product's binned-SAH BVHArrayNode array"
+                                         if refbvh is not None else "oracle restatement of BVHAccel::Intersect", threads)},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -271,3 +271,19 @@ class Emu:
         if want_stats:
             return hits, dict(zip(["rays", "wide_nodes", "triangles", "instances", "motion_samples", "max_stack"], [int(x) for x in st]))
         return hits
+
+
+def reference_scene(desc):
+    """SceneDesc -> the REFERENCE's own mesh objects (oracle/_ref, oracle/refapi.py), same dataset order."""
+    from oracle import refapi as RF
+    sc = RF.Scene()
+    for v, t in desc.shapes:
+        sc.add_shape(v, t)
+    for m in desc.meshes:
+        if m.kind == S.PLAIN:
+            sc.add_plain(m.shape)
+        elif m.kind == S.INSTANCE:
+            sc.add_instance(m.shape, m.xform)
+        else:
+            sc.add_motion(m.shape, m.times, m.motion_xforms)
+    return sc

@@ -209,3 +209,26 @@ def test_hit_buffer_alignment(dev, offset):
     dev.free(d_rays)
     dev.free(d_hits)
     scene.free()
+
+
+@pytest.mark.parametrize("name,tree_type", [("kitchen", 4), ("cornell", 8)])
+def test_cuda_path_against_the_reference_library(dev, name, tree_type):
+    """The CUDA device against the REFERENCE ITSELF (oracle/_ref: BVHAccel built and intersected by the
+    reference's own sources), not only against the restatement."""
+    from oracle import refapi as RF
+    if not RF.available():
+        pytest.skip("oracle/_ref is not built")
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    rb = RF.BVH(H.reference_scene(desc), tree_type=tree_type)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(rb.nodes().view(capi.NODE_DTYPE), verts, offs)
+    rays = _rays_for(desc, 400000, seed=61)
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = np.concatenate([rays, R.to_numpy_rays(R.surface_rays(p0, e1, e2, 200000, seed=62))])
+    ref = rb.intersect(rays)
+    got = scene.trace_host(rays)
+    rep = H.compare_hits_tie_aware(got, ref.view(capi.HIT_DTYPE), rays, osc, what="vs reference library " + name)
+    assert rep["hits"] > 0.3 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
