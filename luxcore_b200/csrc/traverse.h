@@ -515,13 +515,22 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 	const uint32_t exps = LRB_F2U(A.v[3]);
 	const uint32_t next = LRB_F2U(B.v[6]);
 
-	// per-axis decode constants
-	const float ax = LRB_MUL(LRB_U2F((exps << 23) & 0x7f800000u), s.ix);
-	const float ay = LRB_MUL(LRB_U2F((exps << 15) & 0x7f800000u), s.iy);
-	const float az = LRB_MUL(LRB_U2F((exps << 7) & 0x7f800000u), s.iz);
-	const float bx = LRB_SUB(LRB_MUL(LRB_SUB(A.v[0], s.ox), s.ix), ax);
-	const float by = LRB_SUB(LRB_MUL(LRB_SUB(A.v[1], s.oy), s.iy), ay);
-	const float bz = LRB_SUB(LRB_MUL(LRB_SUB(A.v[2], s.oz), s.iz), az);
+	// per-axis decode constants.  A zero direction component has 1/d = +-inf, for which A = inf and
+	// B = inf - inf = NaN: the slab would be ignored and an axis-parallel ray would walk every box in
+	// its column (15 000 nodes per ray on the kitchen, half the tree on a 50 M-triangle soup).  With
+	// the reciprocal clamped to +-2^100 the slab keeps deciding by position, like the reference's
+	// (lo - o) * inf = +-inf: t = (plane - o) * 2^100 is astronomically negative / positive on either
+	// side of the plane and 0 on it.  Directions with |d| > 2^-100 are not affected.
+	const float kBig = 1.2676506e30f;
+	const float cix = LRB_FMIN(LRB_FMAX(s.ix, -kBig), kBig);
+	const float ciy = LRB_FMIN(LRB_FMAX(s.iy, -kBig), kBig);
+	const float ciz = LRB_FMIN(LRB_FMAX(s.iz, -kBig), kBig);
+	const float ax = LRB_MUL(LRB_U2F((exps << 23) & 0x7f800000u), cix);
+	const float ay = LRB_MUL(LRB_U2F((exps << 15) & 0x7f800000u), ciy);
+	const float az = LRB_MUL(LRB_U2F((exps << 7) & 0x7f800000u), ciz);
+	const float bx = LRB_SUB(LRB_MUL(LRB_SUB(A.v[0], s.ox), cix), ax);
+	const float by = LRB_SUB(LRB_MUL(LRB_SUB(A.v[1], s.oy), ciy), ay);
+	const float bz = LRB_SUB(LRB_MUL(LRB_SUB(A.v[2], s.oz), ciz), az);
 	// near / far plane words by direction sign (see ChildEntry)
 	const bool nx = s.ix < 0.f, ny = s.iy < 0.f, nz = s.iz < 0.f;
 	const uint32_t qlx = LRB_F2U(B.v[0]), qly = LRB_F2U(B.v[1]), qlz = LRB_F2U(B.v[2]);
