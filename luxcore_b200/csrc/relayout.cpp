@@ -61,6 +61,8 @@ struct TreeInput {
 	const std::vector<uint32_t> *leafRootWide;
 	const std::vector<uint32_t> *leafStackNeed;
 	uint32_t nTransforms, nMotions;
+	const std::vector<float> *leafBox;      // 6 floats per unique leaf: its tree's root box (instance space)
+	const float *minv;                      // 16 floats per transform
 };
 
 static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr) {
@@ -234,6 +236,80 @@ static void TriBuildBox(const TriRecord &tr, float lo[3], float hi[3]) {
 	}
 }
 
+// 4x4 inverse in double precision (Gauss-Jordan with partial pivoting); false when singular.
+static bool Invert4x4(const float *m, double out[16]) {
+	double a[4][8];
+	for (int r = 0; r < 4; ++r)
+		for (int c = 0; c < 4; ++c) {
+			a[r][c] = m[4 * r + c];
+			a[r][4 + c] = (r == c) ? 1.0 : 0.0;
+		}
+	for (int col = 0; col < 4; ++col) {
+		int piv = col;
+		for (int r = col + 1; r < 4; ++r)
+			if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+		if (!(fabs(a[piv][col]) > 1e-300) || !std::isfinite(a[piv][col]))
+			return false;
+		if (piv != col)
+			for (int c = 0; c < 8; ++c) std::swap(a[piv][c], a[col][c]);
+		const double inv = 1.0 / a[col][col];
+		for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+		for (int r = 0; r < 4; ++r) {
+			if (r == col) continue;
+			const double f = a[r][col];
+			if (f != 0.0)
+				for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+		}
+	}
+	for (int r = 0; r < 4; ++r)
+		for (int c = 0; c < 4; ++c) {
+			out[4 * r + c] = a[r][4 + c];
+			if (!std::isfinite(out[4 * r + c])) return false;
+		}
+	return true;
+}
+
+// World-space bounds of one instance: the leaf tree's root box (instance space) taken through the
+// inverse of mInv, grown generously.  The reference enters every instance of a visited root node and
+// then tests the same root box in instance space (mbvhaccel.cpp:312-333 -> bvhaccel.cpp:245-255); a ray
+// that misses the world-space bounds of that box misses the box itself, so skipping the instance
+// changes nothing.  Returns false (=> the slot takes the whole grid) for motion-blurred instances,
+// singular or projective matrices and non-finite results.
+static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float lo[3], float hi[3]) {
+	if (!in.leafBox || nd.bvhLeaf.motionIndex != kNullIndex)
+		return false;
+	const float *lb = in.leafBox->data() + 6 * (size_t)nd.bvhLeaf.leafIndex;
+	for (int k = 0; k < 6; ++k)
+		if (!std::isfinite(lb[k])) return false;
+	double M[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+	if (nd.bvhLeaf.transformIndex != kNullIndex) {
+		if (!in.minv || !Invert4x4(in.minv + 16 * (size_t)nd.bvhLeaf.transformIndex, M))
+			return false;
+		if (fabs(M[12]) > 1e-12 || fabs(M[13]) > 1e-12 || fabs(M[14]) > 1e-12 || fabs(M[15] - 1.0) > 1e-9)
+			return false;       // projective: the bounds of the corners do not bound the box
+	}
+	double wlo[3] = { 1e300, 1e300, 1e300 }, whi[3] = { -1e300, -1e300, -1e300 }, mag = 0.0;
+	for (int corner = 0; corner < 8; ++corner) {
+		const double p[3] = { lb[(corner & 1) ? 3 : 0], lb[(corner & 2) ? 4 : 1], lb[(corner & 4) ? 5 : 2] };
+		for (int r = 0; r < 3; ++r) {
+			const double v = M[4 * r] * p[0] + M[4 * r + 1] * p[1] + M[4 * r + 2] * p[2] + M[4 * r + 3];
+			wlo[r] = std::min(wlo[r], v);
+			whi[r] = std::max(whi[r], v);
+			mag = std::max(mag, fabs(v));
+		}
+	}
+	const double diag = std::max(std::max(whi[0] - wlo[0], whi[1] - wlo[1]), whi[2] - wlo[2]);
+	const double grow = 1e-4 * diag + 4e-6 * mag + 1e-6;    // far above the float rounding of the reference's ray transform
+	for (int r = 0; r < 3; ++r) {
+		lo[r] = (float)(wlo[r] - grow);
+		hi[r] = (float)(whi[r] + grow);
+		if (!std::isfinite(lo[r]) || !std::isfinite(hi[r])) return false;
+		lo[r] = std::nextafter(lo[r], -kInfF);
+		hi[r] = std::nextafter(hi[r], kInfF);
+	}
+	return true;
+}
+
 // Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.
 static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, const lrb_bvh_node *parent,
 		SlotBoxes *b, WideScene *out) {
@@ -244,7 +320,7 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 		for (int a = 0; a < 3; ++a) { b->lo[k][a] = ch.bvhNode.bboxMin[a]; b->hi[k][a] = ch.bvhNode.bboxMax[a]; }
 		b->child[k] = wideOf[c];
 	} else if (in.instLeaves) {
-		b->whole[k] = true;
+		b->whole[k] = !InstanceWorldBox(in, ch, b->lo[k], b->hi[k]);
 		InstRecord ir;
 		FillInst(in, c, &ir);
 		b->child[k] = kTagInstance | (uint32_t)out->insts.size();
@@ -469,6 +545,8 @@ static void ConvertRoot(const lrb_bvh_node *rootNodes, uint32_t nRootNodes, uint
 	in.leafStackNeed = &out->leafStackNeed;
 	in.nTransforms = nTransforms;
 	in.nMotions = nMotions;
+	in.leafBox = &out->leafBox;
+	in.minv = out->minv.empty() ? nullptr : out->minv.data();
 	const size_t before = out->wide.size();
 	uint32_t need = 0;
 	out->rootWide = ConvertTree(in, out, &need);
@@ -499,6 +577,16 @@ void BuildWideMBVH(const lrb_mbvh_desc &d, WideScene *out) {
 		uint32_t need = 0;
 		out->leafRootWide.push_back(ConvertTree(in, out, &need));
 		out->leafStackNeed.push_back(need);
+		// root box of the leaf tree in instance space: its node 0, or the lone triangle's build box
+		float lb[6] = { kInfF, kInfF, kInfF, -kInfF, -kInfF, -kInfF };      // empty tree: never entered anyway
+		if (in.n > 0 && !IsLeaf(in.nodes[0].nodeData)) {
+			for (int a = 0; a < 3; ++a) { lb[a] = in.nodes[0].bvhNode.bboxMin[a]; lb[3 + a] = in.nodes[0].bvhNode.bboxMax[a]; }
+		} else if (in.n > 0) {
+			TriRecord tr;
+			FillTri(in, 0, &tr);
+			TriBuildBox(tr, lb, lb + 3);
+		}
+		out->leafBox.insert(out->leafBox.end(), lb, lb + 6);
 		out->nRefNodes += d.leaf_n_nodes[i];
 	}
 

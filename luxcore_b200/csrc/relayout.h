@@ -29,6 +29,7 @@ struct WideScene {
 	float entryBox[6];      // exact box of the top-level tree's root (reference node 0): min xyz, max xyz
 	std::vector<uint32_t> leafRootWide;   // per unique leaf: wide index of its root
 	std::vector<uint32_t> leafStackNeed;
+	std::vector<float> leafBox;           // per unique leaf: root box of its tree in instance space (min xyz, max xyz)
 
 	WideScene() : rootWide(0), nRootWide(0), stackNeed(0), nRefNodes(0), twoLevel(false) { for (int i = 0; i < 6; ++i) entryBox[i] = 0.f; }
 };
