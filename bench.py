@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -84,9 +84,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples that arrived inside [t_begin, t_end] (the timed region); when the region
+        was shorter than the sampling period, the samples closest to it."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,7 +98,14 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for line in self.lines:
+        lines = list(self.lines)
+        if t_begin is not None and t_end is not None and lines:
+            inside = [l for l in lines if t_begin - 0.005 <= l[0] <= t_end + 0.03]
+            if not inside:
+                mid = 0.5 * (t_begin + t_end)
+                inside = sorted(lines, key=lambda l: abs(l[0] - mid))[:2]
+            lines = inside
+        for _, line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -321,23 +330,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()         # started before the warm-up so that nvidia-smi is already streaming samples
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
     # ---- timed region: device-resident inputs ----
     c0 = sess.counters()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e_start.record()
     for i in range(args.steps):
         step()
     e_stop.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     c1 = sess.counters()
     total_ms = shard.max_over_ranks(e_start.elapsed_time(e_stop), device)
     ms_per_step = total_ms / args.steps

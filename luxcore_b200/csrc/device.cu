@@ -62,7 +62,7 @@ struct lrb_device {
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
 	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
-	int sortRays;                   // 1 = order the rays of a batch for coherence before tracing them
+	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
 	int sortMinRays;                // batches smaller than this are traced in index order
 	// scratch of the ray-ordering pre-pass (keys / indices, double-buffered, + CUB temp storage)
@@ -164,7 +164,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->smemDepth = 16;
 	dev->refillBelow = 24;
 	dev->triBias = 8;
-	dev->sortRays = 0;
+	dev->sortRays = 2;
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
 	dev->gatherChunkShift = 19;
@@ -255,7 +255,8 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
 		dev->wideStores = iv;
 	} else if (k == "sort_rays") {
-		dev->sortRays = iv ? 1 : 0;
+		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "sort_rays must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
+		dev->sortRays = iv;
 	} else if (k == "sort_bits") {
 		if (iv < 1 || iv > 9) return Fail(LRB_ERR_INVALID, "sort_bits (per axis) must be 1..9");
 		dev->sortBitsPerAxis = iv;
@@ -767,7 +768,10 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
 		// optional coherence pre-pass
-		if (dev->sortRays && !signal && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
+		// (measured on a 2 GB triangle soup: 614 -> 720 Mrays/s; on the L2-resident kitchen the sort costs what it gains)
+		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
+		const bool wantSort = dev->sortRays == 1 || (dev->sortRays == 2 && sceneBytes > (size_t)dev->prop.l2CacheSize);
+		if (wantSort && !signal && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
 		}
 		if (signal) {
