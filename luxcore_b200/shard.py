@@ -63,6 +63,16 @@ def gather_hits(hits_local, dst=0, counts=None):
     return out
 
 
+def reduce_film_tiles(tile, dst=0):
+    """Sum-reduce of per-rank film tiles (fp32 radiance/weight planes of identical shape) onto `dst` --
+    the collective that replaces the reference's host-side Film::AddFilm merge of per-device films
+    (src/slg/engines/pathocl/pathocl.cpp:184-206) when every GPU renders its own samples of the same
+    tile.  In place; NCCL on CUDA tensors, gloo on CPU tensors.  Returns the tile on dst, None elsewhere."""
+    assert tile.dtype == torch.float32
+    dist.reduce(tile, dst=dst, op=dist.ReduceOp.SUM)
+    return tile if dist.get_rank() == dst else None
+
+
 def max_over_ranks(value, device="cpu"):
     """Timing rule of the benchmark: a multi-GPU number is the MAX over ranks."""
     if not dist.is_available() or not dist.is_initialized():

@@ -49,6 +49,13 @@ def _worker(rank, world, port, n_total, out_path):
     hits = bvh.intersect(rays_all[first:first + count], nthreads=1)
     local = torch.from_numpy(hits.view(np.uint8).reshape(-1, 20).copy())
     gathered = shard.gather_hits(local, dst=0)
+    # film tiles: every rank contributes its own samples, rank 0 ends up with the sum
+    tile = torch.full((4, 8, 8), float(rank + 1), dtype=torch.float32)
+    summed = shard.reduce_film_tiles(tile, dst=0)
+    if rank == 0:
+        assert torch.equal(summed, torch.full((4, 8, 8), float(world * (world + 1) // 2)))
+    else:
+        assert summed is None
     tmax = shard.max_over_ranks(1.0 + rank)
     total = shard.sum_over_ranks(count)
     if rank == 0:
