@@ -153,8 +153,8 @@ static void QuantizeNode(const SlotBoxes &b, uint32_t next, uint32_t flags, Wide
 		if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {
 			// nothing finite to bound (a lone MBVH root leaf, or non-finite input): a grid that spans
 			// (practically) everything, so that every ray passes
-			org = -ldexpf(1.f, 126);
-			eb = 119 + kGridShift + 127;
+			org = -ldexpf(1.f, 118);            // grid = [-2^118, -2^118 + 255 * 2^111] ~ +-3e35
+			eb = 111 + kGridShift + 127;        // = 253: the largest step whose 2^15 multiple still has a float exponent
 			for (uint32_t k = 0; k < kWideSlots; ++k) {
 				qlo |= (k < b.n ? 0u : 255u) << (8 * k);
 				qhi |= (k < b.n ? 255u : 0u) << (8 * k);
@@ -210,7 +210,7 @@ static void QuantizeNode(const SlotBoxes &b, uint32_t next, uint32_t flags, Wide
 					if (!b.whole[k] && (!std::isfinite(b.lo[k][a]) || !std::isfinite(b.hi[k][a]) || !(b.lo[k][a] <= b.hi[k][a])))
 						finite = false;
 				if (!finite)
-					throw std::runtime_error("BVH node with a non-finite or inverted box");
+					throw std::runtime_error("internal error: a non-finite slot box reached the node grid");
 			}
 		}
 		w->org[a] = org;
@@ -310,6 +310,21 @@ static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float 
 	return true;
 }
 
+// Boxes the reference's builders never emit but its traversal tolerates: BBox::IntersectP swaps the two
+// slab distances when they come out of order, so a box with min > max behaves like the sorted box, and
+// every comparison with a NaN is false, so a NaN plane never rejects.  Same behaviour here: corners
+// are sorted per axis, a box with a non-finite corner covers the whole grid of its node.
+static void SanitizeSlot(SlotBoxes *b, uint32_t k) {
+	for (int a = 0; a < 3; ++a) {
+		if (!std::isfinite(b->lo[k][a]) || !std::isfinite(b->hi[k][a])) {
+			b->whole[k] = true;
+			return;
+		}
+		if (b->lo[k][a] > b->hi[k][a])
+			std::swap(b->lo[k][a], b->hi[k][a]);
+	}
+}
+
 // Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.
 static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, const lrb_bvh_node *parent,
 		SlotBoxes *b, WideScene *out) {
@@ -319,6 +334,7 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 	if (!IsLeaf(ch.nodeData)) {
 		for (int a = 0; a < 3; ++a) { b->lo[k][a] = ch.bvhNode.bboxMin[a]; b->hi[k][a] = ch.bvhNode.bboxMax[a]; }
 		b->child[k] = wideOf[c];
+		SanitizeSlot(b, k);
 	} else if (in.instLeaves) {
 		b->whole[k] = !InstanceWorldBox(in, ch, b->lo[k], b->hi[k]);
 		InstRecord ir;
@@ -329,6 +345,7 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 		TriRecord tr;
 		FillTri(in, c, &tr);
 		TriBuildBox(tr, b->lo[k], b->hi[k]);
+		SanitizeSlot(b, k);
 		b->child[k] = kTagTri | (uint32_t)out->tris.size();
 		out->tris.push_back(tr);
 		// the reference's gate for this triangle: its parent's exact box (none for a root that is a leaf)
@@ -337,6 +354,8 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 		for (int a = 0; a < 3; ++a) {
 			g.lo[a] = parent ? parent->bvhNode.bboxMin[a] : -kInfF;
 			g.hi[a] = parent ? parent->bvhNode.bboxMax[a] : kInfF;
+			if (g.lo[a] > g.hi[a])      // see SanitizeSlot: the reference's slab swap
+				std::swap(g.lo[a], g.hi[a]);
 		}
 		out->gates.push_back(g);
 	}
@@ -403,9 +422,15 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		b.whole[0] = false;
 		for (int a = 0; a < 3; ++a) { b.lo[0][a] = nodes[0].bvhNode.bboxMin[a]; b.hi[0][a] = nodes[0].bvhNode.bboxMax[a]; }
 		b.child[0] = wideOf[0];
+		SanitizeSlot(&b, 0);
 		QuantizeNode(b, kNullIndex, kNodeEntry, &out->wide[wideStart]);
 		if (in.instLeaves || !out->twoLevel) {
-			for (int a = 0; a < 3; ++a) { out->entryBox[a] = nodes[0].bvhNode.bboxMin[a]; out->entryBox[3 + a] = nodes[0].bvhNode.bboxMax[a]; }
+			for (int a = 0; a < 3; ++a) {
+				out->entryBox[a] = nodes[0].bvhNode.bboxMin[a];
+				out->entryBox[3 + a] = nodes[0].bvhNode.bboxMax[a];
+				if (out->entryBox[a] > out->entryBox[3 + a])    // see SanitizeSlot
+					std::swap(out->entryBox[a], out->entryBox[3 + a]);
+			}
 		}
 	}
 

@@ -181,3 +181,49 @@ def test_axis_parallel_rays_keep_their_box_culling(name):
         rep = H.compare_hits_tie_aware(got, bvh.intersect(r), r, osc, what="axis %r" % (d,))
         assert rep["bit_exact_hits"] == rep["hits"]
         assert st["wide_nodes"] / st["rays"] < 4 * generic + 8, (d, st["wide_nodes"] / st["rays"], generic)
+
+
+def _tiny_tree():
+    """Three triangles under one inner node, in the reference array format."""
+    verts = np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0], [2, 0, 1], [3, 0, 1], [2, 1, 1], [0, 2, 2], [1, 2, 2], [0, 3, 2]], dtype=np.float32)
+    nodes = np.zeros(4, dtype=H.Emu.NODE_DTYPE if hasattr(H.Emu, "NODE_DTYPE") else np.dtype([("w", "<u4", 6), ("nodeData", "<u4"), ("pad0", "<i4")]))
+    w = nodes.view(np.uint32).reshape(-1, 8)
+    w[0, :6] = np.asarray([-0.1, -0.1, -0.1, 3.1, 3.1, 2.1], dtype=np.float32).view(np.uint32)
+    w[0, 6] = 4
+    for k in range(3):
+        w[1 + k, :5] = [3 * k, 3 * k + 1, 3 * k + 2, 0, k]
+        w[1 + k, 6] = 0x80000000 | (k + 2)
+    return nodes, verts, np.zeros(1, dtype=np.uint32)
+
+
+def test_relayout_rejects_malformed_input():
+    """The device refuses arrays it could walk off: bad skip indices, vertex / mesh indices out of range,
+    non-finite boxes -- with an error, not a crash (lrb_bvh_upload returns LRB_ERR_INVALID for the same input)."""
+    nodes, verts, offs = _tiny_tree()
+    emu = H.Emu.bvh(nodes, verts, offs)                      # the well-formed tree is accepted ...
+    rays = R.to_numpy_rays(R.uniform_rays([-1, -1, 3], [3, 3, 4], 64, seed=1))
+    rays["d"][:] = [0, 0, -1]
+    assert (emu.trace(rays)["meshIndex"] != H.NULL).any()     # ... and hit from above
+
+    def broken(mutate, what):
+        n, v, o = _tiny_tree()
+        mutate(n.view(np.uint32).reshape(-1, 8), v)
+        with pytest.raises(RuntimeError) as e:
+            H.Emu.bvh(n, v, o)
+        assert what in str(e.value), str(e.value)
+
+    broken(lambda w, v: w.__setitem__((0, 6), 5), "root skip index")
+    broken(lambda w, v: w.__setitem__((2, 6), 0x80000000 | 7), "leaf skip index")
+    broken(lambda w, v: w.__setitem__((1, 0), 1000), "vertex outside")
+    broken(lambda w, v: w.__setitem__((1, 3), 5), "mesh outside")
+    # boxes the reference tolerates are tolerated the same way: a NaN plane never rejects, corners given in
+    # the wrong order behave like the sorted box (BBox::IntersectP swaps the slab distances)
+    n2, v2, o2 = _tiny_tree()
+    w2 = n2.view(np.uint32).reshape(-1, 8)
+    w2[0, 0] = np.asarray([np.nan], np.float32).view(np.uint32)[0]
+    w2[0, 1], w2[0, 4] = w2[0, 4], w2[0, 1]
+    osc = O.Scene()
+    osc.add_plain(osc.add_shape(v2, np.arange(9, dtype=np.uint32).reshape(3, 3)))
+    rep = H.compare_hits(H.Emu.bvh(n2, v2, o2).trace(rays), O.BVH(osc, nodes=n2).intersect(rays), rays, what="tolerated boxes")
+    assert rep["hits"] > 0 and rep["bit_exact_hits"] == rep["hits"]
+    assert H.Emu.lib().emu_validate_tree(nodes.ctypes.data, 3) != 0      # truncated array
