@@ -151,10 +151,12 @@ static void QuantizeNode(const SlotBoxes &b, uint32_t next, uint32_t flags, Wide
 		float org;
 		uint32_t qlo = 0, qhi = 0;
 		if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {
-			// nothing finite to bound (a lone MBVH root leaf, or non-finite input): a grid that spans
-			// (practically) everything, so that every ray passes
-			org = -ldexpf(1.f, 118);            // grid = [-2^118, -2^118 + 255 * 2^111] ~ +-3e35
-			eb = 111 + kGridShift + 127;        // = 253: the largest step whose 2^15 multiple still has a float exponent
+			// nothing finite to bound (a lone MBVH root leaf, or non-finite input): the axis never rejects.
+			// Exponent byte 255 makes the decode scale +inf: A = +-inf, B = finite - A = -+inf, and every
+			// plane distance fma(q, A, B) is inf - inf = NaN, which the slab test ignores -- for every ray,
+			// with no overflow edge (a huge finite grid fails where A is finite but B overflows).
+			org = 0.f;
+			eb = 255;
 			for (uint32_t k = 0; k < kWideSlots; ++k) {
 				qlo |= (k < b.n ? 0u : 255u) << (8 * k);
 				qhi |= (k < b.n ? 255u : 0u) << (8 * k);

@@ -518,10 +518,11 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 	// per-axis decode constants.  A zero direction component has 1/d = +-inf, for which A = inf and
 	// B = inf - inf = NaN: the slab would be ignored and an axis-parallel ray would walk every box in
 	// its column (15 000 nodes per ray on the kitchen, half the tree on a 50 M-triangle soup).  With
-	// the reciprocal clamped to +-2^100 the slab keeps deciding by position, like the reference's
-	// (lo - o) * inf = +-inf: t = (plane - o) * 2^100 is astronomically negative / positive on either
-	// side of the plane and 0 on it.  Directions with |d| > 2^-100 are not affected.
-	const float kBig = 1.2676506e30f;
+	// the reciprocal clamped to +-2^80 the slab keeps deciding by position, like the reference's
+	// (lo - o) * inf = +-inf: t = (plane - o) * 2^80 is astronomically negative / positive on either
+	// side of the plane (>= 1e17 for planes one float spacing away) and 0 on it, and A = step * 2^15
+	// * 2^80 stays finite for any grid step below 2^33.  Directions with |d| > 2^-80 are not affected.
+	const float kBig = 1.2089258e24f;
 	const float cix = LRB_FMIN(LRB_FMAX(s.ix, -kBig), kBig);
 	const float ciy = LRB_FMIN(LRB_FMAX(s.iy, -kBig), kBig);
 	const float ciz = LRB_FMIN(LRB_FMAX(s.iz, -kBig), kBig);

@@ -100,3 +100,20 @@ def test_instances_grazing_rays(which):
     rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="grazing " + which, two_level=True)
     assert rep["hits"] > 0.3 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
+
+
+@pytest.mark.parametrize("kind", ["instance", "motion", "plain"])
+def test_single_mesh_dataset_root_is_a_leaf(kind):
+    """A dataset with ONE mesh: the MBVH root tree is a single leaf without any box (the node takes an
+    unbounded grid), for an instanced, a motion-blurred and a plain mesh."""
+    s = S.SceneDesc("single-" + kind)
+    shape = s.add_shape(*Z.blob(12, 9))
+    if kind == "instance":
+        s.add_instance(shape, Z.translate(0.5, -0.25, 0.75) @ Z.rot_z(25.0))
+    elif kind == "motion":
+        s.add_motion(shape, [0.0, 1.0], [np.linalg.inv(Z.translate(0, 0, 0)).astype(np.float32), np.linalg.inv(Z.translate(1.0, 0.5, 0.0)).astype(np.float32)])
+    else:
+        s.add_plain(shape)
+    s.cam = np.asarray([0.5, -6.0, 0.75, 0.5, 0.0, 0.75, 0, 0, 1, 45], dtype=np.float32)
+    tr = (0.0, 1.0) if kind == "motion" else None
+    _check(s, 4, 12000, time_range=tr, motion=(kind == "motion"))
