@@ -15,7 +15,10 @@
 //                              topology.
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <future>
 #include <thread>
 
@@ -370,11 +373,289 @@ struct SAHBuilder {
 
 }   // namespace
 
+
+//------------------------------------------------------------------------------
+// Binary SAH tree -> insertion-based optimisation -> optimal k-ary collapse
+//------------------------------------------------------------------------------
+//
+// What the traversal pays for is node visits: with one triangle per leaf every triangle carries its
+// own box, so the expected number of triangle tests of a ray does not depend on the topology, and
+// the expected number of node visits is  sum over inner nodes of area(node) / area(root).  This
+// builder minimises that sum in three steps:
+//   1. a binary tree by top-down SAH (32 bins; exact sweep for small ranges),
+//   2. insertion-based optimisation of that tree (remove a subtree, re-insert it where the summed
+//      area of the inner nodes grows least, branch-and-bound search; after Bittner, Hapala and
+//      Havran, "Fast insertion-based optimization of bounding volume hierarchies", 2013),
+//   3. the k-ary tree with the smallest summed inner-node area that can be obtained from the binary
+//      tree by dissolving inner nodes into their parents (dynamic programme over "subtree of n as a
+//      forest of at most i trees", after Ylitie, Karras and Laine 2017, section 3.1).
+// The result is emitted in the reference's array format like every other builder here.
+
+namespace {
+
+static const size_t kOptMaxPrims = 4u << 20;        // larger inputs keep the plain top-down k-ary builder
+static const size_t kOptStepBudget = 400u << 20;    // search steps of the optimisation (deterministic bound)
+
+struct OptBuilder {
+	const BVHParams &params;
+	const std::deque<const Mesh *> *meshes;
+	LeafList &list;
+	const u_int N;
+	SAHBuilder splitter;
+
+	// binary tree: ids [0, N-1) are inner nodes, id N-1+i is the leaf list[i]
+	std::vector<BBox> box;
+	std::vector<float> area;
+	std::vector<int> kid0, kid1, parent;
+	int root;
+
+	OptBuilder(const BVHParams &p, const std::deque<const Mesh *> *m, LeafList &l) : params(p), meshes(m), list(l),
+			N((u_int)l.size()), splitter(p, m, l), root(-1) { }
+
+	bool IsLeafId(const int id) const { return id >= (int)N - 1; }
+
+	// ---- 1. binary SAH tree.  The inner node that cuts [b, e) at m gets id m - 1 (unique), so
+	// sub-ranges are built concurrently without any shared allocation.
+	int BuildBinary(const u_int b, const u_int e, const int depthBudget) {
+		if (e - b == 1) {
+			const int id = (int)(N - 1 + b);
+			box[id] = list[b]->bbox;
+			return id;
+		}
+		const u_int m = splitter.Split(b, e);
+		const int id = (int)m - 1;
+		int l, r;
+		if (depthBudget > 0 && e - b >= SAHBuilder::kParallelMin) {
+			std::future<int> job = std::async(std::launch::async, [this, b, m, depthBudget]() { return BuildBinary(b, m, depthBudget - 1); });
+			r = BuildBinary(m, e, depthBudget - 1);
+			l = job.get();
+		} else {
+			l = BuildBinary(b, m, 0);
+			r = BuildBinary(m, e, 0);
+		}
+		kid0[id] = l; kid1[id] = r;
+		parent[l] = id; parent[r] = id;
+		box[id] = Union(box[l], box[r]);
+		return id;
+	}
+
+	// ---- 2. insertion-based optimisation
+	void Refit(int id) {
+		while (id >= 0) {
+			const BBox nb = Union(box[kid0[id]], box[kid1[id]]);
+			const float na = nb.SurfaceArea();
+			if (na == area[id] && nb.pMin.x == box[id].pMin.x && nb.pMin.y == box[id].pMin.y && nb.pMin.z == box[id].pMin.z &&
+					nb.pMax.x == box[id].pMax.x && nb.pMax.y == box[id].pMax.y && nb.pMax.z == box[id].pMax.z)
+				break;
+			box[id] = nb;
+			area[id] = na;
+			id = parent[id];
+		}
+	}
+
+	struct Cand { float induced; int id; };
+	struct CandLess { bool operator()(const Cand &a, const Cand &b) const { return a.induced > b.induced; } };
+
+	// Takes subtree n out of the tree (its parent p goes with it) and puts it back at the cheapest
+	// position.  Returns the number of search steps.
+	size_t Reinsert(const int n, std::vector<Cand> &heap) {
+		const int p = parent[n];
+		if (p < 0)
+			return 0;
+		const int g = parent[p];
+		if (g < 0)
+			return 0;       // children of the root stay
+		const int s = (kid0[p] == n) ? kid1[p] : kid0[p];
+		// unlink p (and n with it)
+		if (kid0[g] == p) kid0[g] = s; else kid1[g] = s;
+		parent[s] = g;
+		Refit(g);
+
+		const BBox nb = box[n];
+		const float an = area[n];
+		float best = std::numeric_limits<float>::infinity();
+		int bestAt = s;
+		size_t steps = 0;
+		heap.clear();
+		Cand c0 = { 0.f, root };
+		heap.push_back(c0);
+		while (!heap.empty()) {
+			std::pop_heap(heap.begin(), heap.end(), CandLess());
+			const Cand c = heap.back();
+			heap.pop_back();
+			if (c.induced + an >= best)
+				break;          // every remaining candidate is at least as expensive
+			++steps;
+			const float direct = Union(box[c.id], nb).SurfaceArea();
+			const float total = c.induced + direct;
+			if (total < best) {
+				best = total;
+				bestAt = c.id;
+			}
+			if (!IsLeafId(c.id)) {
+				const float below = total - area[c.id];
+				if (below + an < best) {
+					Cand a = { below, kid0[c.id] }, b2 = { below, kid1[c.id] };
+					heap.push_back(a); std::push_heap(heap.begin(), heap.end(), CandLess());
+					heap.push_back(b2); std::push_heap(heap.begin(), heap.end(), CandLess());
+				}
+			}
+		}
+
+		// link p above bestAt, with children (bestAt, n)
+		const int x = bestAt, px = parent[x];
+		if (px < 0)
+			root = p;
+		else if (kid0[px] == x) kid0[px] = p; else kid1[px] = p;
+		parent[p] = px;
+		kid0[p] = x; kid1[p] = n;
+		parent[x] = p; parent[n] = p;
+		box[p] = Union(box[x], nb);
+		area[p] = box[p].SurfaceArea();
+		if (px >= 0)
+			Refit(px);
+		return steps;
+	}
+
+	double InnerAreaSum() const {
+		double s = 0.0;
+		for (u_int i = 0; i + 1 < N; ++i) s += area[i];
+		return s;
+	}
+
+	void Optimise(const int maxPasses, const size_t stepBudget) {
+		std::vector<int> order;
+		std::vector<Cand> heap;
+		size_t steps = 0;
+		double before = InnerAreaSum();
+		for (int pass = 0; pass < maxPasses && steps < stepBudget; ++pass) {
+			// largest subtrees first: moving them changes the most, and later moves see their new places
+			order.resize(2 * (size_t)N - 1);
+			for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+			std::sort(order.begin(), order.end(), [this](int a, int b) { return area[a] > area[b] || (area[a] == area[b] && a < b); });
+			for (size_t i = 0; i < order.size() && steps < stepBudget; ++i)
+				steps += Reinsert(order[i], heap);
+			const double now = InnerAreaSum();
+			if (!(now < before * 0.9995))
+				break;
+			before = now;
+		}
+	}
+
+	// ---- 3. optimal collapse.  cost[(k-1) * n + (i-1)]: smallest summed area of the k-ary inner
+	// nodes needed for the subtree of binary inner node n presented as at most i sibling entries.
+	std::vector<float> cost;
+	u_int K;
+
+	float CostOf(const int id, const u_int i) const { return IsLeafId(id) ? 0.f : cost[(size_t)(K - 1) * id + (i - 1)]; }
+
+	// best way to hand j entries to the two children of n: entries given to kid0
+	float Distribute(const int n, const u_int j, u_int *give0) const {
+		float bestC = std::numeric_limits<float>::infinity();
+		u_int bestA = 1;
+		for (u_int a = 1; a + 1 <= j; ++a) {
+			const float c = CostOf(kid0[n], a) + CostOf(kid1[n], j - a);
+			if (c < bestC) { bestC = c; bestA = a; }
+		}
+		if (give0) *give0 = bestA;
+		return bestC;
+	}
+
+	void SolveCollapse() {
+		K = params.treeType < 2 ? 2 : params.treeType;
+		cost.assign((size_t)(K - 1) * (N - 1), 0.f);
+		// post-order over the inner nodes
+		std::vector<int> stack, order;
+		order.reserve(N - 1);
+		stack.push_back(root);
+		while (!stack.empty()) {
+			const int id = stack.back();
+			stack.pop_back();
+			if (IsLeafId(id)) continue;
+			order.push_back(id);
+			stack.push_back(kid0[id]);
+			stack.push_back(kid1[id]);
+		}
+		for (size_t r = order.size(); r-- > 0;) {
+			const int n = order[r];
+			float *c = &cost[(size_t)(K - 1) * n];
+			c[0] = area[n] + Distribute(n, K, nullptr);        // n survives as a k-ary node
+			for (u_int i = 2; i <= K - 1; ++i)
+				c[i - 1] = std::min(c[i - 2], Distribute(n, i, nullptr));   // or dissolves into i entries of its parent
+		}
+	}
+
+	// entries of the k-ary node that presents subtree `id` within a budget of `i` entries
+	void Entries(const int id, u_int i, std::vector<int> &outIds) const {
+		if (IsLeafId(id)) { outIds.push_back(id); return; }
+		while (i > 1 && CostOf(id, i) == CostOf(id, i - 1)) --i;
+		if (i == 1) { outIds.push_back(id); return; }
+		u_int a;
+		Distribute(id, i, &a);
+		Entries(kid0[id], a, outIds);
+		Entries(kid1[id], i - a, outIds);
+	}
+
+	void Emit(const int id, std::vector<Node> &out) const {
+		if (IsLeafId(id)) {
+			EmitLeaf(meshes, list[id - (int)(N - 1)], out);
+			return;
+		}
+		const size_t self = out.size();
+		out.push_back(Node());
+		std::vector<int> kids;
+		u_int a;
+		Distribute(id, K, &a);
+		Entries(kid0[id], a, kids);
+		Entries(kid1[id], K - a, kids);
+		for (size_t i = 0; i < kids.size(); ++i)
+			Emit(kids[i], out);
+		Node &n = out[self];
+		memset(&n, 0, sizeof(n));
+		StoreBox(n, box[id]);
+		n.nodeData = (u_int)out.size();
+	}
+
+	void Run(std::vector<Node> &out, const int optimisePasses, const size_t stepBudget) {
+		if (N == 0)
+			return;
+		if (N == 1) {
+			EmitLeaf(meshes, list[0], out);
+			return;
+		}
+		box.resize(2 * (size_t)N - 1);
+		area.resize(2 * (size_t)N - 1);
+		parent.assign(2 * (size_t)N - 1, -1);
+		kid0.assign(N - 1, -1);
+		kid1.assign(N - 1, -1);
+		root = BuildBinary(0, N, 4);
+		for (size_t i = 0; i < box.size(); ++i) area[i] = box[i].SurfaceArea();
+		const bool verbose = getenv("LRB_BVH_VERBOSE") != nullptr;
+		const double a0 = InnerAreaSum() / area[root];
+		if (optimisePasses > 0 && N >= 4)
+			Optimise(optimisePasses, stepBudget);
+		SolveCollapse();
+		if (verbose)
+			fprintf(stderr, "[bvhbuild] %u prims: binary SAH %.3f -> optimised %.3f -> %u-ary %.3f (expected node visits of a long random ray)\n",
+					N, a0, InnerAreaSum() / area[root], K, (double)CostOf(root, 1) / area[root]);
+		Emit(root, out);
+	}
+};
+
+}   // namespace
+
 Node *BuildEmbreeBVHBinnedSAH(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
-	SAHBuilder b(params, meshes, leafList);
 	std::vector<Node> out;
 	out.reserve(leafList.size() + leafList.size() / 2 + 1);
-	if (!leafList.empty()) {
+	const char *env = getenv("LRB_BVH_OPT");
+	const int mode = env ? atoi(env) : 2;
+	const char *envP = getenv("LRB_BVH_OPT_PASSES");
+	const int passes = envP ? atoi(envP) : 3;
+	if (mode > 0 && leafList.size() <= kOptMaxPrims) {
+		OptBuilder b(params, meshes, leafList);
+		b.Run(out, mode >= 2 ? passes : 0, kOptStepBudget);
+	} else if (!leafList.empty()) {
+		SAHBuilder b(params, meshes, leafList);
 		BBox box;
 		b.Build(0, (u_int)leafList.size(), out, &box);
 	}

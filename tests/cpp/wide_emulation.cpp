@@ -66,6 +66,137 @@ template <bool TWO> static void Run(const WideScene &w, const lrb_ray *rays, lrb
 		stats6[3] = st.instances; stats6[4] = st.motionSamples; stats6[5] = st.maxStack;
 	}
 }
+
+// ---- scheduling model of the persistent kernel ------------------------------------------------
+// Replays TracePersistent's control flow (trace_kernels.cuh) for `nWarps` warps that share the ray
+// counter, one outer-loop iteration per warp in turn: bulk re-fill when fewer than refillBelow lanes
+// are alive, per-iteration Resolve, node / triangle phase vote with triBias.  Counts what the warp
+// ISSUES (phases, pop-loop trips = the longest lane's), which is what an issue-bound kernel pays
+// for; used to compare trees and policies without a GPU (tools/warp_model.py).
+struct SimLane {
+	RayState s;
+	HostStack stk;
+	uint32_t rayIdx;
+	int state;      // 0 idle, 1 active, 2 unsaved
+};
+struct SimWarp {
+	SimLane lane[32];
+	bool exhausted;
+	SimWarp() : exhausted(false) { for (int i = 0; i < 32; ++i) lane[i].state = 0; }
+};
+
+template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n,
+		uint32_t nWarps, uint32_t refillBelow, uint32_t triBias, unsigned long long *out16) {
+	const SceneView v = View(w);
+	std::vector<SimWarp> warps(nWarps);
+	uint32_t counter = 0;
+	unsigned long long outer = 0, inner = 0, nodePhases = 0, triPhases = 0, nodeLanes = 0, triLanes = 0,
+			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0;
+	uint32_t live = nWarps;
+	std::vector<char> done(nWarps, 0);
+	while (live) {
+		for (uint32_t wi = 0; wi < nWarps; ++wi) {
+			if (done[wi]) continue;
+			SimWarp &W = warps[wi];
+			++outer;
+			bool anyStore = false;
+			for (int l = 0; l < 32; ++l) {
+				SimLane &L = W.lane[l];
+				if (L.state == 2) {
+					WriteHit(L.s, rays[L.rayIdx].maxt, &hits[L.rayIdx]);
+					L.state = 0;
+					anyStore = true;
+				}
+			}
+			if (anyStore) ++storePhases;
+			int nIdle = 0;
+			for (int l = 0; l < 32; ++l) nIdle += W.lane[l].state == 0;
+			if (!W.exhausted && nIdle) {
+				++refills;
+				const uint32_t base = counter;
+				counter += (uint32_t)nIdle;
+				uint32_t k = 0;
+				for (int l = 0; l < 32; ++l) {
+					SimLane &L = W.lane[l];
+					if (L.state != 0) continue;
+					const uint32_t slot = base + k++;
+					if (slot >= n) continue;
+					if (rays[slot].flags & LRB_RAY_FLAGS_MASKED) continue;
+					L.rayIdx = slot;
+					++traced;
+					L.stk.n.clear(); L.stk.t.clear();
+					if (InitRay(v, rays[slot], L.s)) L.state = 1;
+					else WriteHit(L.s, rays[slot].maxt, &hits[slot]);
+				}
+				if (base + (uint32_t)nIdle >= n) W.exhausted = true;
+			}
+			int nActive = 0;
+			for (int l = 0; l < 32; ++l) nActive += W.lane[l].state == 1;
+			if (nActive == 0) {
+				if (W.exhausted) { done[wi] = 1; --live; }
+				continue;
+			}
+			const int floorLanes = W.exhausted ? 1 : (int)refillBelow;
+			int nLive;
+			do {
+				++inner;
+				unsigned long long maxTrips = 0;
+				for (int l = 0; l < 32; ++l) {
+					SimLane &L = W.lane[l];
+					if (L.state == 1 && NeedsResolve<TWO>(L.s.cur)) {
+						const size_t before = L.stk.n.size();
+						if (!Resolve<TWO, false>(v, rays[L.rayIdx], L.s, L.stk, nullptr))
+							L.state = 2;
+						// pops performed (an entry into an instance pushes the sentinel: count at least one trip)
+						const size_t after = L.stk.n.size();
+						unsigned long long trips = before > after ? (unsigned long long)(before - after) : 1ull;
+						if (L.state == 2) trips += 1;
+						popLanes += trips;
+						if (trips > maxTrips) maxTrips = trips;
+					}
+				}
+				popTrips += maxTrips;
+				int nTri = 0, nNode = 0;
+				for (int l = 0; l < 32; ++l) {
+					const SimLane &L = W.lane[l];
+					if (L.state != 1) continue;
+					if (L.s.cur & kTagTri) ++nTri; else ++nNode;
+				}
+				if (nTri * (int)triBias >= nNode * 4) {
+					if (nTri) {
+						++triPhases;
+						triLanes += (unsigned long long)nTri;
+						idlePhaseLanes += (unsigned long long)nNode;
+						int accepted = 0;
+						for (int l = 0; l < 32; ++l) {
+							SimLane &L = W.lane[l];
+							if (L.state == 1 && (L.s.cur & kTagTri)) {
+								const float before = L.s.maxt;
+								const uint32_t bt = L.s.bestTri, bi = L.s.bestInst, hm = L.s.hitMesh;
+								TriStep<TWO, false>(v, L.s, nullptr);
+								if (L.s.maxt != before || L.s.bestTri != bt || L.s.bestInst != bi || L.s.hitMesh != hm) ++accepted;
+							}
+						}
+						if (accepted) { ++gatePhases; gateLanes += (unsigned long long)accepted; }
+					}
+				} else {
+					++nodePhases;
+					nodeLanes += (unsigned long long)nNode;
+					idlePhaseLanes += (unsigned long long)nTri;
+					for (int l = 0; l < 32; ++l) {
+						SimLane &L = W.lane[l];
+						if (L.state == 1 && !(L.s.cur & kTagTri))
+							NodeStep<TWO, false>(v, L.s, L.stk, nullptr);
+					}
+				}
+				nLive = nTri + nNode;
+			} while (nLive >= floorLanes);
+		}
+	}
+	out16[0] = traced; out16[1] = outer; out16[2] = inner; out16[3] = nodePhases; out16[4] = triPhases;
+	out16[5] = nodeLanes; out16[6] = triLanes; out16[7] = popTrips; out16[8] = popLanes; out16[9] = gatePhases;
+	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = 0; out16[15] = 0;
+}
 }   // namespace
 
 extern "C" {
@@ -134,6 +265,13 @@ void emu_trace(void *wp, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, unsi
 	const WideScene *w = (const WideScene *)wp;
 	if (w->twoLevel) Run<true>(*w, rays, hits, n, stats6);
 	else Run<false>(*w, rays, hits, n, stats6);
+}
+
+void emu_warp_sim(void *wp, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, uint32_t nWarps, uint32_t refillBelow,
+		uint32_t triBias, unsigned long long *out16) {
+	const WideScene *w = (const WideScene *)wp;
+	if (w->twoLevel) WarpSim<true>(*w, rays, hits, n, nWarps, refillBelow, triBias, out16);
+	else WarpSim<false>(*w, rays, hits, n, nWarps, refillBelow, triBias, out16);
 }
 
 int emu_validate_tree(const lrb_bvh_node *nodes, uint32_t n) {

@@ -186,7 +186,7 @@ class Emu:
                    os.path.join(ROOT, "luxcore_b200", "csrc", "relayout.cpp")]
             deps = src + [os.path.join(ROOT, "luxcore_b200", "csrc", f) for f in ("traverse.h", "layout.h", "relayout.h")]
             if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse", "-msse2", "-mfma", "-ffp-contract=off",
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse", "-msse2", "-mfma", "-ffp-contract=off"] + (["-DLRB_EXIT_ORDER=" + os.environ["LRB_EXIT_ORDER"]] if "LRB_EXIT_ORDER" in os.environ else []) + [
                                        "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "luxcore_b200", "csrc"),
                                        "-o", so] + src)
             L = C.CDLL(so)
@@ -202,6 +202,7 @@ class Emu:
             L.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
             for f in (L.emu_copy_nodes, L.emu_copy_tris, L.emu_copy_gates):
                 f.argtypes = [C.c_void_p, C.c_void_p]
+            L.emu_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
             L.emu_validate_tree.restype = C.c_int
             L.emu_validate_tree.argtypes = [C.c_void_p, C.c_uint32]
             cls._lib = L
@@ -271,6 +272,19 @@ class Emu:
         if want_stats:
             return hits, dict(zip(["rays", "wide_nodes", "triangles", "instances", "motion_samples", "max_stack"], [int(x) for x in st]))
         return hits
+
+
+WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_phases", "node_lanes", "tri_lanes", "pop_trips",
+                   "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes"]
+
+
+def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8):
+    """Scheduling model of TracePersistent (tests/cpp/wide_emulation.cpp WarpSim): -> (hits, counts)."""
+    rays = np.ascontiguousarray(rays)
+    hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+    out = np.zeros(16, dtype=np.uint64)
+    emu.lib().emu_warp_sim(emu.h, rays.ctypes.data, hits.ctypes.data, rays.shape[0], n_warps, refill_below, tri_bias, out.ctypes.data)
+    return hits, dict(zip(WARP_SIM_FIELDS, [int(x) for x in out]))
 
 
 def reference_scene(desc):

@@ -141,22 +141,49 @@ def test_quantized_nodes_contain_the_reference_boxes(name, tree_type):
         idx += max(1, (len(kids_of[i]) + 3) // 4)
     assert idx == len(wide)
     assert wide["child"][0, 0] == wide_of[0] and (wide["flags"][0] & 1) == 1      # entry node -> root
+    # slot order inside a node: ascending size of the slot's box (relayout.cpp SlotSizeKey): inner child = its
+    # reference box, triangle = bounds of the vertices grown by MachineEpsilon::E (bvhaccel.cpp:116-122)
+    def eps32(v):
+        v = np.asarray(v, dtype=np.float32)
+        e = np.abs((v.view(np.int32) + 0x80).view(np.float32) - v)
+        return np.clip(e, np.float32(1e-5), np.float32(1e-1))
+
+    def half_area(lo, hi):
+        d = np.abs(hi.astype(np.float64) - lo.astype(np.float64))
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+
+    ref_box32 = raw[:, :24].copy().view(np.float32).reshape(-1, 6)
+    tlo32 = np.minimum(np.minimum(tris["p0"], tris["p1"]), tris["p2"])
+    thi32 = np.maximum(np.maximum(tris["p0"], tris["p1"]), tris["p2"])
+    inner_of_wide = {w: i for i, w in wide_of.items()}
     n_checked = 0
     for i, ks in kids_of.items():
-        for k, c in enumerate(ks):
-            w, slot = wide_of[i] + k // 4, k % 4
-            if is_leaf[c]:
-                assert (wide["child"][w, slot] & 0xC0000000) == 0x40000000
-                assert tris["order"][wide["child"][w, slot] & 0x3FFFFFFF] == c
-                continue
-            assert wide["child"][w, slot] == wide_of[int(c)]
-            ql = np.array([(wide["qlo"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
-            qh = np.array([(wide["qhi"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
-            lo, hi = org[w] + ql * step[w], org[w] + qh * step[w]
-            assert (lo <= ref_box[c, :3] - step[w] / 64.0).all() and (hi >= ref_box[c, 3:] + step[w] / 64.0).all()
-            n_checked += 1
-        for j in range((len(ks) + 3) // 4):
-            assert wide["next"][wide_of[i] + j] == (wide_of[i] + j + 1 if j + 1 < (len(ks) + 3) // 4 else 0xFFFFFFFF)
+        n_w = max(1, (len(ks) + 3) // 4)
+        seen, sizes = [], []
+        for j in range(n_w):
+            w = wide_of[i] + j
+            assert n_slots[w] == min(4, len(ks) - 4 * j)
+            for slot in range(int(n_slots[w])):
+                ref = int(wide["child"][w, slot])
+                if (ref & 0xC0000000) == 0x40000000:
+                    t = ref & 0x3FFFFFFF
+                    c = int(tris["order"][t])
+                    assert is_leaf[c]
+                    e = np.float32(max(eps32(tlo32[t]).max(), eps32(thi32[t]).max()))
+                    sizes.append(half_area(tlo32[t] - e, thi32[t] + e))
+                else:
+                    c = inner_of_wide[ref]
+                    assert not is_leaf[c]
+                    ql = np.array([(wide["qlo"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
+                    qh = np.array([(wide["qhi"][w, a] >> (8 * slot)) & 0xFF for a in range(3)], dtype=np.float64)
+                    lo, hi = org[w] + ql * step[w], org[w] + qh * step[w]
+                    assert (lo <= ref_box[c, :3] - step[w] / 64.0).all() and (hi >= ref_box[c, 3:] + step[w] / 64.0).all()
+                    sizes.append(half_area(ref_box32[c, :3], ref_box32[c, 3:]))
+                    n_checked += 1
+                seen.append(c)
+            assert wide["next"][w] == (w + 1 if j + 1 < n_w else 0xFFFFFFFF)
+        assert sorted(seen) == sorted(int(c) for c in ks)          # every child of the reference node, once
+        assert all(a <= b for a, b in zip(sizes, sizes[1:])), (i, sizes)
     assert n_checked == int((~is_leaf).sum()) - 1
 
 

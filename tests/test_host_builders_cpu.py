@@ -95,3 +95,34 @@ def test_host_geometry_matches_oracle():
         assert hostapi.matrix_inverse(m).tobytes() == O.matrix_inverse(m).tobytes()
     with pytest.raises(hostapi.HostError):
         hostapi.matrix_inverse(np.zeros((4, 4), np.float32))
+
+
+def _expected_node_visits(nodes):
+    """Sum over inner nodes of area(node) / area(root): the expected number of inner-node visits of a long
+    random ray, the quantity the SAH builder minimises (one triangle per leaf: the leaf term is constant)."""
+    leaf = (nodes["nodeData"] & 0x80000000) != 0
+    box = nodes["w"][~leaf][:, :6].copy().view(np.float32).astype(np.float64)
+    d = box[:, 3:] - box[:, :3]
+    area = d[:, 0] * d[:, 1] + d[:, 1] * d[:, 2] + d[:, 2] * d[:, 0]
+    return float(area.sum() / area[0])
+
+
+@pytest.mark.parametrize("name,tree_type", [("kitchen", 4), ("classroom", 4), ("bigmonkey", 8)])
+def test_sah_builder_optimised_tree_is_cheaper_and_deterministic(name, tree_type, monkeypatch):
+    """The default builder (binary SAH -> insertion-based optimisation -> optimal k-ary collapse) must beat
+    the plain top-down k-ary builder it replaced on the cost both minimise, and give the same array twice."""
+    desc = S.load_fixture(name)
+
+    def build():
+        s = _session(desc, "EMBREE_BINNED_SAH", tree_type)
+        s.build_accelerator("BVH")
+        return s.bvh_nodes().copy()
+    a = build()
+    b = build()
+    assert a.tobytes() == b.tobytes()
+    _check_tree(a, desc.triangle_count(), tree_type)
+    monkeypatch.setenv("LRB_BVH_OPT", "0")
+    legacy = build()
+    _check_tree(legacy, desc.triangle_count(), tree_type)
+    assert _expected_node_visits(a) < 0.97 * _expected_node_visits(legacy), (_expected_node_visits(a), _expected_node_visits(legacy))
+    assert a.shape[0] <= legacy.shape[0]

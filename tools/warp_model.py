@@ -1,0 +1,74 @@
+"""CPU-only issue-slot model of the persistent trace kernel.
+
+The kernel is issue-bound on L2-resident scenes (profiles/r01_f: issue-active 75 %, 306 warp
+instructions per ray at 16.9 active threads).  tests/cpp/wide_emulation.cpp::WarpSim replays the
+kernel's scheduling (bulk re-fill, Resolve, node / triangle phase vote) with the real traverse.h
+bodies and counts the phases a warp issues; this tool weights them with the SASS instruction counts
+of the sections of TracePersistent<0,1,0> (cuobjdump -sass) and prints warp instructions per ray --
+a GPU-free figure of merit for comparing trees (builder, re-layout) and scheduling policies.
+
+    python tools/warp_model.py [scene] [n_rays] [depth] [refill_below] [tri_bias]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np
+
+import bench as B
+import helpers as H
+import tree_stats as TS
+from luxcore_b200 import hostapi
+
+# warp instructions per executed section (SASS of TracePersistent<0,1,0>, sm_100a, this tree)
+COST = {"inner_fixed": 30,      # Resolve entry test, __syncwarp, two ballots, vote, loop branch
+        "pop_trip": 16,         # one trip of the pop loop (longest lane decides)
+        "node_phase": 164,      # fetch + decode + 4 slab tests + network + predicated pushes
+        "tri_phase": 88,        # fetch + Moller-Trumbore + accept predicate
+        "gate": 40,             # accepted hit: gate fetch + box test + state update
+        "outer_fixed": 40,      # store / re-fill section when nothing to do
+        "store": 30,            # RayHit stores of the finished lanes
+        "refill": 120}          # atomic, ray fetch, 1/d, root box
+
+
+def model(c):
+    instr = (c["inner_iters"] * COST["inner_fixed"] + c["pop_trips"] * COST["pop_trip"] + c["node_phases"] * COST["node_phase"] +
+             c["tri_phases"] * COST["tri_phase"] + c["gate_phases"] * COST["gate"] + c["outer_iters"] * COST["outer_fixed"] +
+             c["store_phases"] * COST["store"] + c["refills"] * COST["refill"])
+    lanes = (c["node_lanes"] * COST["node_phase"] + c["tri_lanes"] * COST["tri_phase"] + c["gate_lanes"] * COST["gate"] +
+             c["pop_lanes"] * COST["pop_trip"])
+    return instr, lanes
+
+
+def main():
+    scene = sys.argv[1] if len(sys.argv) > 1 else "kitchen"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+    depth = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    refill = int(sys.argv[4]) if len(sys.argv) > 4 else 24
+    bias = int(sys.argv[5]) if len(sys.argv) > 5 else 8
+    desc = B.build_scene_arrays(scene)
+    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": 4}, desc)
+    sess.build_accelerator("BVH")
+    nodes = sess.bvh_nodes()
+    rays, obvh = TS.bounce_batch_cpu(desc, nodes, n, depth)
+    osc = H.oracle_scene(desc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(nodes, verts, offs)
+    ref, st = emu.trace(rays, want_stats=True)
+    hits, c = H.warp_sim(emu, rays, n_warps=256, refill_below=refill, tri_bias=bias)
+    assert hits.tobytes() == ref.tobytes(), "scheduling model and per-ray emulation disagree"
+    instr, lanes = model(c)
+    r = c["rays"]
+    print("scene %s: ref nodes %d wide %d | per ray: nodes %.2f tris %.2f | node phases %.2f (%.1f lanes) tri phases %.2f (%.1f lanes) "
+          "pop trips %.2f inner %.2f" % (scene, nodes.shape[0], emu.info()["wide"], st["wide_nodes"] / r, st["triangles"] / r,
+                                       c["node_phases"] / r, c["node_lanes"] / max(1, c["node_phases"]), c["tri_phases"] / r,
+                                       c["tri_lanes"] / max(1, c["tri_phases"]), c["pop_trips"] / r, c["inner_iters"] / r))
+    print("MODEL warp instructions / ray: %.1f   (lane-useful fraction of phase work %.2f; refill_below %d tri_bias %d)" % (
+        instr / r, lanes / (32.0 * max(1, instr)), refill, bias))
+
+
+if __name__ == "__main__":
+    main()
