@@ -91,7 +91,8 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	std::vector<SimWarp> warps(nWarps);
 	uint32_t counter = 0;
 	unsigned long long outer = 0, inner = 0, nodePhases = 0, triPhases = 0, nodeLanes = 0, triLanes = 0,
-			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0;
+			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0, slowPhases = 0, slowLanes = 0;
+	const size_t smemDepth = 16;
 	uint32_t live = nWarps;
 	std::vector<char> done(nWarps, 0);
 	while (live) {
@@ -182,6 +183,14 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 				} else {
 					++nodePhases;
 					nodeLanes += (unsigned long long)nNode;
+					{
+						int slow = 0;
+						for (int l = 0; l < 32; ++l) {
+							const SimLane &L = W.lane[l];
+							if (L.state == 1 && !(L.s.cur & kTagTri) && L.stk.n.size() + 4 > smemDepth) ++slow;
+						}
+						if (slow) { ++slowPhases; slowLanes += (unsigned long long)slow; }
+					}
 					idlePhaseLanes += (unsigned long long)nTri;
 					for (int l = 0; l < 32; ++l) {
 						SimLane &L = W.lane[l];
@@ -195,7 +204,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	}
 	out16[0] = traced; out16[1] = outer; out16[2] = inner; out16[3] = nodePhases; out16[4] = triPhases;
 	out16[5] = nodeLanes; out16[6] = triLanes; out16[7] = popTrips; out16[8] = popLanes; out16[9] = gatePhases;
-	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = 0; out16[15] = 0;
+	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes;
 }
 }   // namespace
 

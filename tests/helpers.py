@@ -275,7 +275,7 @@ class Emu:
 
 
 WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_phases", "node_lanes", "tri_lanes", "pop_trips",
-                   "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes"]
+                   "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes", "slow_push_phases", "slow_push_lanes"]
 
 
 def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8):
