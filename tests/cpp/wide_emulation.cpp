@@ -206,6 +206,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	out16[5] = nodeLanes; out16[6] = triLanes; out16[7] = popTrips; out16[8] = popLanes; out16[9] = gatePhases;
 	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes;
 }
+
 }   // namespace
 
 extern "C" {
