@@ -117,3 +117,42 @@ def test_single_mesh_dataset_root_is_a_leaf(kind):
     s.cam = np.asarray([0.5, -6.0, 0.75, 0.5, 0.0, 0.75, 0, 0, 1, 45], dtype=np.float32)
     tr = (0.0, 1.0) if kind == "motion" else None
     _check(s, 4, 12000, time_range=tr, motion=(kind == "motion"))
+
+
+@pytest.mark.parametrize("fixture,kw", [("bigmonkey-instances", {}), ("bigmonkey-motion", {"time_range": (0.0, 1.0)}),
+                                        ("lightinstances", {"max_objects": 300})])
+def test_host_layer_sah_trees_two_level(fixture, kw):
+    """The product host layer's MBVHAccel::Init with the default builder (binary SAH -> optimisation ->
+    k-ary collapse, bvhbuild.cpp) emits root and leaf trees of its own topology; payloads (leaf /
+    transform / motion / mesh-offset indices) follow mbvhaccel.cpp:58-250 like the oracle's, so its
+    arrays can be dropped into the oracle's array set.  The re-layout + traversal body over THOSE trees
+    must reproduce the oracle's MBVHAccel::Intersect bit for bit (results do not depend on topology)."""
+    from luxcore_b200 import hostapi
+    time_range = kw.pop("time_range", None)
+    desc = S.load_fixture(fixture, **kw)
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=4)
+    arr = H.mbvh_arrays(desc, mb)
+    s = hostapi.Session({"accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": 4}, desc)
+    assert s.build_accelerator("MBVH") == hostapi.ACCEL_MBVH
+    assert s.mbvh_leaf_count() == len(arr["leaf_nodes"])
+    root = s.mbvh_root_nodes().copy()
+    # same multiset of root-leaf payloads as the oracle's root tree
+    def payloads(nodes):
+        leaf = (nodes["nodeData"] & 0x80000000) != 0
+        return sorted(map(tuple, nodes["w"][leaf][:, :4].tolist()))
+    assert payloads(root) == payloads(arr["root_nodes"])
+    for i in range(s.mbvh_leaf_count()):
+        ln = s.mbvh_leaf_nodes(i).copy()
+        assert int(((ln["nodeData"] & 0x80000000) != 0).sum()) == int(((arr["leaf_nodes"][i]["nodeData"] & 0x80000000) != 0).sum())
+        assert H.Emu.lib().emu_validate_tree(ln.ctypes.data, ln.shape[0]) == 0
+        arr["leaf_nodes"][i] = ln
+    arr["root_nodes"] = root
+    emu = H.Emu.mbvh(arr)
+    rays = _rays(desc, 20000, 47, time_range)
+    ref = mb.intersect(rays)
+    got, st = emu.trace(rays, want_stats=True)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="host sah mbvh " + fixture, two_level=True)
+    assert rep["hits"] > 0.1 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    assert st["max_stack"] <= emu.info()["stack_need"]
