@@ -352,15 +352,51 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	return true;
 }
 
-// True when s.cur is neither a wide node nor a triangle: the ray needs Resolve before its next step.
+// True when s.cur is neither a wide node nor a triangle: the ray needs Resolve (and, for an instance
+// reference, EnterInstance) before its next step.
 template <bool TWO_LEVEL>
 LRB_HD bool NeedsResolve(const uint32_t cur) {
 	return TWO_LEVEL ? (cur >= kTagInstance) : (cur == kNullIndex);
 }
 
-// Turns s.cur into a wide-node or triangle reference: pops the stack while there is nothing to do
-// or the popped entry lies behind the best hit, leaves (sentinel) and enters (instance reference)
-// leaf trees.  Returns false when the ray is finished.
+// True for kTagInstance | index (not the sentinel, not kNullIndex): the ray is about to enter a leaf tree.
+LRB_HD bool IsInstanceRef(const uint32_t cur) { return (cur >> 30) == 2u; }
+
+// Enters the leaf tree s.cur refers to (mbvhaccel.cpp:312-333): ray into instance space, sentinel on
+// the stack, s.cur = root of the leaf tree -- or kNullIndex for an empty leaf tree (the next Resolve
+// pops on).  Kept out of Resolve's pop loop: that loop runs a different number of trips on every lane,
+// and this is its one expensive step (64-B matrix fetch, ~40 flops, three IEEE reciprocals); here all
+// lanes of a warp that enter an instance in the same iteration do it in the same instructions.
+template <bool STATS, class STACK>
+LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+	const char *ip = reinterpret_cast<const char *>(&sc.insts[s.cur & kRefIndexMask]);
+	const uint4 ir = LRB_LDGU4(ip);
+	const uint4 ir2 = LRB_LDGU4(ip + 16);
+	if (STATS) stats->instances++;
+	if (ir.x == kNullIndex) {
+		s.cur = kNullIndex;     // empty leaf tree
+		return;
+	}
+	if (ir.y != kNullIndex) {
+		TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
+				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+	} else if (ir.z != kNullIndex) {
+		float m[16];
+		MotionSample(sc, ir.z, s.time, m);
+		if (STATS) stats->motionSamples++;
+		TransformRayLocal(s, m, worldRay.o[0], worldRay.o[1], worldRay.o[2],
+				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+	}
+	s.curMeshOffset = ir.w;
+	s.curInstOrder = ir2.x;
+	s.inInstance = true;
+	stk.push(kStackSentinel, -LRB_INF);
+	s.cur = ir.x;
+}
+
+// Turns s.cur into a wide-node, triangle or instance reference: pops the stack while there is nothing
+// to do or the popped entry lies behind the best hit, and leaves leaf trees (sentinel).  An instance
+// reference is returned as it is (EnterInstance follows).  Returns false when the ray is finished.
 // STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n).
 template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
@@ -398,31 +434,7 @@ LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, S
 			}
 			if (cur == kNullIndex)
 				continue;           // the reference of an empty slot (NaN / inf rays only)
-			// enter a leaf tree (mbvhaccel.cpp:312-333)
-			const char *ip = reinterpret_cast<const char *>(&sc.insts[cur & kRefIndexMask]);
-			const uint4 ir = LRB_LDGU4(ip);
-			const uint4 ir2 = LRB_LDGU4(ip + 16);
-			if (STATS) stats->instances++;
-			if (ir.x == kNullIndex) {
-				cur = kNullIndex;       // empty leaf tree
-				continue;
-			}
-			if (ir.y != kNullIndex) {
-				TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-						worldRay.d[0], worldRay.d[1], worldRay.d[2]);
-			} else if (ir.z != kNullIndex) {
-				float m[16];
-				MotionSample(sc, ir.z, s.time, m);
-				if (STATS) stats->motionSamples++;
-				TransformRayLocal(s, m, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-						worldRay.d[0], worldRay.d[1], worldRay.d[2]);
-			}
-			s.curMeshOffset = ir.w;
-			s.curInstOrder = ir2.x;
-			s.inInstance = true;
-			stk.push(kStackSentinel, -LRB_INF);
-			cur = ir.x;
-			break;
+			break;                  // an instance reference: the caller runs EnterInstance
 		}
 	}
 	s.cur = cur;
@@ -583,6 +595,11 @@ LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STAC
 	if (NeedsResolve<TWO_LEVEL>(s.cur)) {
 		if (!Resolve<TWO_LEVEL, STATS>(sc, worldRay, s, stk, stats))
 			return false;
+	}
+	if (TWO_LEVEL && IsInstanceRef(s.cur)) {
+		EnterInstance<STATS>(sc, worldRay, s, stk, stats);
+		if (s.cur == kNullIndex)
+			return true;        // empty leaf tree: pop on at the next step
 	}
 	if (s.cur & kTagTri)
 		TriStep<TWO_LEVEL, STATS>(sc, s, stats);

@@ -91,7 +91,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	std::vector<SimWarp> warps(nWarps);
 	uint32_t counter = 0;
 	unsigned long long outer = 0, inner = 0, nodePhases = 0, triPhases = 0, nodeLanes = 0, triLanes = 0,
-			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0, slowPhases = 0, slowLanes = 0;
+			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0, slowPhases = 0, slowLanes = 0, instTrips = 0, instLanes = 0;
 	const size_t smemDepth = 16;
 	uint32_t live = nWarps;
 	std::vector<char> done(nWarps, 0);
@@ -141,7 +141,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 			int nLive;
 			do {
 				++inner;
-				unsigned long long maxTrips = 0;
+				unsigned long long maxTrips = 0, maxInst = 0;
 				for (int l = 0; l < 32; ++l) {
 					SimLane &L = W.lane[l];
 					if (L.state == 1 && NeedsResolve<TWO>(L.s.cur)) {
@@ -157,10 +157,22 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					}
 				}
 				popTrips += maxTrips;
+				if (TWO) {
+					// instance entries of this iteration, converged (trace_kernels.cuh)
+					for (int l = 0; l < 32; ++l) {
+						SimLane &L = W.lane[l];
+						if (L.state == 1 && IsInstanceRef(L.s.cur)) {
+							EnterInstance<false>(v, rays[L.rayIdx], L.s, L.stk, nullptr);
+							++instLanes;
+							maxInst = 1;
+						}
+					}
+				}
+				instTrips += maxInst;
 				int nTri = 0, nNode = 0;
 				for (int l = 0; l < 32; ++l) {
 					const SimLane &L = W.lane[l];
-					if (L.state != 1) continue;
+					if (L.state != 1 || (TWO && L.s.cur == kNullIndex)) continue;
 					if (L.s.cur & kTagTri) ++nTri; else ++nNode;
 				}
 				if (nTri * (int)triBias >= nNode * 4) {
@@ -171,7 +183,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 						int accepted = 0;
 						for (int l = 0; l < 32; ++l) {
 							SimLane &L = W.lane[l];
-							if (L.state == 1 && (L.s.cur & kTagTri)) {
+							if (L.state == 1 && L.s.cur != kNullIndex && (L.s.cur & kTagTri)) {
 								const float before = L.s.maxt;
 								const uint32_t bt = L.s.bestTri, bi = L.s.bestInst, hm = L.s.hitMesh;
 								TriStep<TWO, false>(v, L.s, nullptr);
@@ -187,14 +199,14 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 						int slow = 0;
 						for (int l = 0; l < 32; ++l) {
 							const SimLane &L = W.lane[l];
-							if (L.state == 1 && !(L.s.cur & kTagTri) && L.stk.n.size() + 4 > smemDepth) ++slow;
+							if (L.state == 1 && L.s.cur != kNullIndex && !(L.s.cur & kTagTri) && L.stk.n.size() + 4 > smemDepth) ++slow;
 						}
 						if (slow) { ++slowPhases; slowLanes += (unsigned long long)slow; }
 					}
 					idlePhaseLanes += (unsigned long long)nTri;
 					for (int l = 0; l < 32; ++l) {
 						SimLane &L = W.lane[l];
-						if (L.state == 1 && !(L.s.cur & kTagTri))
+						if (L.state == 1 && L.s.cur != kNullIndex && !(L.s.cur & kTagTri))
 							NodeStep<TWO, false>(v, L.s, L.stk, nullptr);
 					}
 				}
@@ -204,7 +216,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	}
 	out16[0] = traced; out16[1] = outer; out16[2] = inner; out16[3] = nodePhases; out16[4] = triPhases;
 	out16[5] = nodeLanes; out16[6] = triLanes; out16[7] = popTrips; out16[8] = popLanes; out16[9] = gatePhases;
-	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes;
+	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes; out16[16] = instTrips; out16[17] = instLanes;
 }
 
 }   // namespace

@@ -254,3 +254,23 @@ def test_relayout_rejects_malformed_input():
     rep = H.compare_hits(H.Emu.bvh(n2, v2, o2).trace(rays), O.BVH(osc, nodes=n2).intersect(rays), rays, what="tolerated boxes")
     assert rep["hits"] > 0 and rep["bit_exact_hits"] == rep["hits"]
     assert H.Emu.lib().emu_validate_tree(nodes.ctypes.data, 3) != 0      # truncated array
+
+
+def test_scheduling_model_is_consistent_with_the_per_ray_emulation():
+    """tools/warp_model.py's engine (WarpSim: the persistent kernel's re-fill / Resolve / phase-vote control
+    flow around the real traverse.h bodies) must produce the same hits and do the same amount of traversal
+    work as the plain per-ray emulation, for any policy setting -- it only regroups the work into warps."""
+    desc = S.load_fixture("kitchen")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=4)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(bvh.nodes(), verts, offs)
+    lo, hi = desc.bbox()
+    rays = R.to_numpy_rays(R.uniform_rays(lo, hi, 20000, seed=5))
+    rays["flags"][::7] = 1      # masked rays are skipped, their RayHit stays untouched (zero here)
+    ref, st = emu.trace(rays, want_stats=True)
+    for n_warps, refill, bias in ((1, 24, 8), (64, 24, 8), (16, 32, 2), (16, 1, 64)):
+        hits, c = H.warp_sim(emu, rays, n_warps=n_warps, refill_below=refill, tri_bias=bias)
+        assert hits.tobytes() == ref.tobytes()
+        assert c["rays"] == st["rays"] and c["node_lanes"] == st["wide_nodes"] and c["tri_lanes"] == st["triangles"]
+        assert c["node_phases"] * 32 >= c["node_lanes"] and c["tri_phases"] * 32 >= c["tri_lanes"]
