@@ -62,6 +62,7 @@ struct lrb_device {
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
 	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
+	int prefetch;                   // L2 prefetch of the children pushed on the stack: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
 	int sortMinRays;                // batches smaller than this are traced in index order
@@ -165,6 +166,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->refillBelow = 24;
 	dev->triBias = 8;
 	dev->sortRays = 2;
+	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
 	dev->gatherChunkShift = 19;
@@ -254,6 +256,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "wide_stores") {
 		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
 		dev->wideStores = iv;
+	} else if (k == "prefetch") {
+		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "prefetch must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
+		dev->prefetch = iv;
 	} else if (k == "sort_rays") {
 		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "sort_rays must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
 		dev->sortRays = iv;
@@ -688,7 +693,10 @@ static int SortRays(lrb_scene *s, const void *rays, uint32_t n, cudaStream_t str
 	return LRB_OK;
 }
 
-static PersistentKernel PickPersistent(bool two, bool spill, bool signal) {
+static PersistentKernel PickPersistent(bool two, bool spill, bool signal, bool prefetch) {
+	// the prefetching variant exists for one-level scenes with a spilling stack (large scenes are both)
+	if (prefetch && !two && spill)
+		return signal ? TracePersistent<false, true, true, true> : TracePersistent<false, true, false, true>;
 	if (two) {
 		if (spill) return signal ? TracePersistent<true, true, true> : TracePersistent<true, true, false>;
 		return signal ? TracePersistent<true, false, true> : TracePersistent<true, false, false>;
@@ -753,7 +761,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const int smemBytes = depth * block * 8;
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
-		PersistentKernel kernel = PickPersistent(two, spill, signal);
+		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
+		const bool bigScene = sceneBytes > (size_t)dev->prop.l2CacheSize;
+		PersistentKernel kernel = PickPersistent(two, spill, signal, dev->prefetch == 1 || (dev->prefetch == 2 && bigScene));
 		if ((rc = Occupancy(kernel, block, smemBytes, &bps)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
@@ -769,8 +779,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
 		// optional coherence pre-pass
 		// (measured on a 2 GB triangle soup: 614 -> 720 Mrays/s; on the L2-resident kitchen the sort costs what it gains)
-		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
-		const bool wantSort = dev->sortRays == 1 || (dev->sortRays == 2 && sceneBytes > (size_t)dev->prop.l2CacheSize);
+		const bool wantSort = dev->sortRays == 1 || (dev->sortRays == 2 && bigScene);
 		if (wantSort && !signal && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
 		}

@@ -259,7 +259,7 @@ __device__ __forceinline__ void DetectorLoop(const TraceArgs &a, const uint32_t 
 	}
 }
 
-template <bool TWO_LEVEL, bool SPILL, bool SIGNAL>
+template <bool TWO_LEVEL, bool SPILL, bool SIGNAL, bool PREFETCH = false>
 __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
 	const uint32_t lane = threadIdx.x & 31u;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersisten
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
 			} else {
 				if (wantNode)
-					NodeStep<TWO_LEVEL, false>(a.sc, s, stk, nullptr);
+					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
 			}
 			nLive = nTri + nNode;
 		} while (nLive >= floorLanes);

@@ -98,7 +98,10 @@ __device__ __forceinline__ F8 Ld256(const void *p) {
 		: "l"(p));
 	return r;
 }
+// L2 prefetch of the record a child reference points at (scenes that do not fit L2; see NodeStep).
+__device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 #else
+static inline void PrefetchL2(const void *) { }
 static inline F8 Ld256(const void *p) { F8 r; __builtin_memcpy(&r, p, 32); return r; }
 static inline uint32_t HostF2U(float x) { uint32_t u; __builtin_memcpy(&u, &x, 4); return u; }
 static inline float HostU2F(uint32_t u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
@@ -516,7 +519,12 @@ LRB_HD float SlotEntry(const RayState &s, const uint32_t one, const uint32_t nqx
 // Visits the wide node s.cur refers to: box-tests its four child slots (no branches), orders the
 // children near-to-far, continues with the nearest and pushes the others with their entry
 // distances.
-template <bool TWO_LEVEL, bool STATS, class STACK>
+//
+// PREFETCH (scenes larger than L2, where every fetch of a deep node is a DRAM round trip the whole warp
+// waits for): the records of the children that go on the stack are requested into L2 now; by the time
+// one of them is popped its fetch hits L2.  Entries that are culled before they are popped cost
+// bandwidth (plentiful: a latency-bound walk uses a small fraction of HBM), not time.
+template <bool TWO_LEVEL, bool STATS, bool PREFETCH = false, class STACK>
 LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	// ---- fetch the 64-byte node with two 256-bit loads ----
 	const char *np = reinterpret_cast<const char *>(sc.nodes + s.cur);
@@ -583,6 +591,13 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 		if (h3) stk.push(c3, d3);
 		if (h2) stk.push(c2, d2);
 		if (h1) stk.push(c1, d1);
+	}
+	if (PREFETCH) {
+		// wide nodes and triangle records are both 64 bytes: one address computation serves either
+		const char *nb = reinterpret_cast<const char *>(sc.nodes), *tb = reinterpret_cast<const char *>(sc.tris);
+		if (h1 && c1 < kTagInstance) PrefetchL2(((c1 & kTagTri) ? tb : nb) + ((size_t)(c1 & kRefIndexMask) << 6));
+		if (h2 && c2 < kTagInstance) PrefetchL2(((c2 & kTagTri) ? tb : nb) + ((size_t)(c2 & kRefIndexMask) << 6));
+		if (h3 && c3 < kTagInstance) PrefetchL2(((c3 & kTagTri) ? tb : nb) + ((size_t)(c3 & kRefIndexMask) << 6));
 	}
 	s.cur = (d0 < kInf) ? c0 : kNullIndex;
 	if (STATS) { const unsigned long long d = stk.depth(); if (d > stats->maxStack) stats->maxStack = d; }
