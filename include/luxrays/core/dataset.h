@@ -37,6 +37,7 @@ public:
 	void UpdateAccelerators();
 
 	const BBox &GetBBox() const { return bbox; }
+	const BSphere &GetBSphere() const { return bsphere; }
 	u_longlong GetTotalVertexCount() const { return totalVertexCount; }
 	u_longlong GetTotalTriangleCount() const { return totalTriangleCount; }
 	u_int GetDataSetID() const { return dataSetID; }
@@ -50,6 +51,7 @@ private:
 	u_longlong totalVertexCount, totalTriangleCount;
 	std::deque<const Mesh *> meshes;
 	BBox bbox;
+	BSphere bsphere;
 	mutable std::mutex accelsMutex;
 	std::map<AcceleratorType, Accelerator *> accels;
 	AcceleratorType accelType;

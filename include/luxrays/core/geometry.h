@@ -93,6 +93,21 @@ inline std::ostream &operator<<(std::ostream &os, const Point &p) { return os <<
 inline std::ostream &operator<<(std::ostream &os, const Vector &v) { return os << "Vector[" << v.x << ", " << v.y << ", " << v.z << "]"; }
 
 //------------------------------------------------------------------------------
+// BSphere (include/luxrays/core/geometry/bsphere.h:28-48)
+//------------------------------------------------------------------------------
+
+class BSphere {
+public:
+	BSphere() : center(0.f, 0.f, 0.f), rad(0.f) { }
+	BSphere(const Point &c, const float r) : center(c), rad(r) { }
+
+	Point center;
+	float rad;
+};
+
+inline std::ostream &operator<<(std::ostream &os, const BSphere &s) { return os << "BSphere[" << s.center << ", " << s.rad << "]"; }
+
+//------------------------------------------------------------------------------
 // BBox
 //------------------------------------------------------------------------------
 
@@ -117,6 +132,16 @@ public:
 		return 2.f * (d.x * d.y + d.y * d.z + d.z * d.x);
 	}
 	bool IsValid() const { return (pMin.x <= pMax.x) && (pMin.y <= pMax.y) && (pMin.z <= pMax.z); }
+	bool Inside(const Point &pt) const {
+		return pt.x >= pMin.x && pt.x <= pMax.x && pt.y >= pMin.y && pt.y <= pMax.y && pt.z >= pMin.z && pt.z <= pMax.z;
+	}
+	// bbox.cpp:65-75: centre of the box, radius to a corner (0 for an invalid box)
+	BSphere BoundingSphere() const {
+		const Point c = (pMin + pMax) * .5f;
+		const float dx = c.x - pMax.x, dy = c.y - pMax.y, dz = c.z - pMax.z;
+		const float rad = Inside(c) ? sqrtf(dx * dx + dy * dy + dz * dz) : 0.f;
+		return BSphere(c, rad);
+	}
 	Point Center() const { return (pMin + pMax) * .5f; }
 
 	Point pMin, pMax;

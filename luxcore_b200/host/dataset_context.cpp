@@ -52,6 +52,7 @@ void DataSet::UpdateBBoxes() {
 	else
 		for (size_t i = 0; i < meshes.size(); ++i)
 			bbox = Union(bbox, meshes[i]->GetBBox());
+	bsphere = bbox.BoundingSphere();    // dataset.cpp:104
 }
 
 bool DataSet::HasAccelerator(const AcceleratorType t) const {

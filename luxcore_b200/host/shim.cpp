@@ -192,6 +192,19 @@ LRH_API int lrh_mesh_bbox(void *sp, int mesh, float *out6) {
 	LRH_CATCH
 }
 
+// DataSet::GetBBox / GetBSphere (dataset.h:60-61): out10 = min xyz, max xyz, centre xyz, radius
+LRH_API int lrh_dataset_bounds(void *sp, float *out10) {
+	Session *s = (Session *)sp;
+	LRH_TRY
+	if (!s->dataSet->IsPreprocessed())
+		s->dataSet->Preprocess();
+	const BBox &b = s->dataSet->GetBBox();
+	const BSphere &bs = s->dataSet->GetBSphere();
+	out10[0] = b.pMin.x; out10[1] = b.pMin.y; out10[2] = b.pMin.z; out10[3] = b.pMax.x; out10[4] = b.pMax.y; out10[5] = b.pMax.z;
+	out10[6] = bs.center.x; out10[7] = bs.center.y; out10[8] = bs.center.z; out10[9] = bs.rad;
+	LRH_CATCH
+}
+
 // ---- device lifecycle ----
 
 // Context::AddIntersectionDevices(descs[deviceIndex]) + SetDataSet + Start

@@ -20,7 +20,7 @@ EXPORTS = [
     "lrh_last_error", "lrh_create", "lrh_destroy", "lrh_device_description_count", "lrh_add_shape", "lrh_add_plain",
     "lrh_add_instance", "lrh_add_motion", "lrh_preprocess", "lrh_build_accelerator", "lrh_bvh_node_count",
     "lrh_bvh_nodes", "lrh_mbvh_root_node_count", "lrh_mbvh_root_nodes", "lrh_mbvh_leaf_count",
-    "lrh_mbvh_leaf_node_count", "lrh_mbvh_leaf_nodes", "lrh_mesh_bbox", "lrh_start", "lrh_stop", "lrh_native_device", "lrh_native_scene",
+    "lrh_mbvh_leaf_node_count", "lrh_mbvh_leaf_nodes", "lrh_mesh_bbox", "lrh_dataset_bounds", "lrh_start", "lrh_stop", "lrh_native_device", "lrh_native_scene",
     "lrh_accelerator_type", "lrh_trace_host", "lrh_trace_device", "lrh_finish", "lrh_trace_ray",
     "lrh_set_instance_transform", "lrh_update", "lrh_stats_total_rays", "lrh_used_memory", "lrh_machine_epsilon",
     "lrh_matrix_inverse",
@@ -56,6 +56,7 @@ def lib():
             "lrh_mbvh_leaf_node_count": (u32, [vp, u32]),
             "lrh_mbvh_leaf_nodes": (vp, [vp, u32]),
             "lrh_mesh_bbox": (i32, [vp, i32, vp]),
+            "lrh_dataset_bounds": (i32, [vp, vp]),
             "lrh_start": (i32, [vp, i32]),
             "lrh_stop": (i32, [vp]),
             "lrh_native_device": (vp, [vp]),
@@ -172,6 +173,12 @@ class Session:
         out = np.zeros(6, dtype=np.float32)
         _check(lib().lrh_mesh_bbox(self.h, i, _ptr(out)))
         return out
+
+    def dataset_bounds(self):
+        """DataSet::GetBBox / GetBSphere -> (min xyz, max xyz, centre xyz, radius)."""
+        out = np.zeros(10, dtype=np.float32)
+        _check(lib().lrh_dataset_bounds(self.h, _ptr(out)))
+        return out[:3].copy(), out[3:6].copy(), out[6:9].copy(), float(out[9])
 
     # ---- builder output (for parity tests) ----
     def bvh_nodes(self):

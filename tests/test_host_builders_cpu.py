@@ -126,3 +126,21 @@ def test_sah_builder_optimised_tree_is_cheaper_and_deterministic(name, tree_type
     _check_tree(legacy, desc.triangle_count(), tree_type)
     assert _expected_node_visits(a) < 0.97 * _expected_node_visits(legacy), (_expected_node_visits(a), _expected_node_visits(legacy))
     assert a.shape[0] <= legacy.shape[0]
+
+
+@pytest.mark.parametrize("name", ["cornell", "bigmonkey-instances", "bigmonkey-motion"])
+def test_dataset_bbox_and_bsphere(name):
+    """DataSet::GetBBox = union of the mesh boxes (instances / motion included, dataset.cpp:91-104);
+    GetBSphere = BBox::BoundingSphere (bbox.cpp:65-75): centre of the box, radius to its max corner."""
+    desc = S.load_fixture(name)
+    s = _session(desc, "CLASSIC")
+    lo, hi, c, rad = s.dataset_bounds()
+    boxes = np.stack([s.mesh_bbox(i) for i in range(len(desc.meshes))])
+    assert np.array_equal(lo, boxes[:, :3].min(axis=0)) and np.array_equal(hi, boxes[:, 3:].max(axis=0))
+    osc = H.oracle_scene(desc)
+    for i in range(len(desc.meshes)):
+        assert np.array_equal(boxes[i], np.asarray(osc.mesh_bbox(i), dtype=np.float32).reshape(6))
+    cc = (lo + hi) * np.float32(0.5)
+    assert np.array_equal(c, cc)
+    d = (cc - hi).astype(np.float32)
+    assert rad == float(np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
