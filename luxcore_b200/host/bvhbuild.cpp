@@ -401,6 +401,7 @@ namespace {
 static const size_t kOptMaxPrims = 4u << 20;
 static const size_t kReinsertMaxPrims = 1u << 18;
 static const int kReinsertPasses = 3;
+static const size_t kMaxStepsPerSearch = 2048;      // typical searches take ~140 steps; boxes that all overlap would visit everything
 static const size_t kOptStepBudget = 256u << 20;    // search steps of the optimisation (deterministic bound)
 
 struct OptBuilder {
@@ -447,24 +448,31 @@ struct OptBuilder {
 	}
 
 	// ---- 2. insertion-based optimisation
+	std::vector<int> height;    // leaves 0, inner nodes 1 + max over children
+	int maxHeight;              // no move may make the tree deeper than this (the traversal stack is sized by it)
+
 	void Refit(int id) {
 		while (id >= 0) {
 			const BBox nb = Union(box[kid0[id]], box[kid1[id]]);
 			const float na = nb.SurfaceArea();
-			if (na == area[id] && nb.pMin.x == box[id].pMin.x && nb.pMin.y == box[id].pMin.y && nb.pMin.z == box[id].pMin.z &&
+			const int nh = 1 + std::max(height[kid0[id]], height[kid1[id]]);
+			if (nh == height[id] && na == area[id] && nb.pMin.x == box[id].pMin.x && nb.pMin.y == box[id].pMin.y && nb.pMin.z == box[id].pMin.z &&
 					nb.pMax.x == box[id].pMax.x && nb.pMax.y == box[id].pMax.y && nb.pMax.z == box[id].pMax.z)
 				break;
 			box[id] = nb;
 			area[id] = na;
+			height[id] = nh;
 			id = parent[id];
 		}
 	}
 
-	struct Cand { float induced; int id; };
+	struct Cand { float induced; int id; int depth; };
 	struct CandLess { bool operator()(const Cand &a, const Cand &b) const { return a.induced > b.induced; } };
 
 	// Takes subtree n out of the tree (its parent p goes with it) and puts it back at the cheapest
-	// position.  Returns the number of search steps.
+	// position -- where it was unless another position is STRICTLY cheaper (equal costs must not
+	// reshuffle the tree: a set of identical boxes would end up as one long chain) and keeps the tree
+	// within maxHeight.  Returns the number of search steps.
 	size_t Reinsert(const int n, std::vector<Cand> &heap) {
 		const int p = parent[n];
 		if (p < 0)
@@ -480,29 +488,33 @@ struct OptBuilder {
 
 		const BBox nb = box[n];
 		const float an = area[n];
-		float best = std::numeric_limits<float>::infinity();
+		const int hn = height[n];
+		// cost of the position it came from
+		float best = Union(box[s], nb).SurfaceArea();
+		for (int a = g; a >= 0; a = parent[a])
+			best += Union(box[a], nb).SurfaceArea() - area[a];
 		int bestAt = s;
 		size_t steps = 0;
 		heap.clear();
-		Cand c0 = { 0.f, root };
+		Cand c0 = { 0.f, root, 0 };
 		heap.push_back(c0);
 		while (!heap.empty()) {
 			std::pop_heap(heap.begin(), heap.end(), CandLess());
 			const Cand c = heap.back();
 			heap.pop_back();
-			if (c.induced + an >= best)
-				break;          // every remaining candidate is at least as expensive
+			if (c.induced + an >= best || steps >= kMaxStepsPerSearch)
+				break;          // every remaining candidate is at least as expensive (or: heavily overlapping input, give up)
 			++steps;
 			const float direct = Union(box[c.id], nb).SurfaceArea();
 			const float total = c.induced + direct;
-			if (total < best) {
+			if (total < best && c.depth + 1 + std::max(height[c.id], hn) <= maxHeight) {
 				best = total;
 				bestAt = c.id;
 			}
 			if (!IsLeafId(c.id)) {
 				const float below = total - area[c.id];
 				if (below + an < best) {
-					Cand a = { below, kid0[c.id] }, b2 = { below, kid1[c.id] };
+					Cand a = { below, kid0[c.id], c.depth + 1 }, b2 = { below, kid1[c.id], c.depth + 1 };
 					heap.push_back(a); std::push_heap(heap.begin(), heap.end(), CandLess());
 					heap.push_back(b2); std::push_heap(heap.begin(), heap.end(), CandLess());
 				}
@@ -519,6 +531,7 @@ struct OptBuilder {
 		parent[x] = p; parent[n] = p;
 		box[p] = Union(box[x], nb);
 		area[p] = box[p].SurfaceArea();
+		height[p] = 1 + std::max(height[x], hn);
 		if (px >= 0)
 			Refit(px);
 		return steps;
@@ -639,6 +652,29 @@ struct OptBuilder {
 		kid1.assign(N - 1, -1);
 		root = BuildBinary(0, N, 4);
 		for (size_t i = 0; i < box.size(); ++i) area[i] = box[i].SurfaceArea();
+		// heights bottom-up (children of inner node m - 1 lie on either side of cut m: explicit post-order)
+		height.assign(box.size(), 0);
+		{
+			std::vector<int> stack, order;
+			stack.push_back(root);
+			while (!stack.empty()) {
+				const int id = stack.back();
+				stack.pop_back();
+				if (IsLeafId(id)) continue;
+				order.push_back(id);
+				stack.push_back(kid0[id]);
+				stack.push_back(kid1[id]);
+			}
+			for (size_t r = order.size(); r-- > 0;)
+				height[order[r]] = 1 + std::max(height[kid0[order[r]]], height[kid1[order[r]]]);
+		}
+		// head-room for the optimisation: half as much again as the SAH tree's own height (not binding on the
+		// reference scenes; it is what keeps nested / coincident geometry from turning into a chain)
+		{
+			const char *e = getenv("LRB_BVH_HEADROOM");
+			const int pct = e ? atoi(e) : 50;
+			maxHeight = height[root] + height[root] * pct / 100 + 4;
+		}
 		const bool verbose = getenv("LRB_BVH_VERBOSE") != nullptr;
 		const double a0 = InnerAreaSum() / area[root];
 		if (optimisePasses > 0 && N >= 4)
@@ -647,6 +683,8 @@ struct OptBuilder {
 		if (verbose)
 			fprintf(stderr, "[bvhbuild] %u prims: binary SAH %.3f -> optimised %.3f -> %u-ary %.3f (expected node visits of a long random ray)\n",
 					N, a0, InnerAreaSum() / area[root], K, (double)CostOf(root, 1) / area[root]);
+		if (verbose)
+			fprintf(stderr, "[bvhbuild] binary height %d (limit %d)\n", height[root], maxHeight);
 		Emit(root, out);
 	}
 };

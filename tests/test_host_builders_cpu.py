@@ -144,3 +144,45 @@ def test_dataset_bbox_and_bsphere(name):
     assert np.array_equal(c, cc)
     d = (cc - hi).astype(np.float32)
     assert rad == float(np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
+
+
+def _one_mesh_scene(name, verts, tris):
+    d = S.SceneDesc(name)
+    d.add_shape(np.asarray(verts, np.float32), np.asarray(tris, np.uint32))
+    d.add_plain(0)
+    return d
+
+
+@pytest.mark.parametrize("kind", ["identical", "nested", "collinear", "points"])
+@pytest.mark.parametrize("tree_type", [2, 4, 8])
+def test_sah_builder_keeps_degenerate_geometry_shallow(kind, tree_type):
+    """Coincident, nested, collinear and zero-size triangles: equal costs must not let the optimisation turn
+    the tree into a chain (the traversal stack, and the kernel's spill buffers, are sized by the worst-case
+    depth), searches through boxes that all overlap are bounded, and results stay those of the oracle."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    if kind == "identical":
+        verts = np.tile(np.asarray([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (n, 1))
+    elif kind == "nested":
+        s = (1.002 ** np.arange(n)).astype(np.float32)
+        verts = np.stack([np.stack([-s, -s, 0 * s], 1), np.stack([s, -s, 0 * s], 1), np.stack([0 * s, s, 0 * s], 1)], 1).reshape(-1, 3)
+    elif kind == "collinear":
+        x = rng.random(3 * n).astype(np.float32)
+        verts = np.stack([x, np.zeros_like(x), np.zeros_like(x)], 1)
+    else:
+        g = np.stack(np.meshgrid(np.arange(15), np.arange(20), np.arange(10), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        verts = np.repeat(g, 3, axis=0)
+    desc = _one_mesh_scene(kind, verts, np.arange(3 * n).reshape(-1, 3))
+    s = _session(desc, "EMBREE_BINNED_SAH", tree_type)
+    s.build_accelerator("BVH")
+    nodes = s.bvh_nodes().copy()
+    _check_tree(nodes, n, tree_type)
+    osc = H.oracle_scene(desc)
+    verts2, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(nodes, verts2, offs)
+    assert emu.info()["stack_need"] <= 8 * int(np.ceil(np.log2(n))) + 32, emu.info()
+    lo, hi = desc.bbox()
+    rays = R.to_numpy_rays(R.uniform_rays(lo - 0.5, hi + 0.5, 3000, seed=3))
+    ref = O.BVH(osc, nodes=nodes).intersect(rays)
+    rep = H.compare_hits_tie_aware(emu.trace(rays), ref, rays, osc, what=kind, max_ties=3000)
+    assert rep["index_mismatch"] == 0 and rep["value_mismatch"] == 0
