@@ -157,7 +157,7 @@ LRB_API int lrb_device_get_props(lrb_device *dev, lrb_device_props *out);
 LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
 LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
 /* Tunables (strings): "kernel" = "persistent"|"simple", "blocks_per_sm", "smem_depth",
- * "refill_below", "tri_bias", "host_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
+ * "refill_below", "tri_bias", "inst_bias", "host_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
  * "sort_bits", "sort_min_rays", "gather_stores", "gather_chunk_shift", "wide_stores",
  * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2). */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);

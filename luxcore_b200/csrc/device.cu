@@ -58,6 +58,7 @@ struct lrb_device {
 	int persistent;                 // 1 = TracePersistent, 0 = TraceStatic
 	int smemDepth;                  // shared-memory stack entries per thread
 	int refillBelow;
+	int instBias;                   // two-level scenes: see TraceArgs::instBias
 	int triBias;
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
@@ -165,6 +166,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->smemDepth = 16;
 	dev->refillBelow = 24;
 	dev->triBias = 8;
+	dev->instBias = 8;
 	dev->sortRays = 2;
 	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
 	dev->wideStores = 2;
@@ -248,6 +250,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "tri_bias") {
 		if (iv < 1 || iv > 64) return Fail(LRB_ERR_INVALID, "tri_bias out of range");
 		dev->triBias = iv;
+	} else if (k == "inst_bias") {
+		if (iv < 0 || iv > 64) return Fail(LRB_ERR_INVALID, "inst_bias out of range");
+		dev->instBias = iv;
 	} else if (k == "gather_stores") {
 		dev->gatherStores = iv ? 1 : 0;
 	} else if (k == "gather_chunk_shift") {
@@ -751,6 +756,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.stats = s->dStats;
 	a.refillBelow = (uint32_t)dev->refillBelow;
 	a.triBias = (uint32_t)dev->triBias;
+	a.instBias = (uint32_t)dev->instBias;
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;

@@ -130,6 +130,7 @@ struct TraceArgs {
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
+	uint32_t instBias;          // two-level: instances are entered when nInst * instBias >= max(nNode * 4, nTri * triBias); 0 = at once
 	TraceStats *stats;          // STATS kernels only
 	// Multi-GPU gather fused into the trace: when set, every RayHit record is ALSO stored here -- this
 	// rank's slice of the gather buffer on the destination GPU, peer-mapped over NVLink.  The five
@@ -356,19 +357,33 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersisten
 					state = kUnsaved;
 			}
 			__syncwarp();
-			const bool ready = state == kActive;
-			const bool wantTri = ready && (s.cur & kTagTri) != 0;
-			const bool wantNode = ready && (s.cur & kTagTri) == 0;
-			const int nTri = __popc(__ballot_sync(0xffffffffu, wantTri));
-			const int nNode = __popc(__ballot_sync(0xffffffffu, wantNode));
-			if (nTri * (int)a.triBias >= nNode * 4) {
-				if (wantTri)
+			LaneWork work = state == kActive ? WorkOf<TWO_LEVEL>(s.cur) : kWorkNone;
+			int nTri = __popc(__ballot_sync(0xffffffffu, work == kWorkTri));
+			int nNode = __popc(__ballot_sync(0xffffffffu, work == kWorkNode));
+			int nInst = 0;
+			if (TWO_LEVEL) {
+				// Entering an instance is a third kind of work, and Resolve leaves it to this place (see
+				// EnterInstance): lanes that reached an instance reference wait until they outweigh the lanes
+				// with node / triangle work, then enter together; the entered lanes join this iteration's vote.
+				nInst = __popc(__ballot_sync(0xffffffffu, work == kWorkInstance));
+				if (VoteEnterInstances(nInst, nNode, nTri, a.instBias, a.triBias)) {
+					if (work == kWorkInstance) {
+						EnterInstance<false>(a.sc, a.rays[rayIdx], s, stk, nullptr);
+						work = WorkOf<TWO_LEVEL>(s.cur);
+					}
+					__syncwarp();
+					nNode = __popc(__ballot_sync(0xffffffffu, work == kWorkNode));
+					nInst = 0;
+				}
+			}
+			if (VoteTrianglePhase(nTri, nNode, a.triBias)) {
+				if (work == kWorkTri)
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
 			} else {
-				if (wantNode)
+				if (work == kWorkNode)
 					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
 			}
-			nLive = nTri + nNode;
+			nLive = nTri + nNode + nInst;
 		} while (nLive >= floorLanes);
 	}
 }

@@ -365,6 +365,25 @@ LRB_HD bool NeedsResolve(const uint32_t cur) {
 // True for kTagInstance | index (not the sentinel, not kNullIndex): the ray is about to enter a leaf tree.
 LRB_HD bool IsInstanceRef(const uint32_t cur) { return (cur >> 30) == 2u; }
 
+// What a live ray holds after Resolve -- the kind of work it waits for.  One definition for the CUDA
+// kernels and for the host model of their scheduling (tests/cpp/wide_emulation.cpp).
+enum LaneWork { kWorkNone = 0, kWorkNode = 1, kWorkTri = 2, kWorkInstance = 3 };
+template <bool TWO_LEVEL>
+LRB_HD LaneWork WorkOf(const uint32_t cur) {
+	if (TWO_LEVEL) {
+		if (cur == kNullIndex || cur == kStackSentinel) return kWorkNone;     // (an empty leaf tree leaves kNullIndex behind)
+		if (IsInstanceRef(cur)) return kWorkInstance;
+	}
+	return (cur & kTagTri) ? kWorkTri : kWorkNode;
+}
+// Phase votes of a warp.  Triangle phase when nTri * triBias >= nNode * 4 (4 = plain majority);
+// instances are entered when the lanes waiting for it outweigh both other kinds (instBias 0: at once).
+LRB_HD bool VoteTrianglePhase(const int nTri, const int nNode, const uint32_t triBias) { return nTri * (int)triBias >= nNode * 4; }
+LRB_HD bool VoteEnterInstances(const int nInst, const int nNode, const int nTri, const uint32_t instBias, const uint32_t triBias) {
+	const int a = nNode * 4, b = nTri * (int)triBias;
+	return nInst > 0 && (instBias == 0 || nInst * (int)instBias >= (a > b ? a : b));
+}
+
 // Enters the leaf tree s.cur refers to (mbvhaccel.cpp:312-333): ray into instance space, sentinel on
 // the stack, s.cur = root of the leaf tree -- or kNullIndex for an empty leaf tree (the next Resolve
 // pops on).  Kept out of Resolve's pop loop: that loop runs a different number of trips on every lane,

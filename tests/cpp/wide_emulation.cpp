@@ -4,6 +4,7 @@
 // layout conversion, stack discipline, tie rule and two-level logic can be checked against the
 // oracle on a machine without a GPU (pytest -m "not gpu").  The GPU tests run the same
 // traverse.h body through the CUDA kernels.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -87,6 +88,8 @@ struct SimWarp {
 
 template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n,
 		uint32_t nWarps, uint32_t refillBelow, uint32_t triBias, unsigned long long *out16) {
+	const uint32_t instBias = triBias >> 16;      // packed by the Python wrapper: low 16 bits tri_bias, high 16 bits inst_bias
+	triBias &= 0xffffu;
 	const SceneView v = View(w);
 	std::vector<SimWarp> warps(nWarps);
 	uint32_t counter = 0;
@@ -157,25 +160,34 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					}
 				}
 				popTrips += maxTrips;
+				// ---- from here on: the same statements as TracePersistent's loop body (trace_kernels.cuh), with
+				// ballots replaced by loops over the lanes; the votes are the kernels' own functions (traverse.h)
+				LaneWork work[32];
+				int nTri = 0, nNode = 0, nInst = 0;
+				for (int l = 0; l < 32; ++l) {
+					work[l] = W.lane[l].state == 1 ? WorkOf<TWO>(W.lane[l].s.cur) : kWorkNone;
+					nTri += work[l] == kWorkTri;
+					nNode += work[l] == kWorkNode;
+					if (TWO) nInst += work[l] == kWorkInstance;
+				}
 				if (TWO) {
-					// instance entries of this iteration, converged (trace_kernels.cuh)
-					for (int l = 0; l < 32; ++l) {
-						SimLane &L = W.lane[l];
-						if (L.state == 1 && IsInstanceRef(L.s.cur)) {
-							EnterInstance<false>(v, rays[L.rayIdx], L.s, L.stk, nullptr);
-							++instLanes;
-							maxInst = 1;
+					if (VoteEnterInstances(nInst, nNode, nTri, instBias, triBias)) {
+						for (int l = 0; l < 32; ++l) {
+							SimLane &L = W.lane[l];
+							if (work[l] == kWorkInstance) {
+								EnterInstance<false>(v, rays[L.rayIdx], L.s, L.stk, nullptr);
+								work[l] = WorkOf<TWO>(L.s.cur);
+								++instLanes;
+								maxInst = 1;
+							}
 						}
+						nNode = 0;
+						for (int l = 0; l < 32; ++l) nNode += work[l] == kWorkNode;
+						nInst = 0;
 					}
 				}
 				instTrips += maxInst;
-				int nTri = 0, nNode = 0;
-				for (int l = 0; l < 32; ++l) {
-					const SimLane &L = W.lane[l];
-					if (L.state != 1 || (TWO && L.s.cur == kNullIndex)) continue;
-					if (L.s.cur & kTagTri) ++nTri; else ++nNode;
-				}
-				if (nTri * (int)triBias >= nNode * 4) {
+				if (VoteTrianglePhase(nTri, nNode, triBias)) {
 					if (nTri) {
 						++triPhases;
 						triLanes += (unsigned long long)nTri;
@@ -183,7 +195,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 						int accepted = 0;
 						for (int l = 0; l < 32; ++l) {
 							SimLane &L = W.lane[l];
-							if (L.state == 1 && L.s.cur != kNullIndex && (L.s.cur & kTagTri)) {
+							if (work[l] == kWorkTri) {
 								const float before = L.s.maxt;
 								const uint32_t bt = L.s.bestTri, bi = L.s.bestInst, hm = L.s.hitMesh;
 								TriStep<TWO, false>(v, L.s, nullptr);
@@ -197,20 +209,18 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					nodeLanes += (unsigned long long)nNode;
 					{
 						int slow = 0;
-						for (int l = 0; l < 32; ++l) {
-							const SimLane &L = W.lane[l];
-							if (L.state == 1 && L.s.cur != kNullIndex && !(L.s.cur & kTagTri) && L.stk.n.size() + 4 > smemDepth) ++slow;
-						}
+						for (int l = 0; l < 32; ++l)
+							if (work[l] == kWorkNode && W.lane[l].stk.n.size() + 4 > smemDepth) ++slow;
 						if (slow) { ++slowPhases; slowLanes += (unsigned long long)slow; }
 					}
 					idlePhaseLanes += (unsigned long long)nTri;
 					for (int l = 0; l < 32; ++l) {
 						SimLane &L = W.lane[l];
-						if (L.state == 1 && L.s.cur != kNullIndex && !(L.s.cur & kTagTri))
+						if (work[l] == kWorkNode)
 							NodeStep<TWO, false>(v, L.s, L.stk, nullptr);
 					}
 				}
-				nLive = nTri + nNode;
+				nLive = nTri + nNode + nInst;
 			} while (nLive >= floorLanes);
 		}
 	}

@@ -278,8 +278,9 @@ WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_pha
                    "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes", "slow_push_phases", "slow_push_lanes", "instance_trips", "instance_lanes"]
 
 
-def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8):
+def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8):
     """Scheduling model of TracePersistent (tests/cpp/wide_emulation.cpp WarpSim): -> (hits, counts)."""
+    tri_bias = (tri_bias & 0xFFFF) | (inst_bias << 16)
     rays = np.ascontiguousarray(rays)
     hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
     out = np.zeros(18, dtype=np.uint64)

@@ -156,3 +156,25 @@ def test_host_layer_sah_trees_two_level(fixture, kw):
     assert rep["hits"] > 0.1 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
     assert st["max_stack"] <= emu.info()["stack_need"]
+
+
+@pytest.mark.parametrize("inst_bias", [0, 2, 8, 64])
+def test_two_level_scheduling_model_matches_per_ray_traversal(inst_bias):
+    """The warp-level replay of the persistent kernel's loop (three-way vote: node / triangle phase, entering
+    instances) must give the per-ray traversal's hits and do the same traversal work for any vote setting:
+    lanes that wait for an instance phase must neither be dropped nor enter twice."""
+    desc = S.load_fixture("lightinstances", max_objects=300)
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=4)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    rays = _rays(desc, 20000, 53)
+    rays["flags"][::11] = 1
+    ref, st = emu.trace(rays, want_stats=True)
+    for n_warps, refill in ((1, 24), (32, 24), (8, 1)):
+        hits, c = H.warp_sim(emu, rays, n_warps=n_warps, refill_below=refill, tri_bias=8, inst_bias=inst_bias)
+        assert hits.tobytes() == ref.tobytes()
+        assert c["rays"] == st["rays"] and c["node_lanes"] == st["wide_nodes"] and c["tri_lanes"] == st["triangles"]
+        assert c["instance_lanes"] == st["instances"]
+    live = rays["flags"] == 0           # masked rays are a device-side notion (bvh.cl:242-244): RayHit untouched
+    got = H.compare_hits(ref[live], mb.intersect(rays[live]), rays[live], what="two-level model")
+    assert got["bit_exact_hits"] == got["hits"] > 0
