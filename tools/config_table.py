@@ -12,12 +12,20 @@ import bench as B
 from luxcore_b200 import capi, hostapi, rays as R, scenes as S
 from oracle import oracle as O
 
+import argparse
+_ap = argparse.ArgumentParser()
+_ap.add_argument("--only", action="append", default=[], help="run only these scenes")
+_ap.add_argument("--opt", action="append", default=[], help="device option key=value")
+ARGS = _ap.parse_args()
+
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 out = []
 
 def run(name, accel, builder, kinds, n, max_objects=None, time_range=None, sample=100000):
+    if ARGS.only and name not in ARGS.only:
+        return
     try:
         desc = S.load_fixture(name, max_objects=max_objects) if max_objects else S.load_fixture(name)
         t0 = time.perf_counter()
@@ -25,6 +33,9 @@ def run(name, accel, builder, kinds, n, max_objects=None, time_range=None, sampl
         sess.build_accelerator(accel)
         build_s = time.perf_counter() - t0
         sess.start(0); sess.set_stream(stream.cuda_stream)
+        for kv in ARGS.opt:
+            k, v = kv.split("=", 1)
+            sess.set_option(k, v)
         scene = sess.native_scene(); info = scene.info()
         def trace_fn(r):
             h = torch.empty((r.shape[0], 20), dtype=torch.uint8, device=dev)
@@ -83,4 +94,5 @@ run("bigmonkey-instances", "MBVH", "EMBREE_BINNED_SAH", ["camera", "bounce-1"], 
 run("bigmonkey-motion", "MBVH", "EMBREE_BINNED_SAH", ["camera"], 4 * M, time_range=(0.0, 1.0))
 run("classroom", "BVH", "EMBREE_BINNED_SAH", ["bounce-2"], 16 * M)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "config_table.json"), "w"), indent=1)
+suffix = ("_" + "_".join(ARGS.only) if ARGS.only else "") + ("_" + "_".join(o.replace("=", "-") for o in ARGS.opt) if ARGS.opt else "")
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "config_table%s.json" % suffix), "w"), indent=1)

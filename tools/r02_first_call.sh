@@ -34,6 +34,12 @@ T=900 run ncu --set full --clock-control none --import-source on -k regex:TraceP
 	python bench.py --scene soup:16000000 --rays 33554432 --steps 1 --warmup 3 --no-cpu-baseline
 T=200 run python tools/ncu_summary.py gpurun_out/r02_soup16m.ncu-rep
 
+# 4b. two-level scenes: instance-entry vote (inst_bias 0 = enter at once, 8 = default)
+for ib in 0 4 8 16; do
+	echo "--- lightinstances inst_bias=$ib"
+	T=600 run python tools/config_table.py --only lightinstances --opt inst_bias=$ib
+done
+
 # 5. the other configurations (MBVH: instance entry out of the pop loop) + one MBVH capture
 T=1200 run python tools/config_table.py
 cp -f gpurun_out/config_table.json gpurun_out/r02_config_table.json 2>/dev/null
