@@ -635,7 +635,16 @@ void BuildWideMBVH(const lrb_mbvh_desc &d, WideScene *out) {
 		in.xyz = d.leaf_vertices[i]; in.nVerts = d.leaf_n_vertices[i];
 		in.meshOff = &zeroOff; in.nMeshes = 1;
 		uint32_t need = 0;
-		out->leafRootWide.push_back(ConvertTree(in, out, &need));
+		uint32_t leafRoot = ConvertTree(in, out, &need);
+		// ConvertTree puts a one-child entry node in front of a tree whose root is an inner node: it holds
+		// the root's own box, which the reference tests first (bvhaccel.cpp:245-255).  For a leaf tree that
+		// test has already happened in world space -- the instance's slot in the root tree bounds this very
+		// box (InstanceWorldBox) -- so instances enter at the real root node: one node visit less per
+		// instance entry (lightinstances: 3.3-3.6 entries per ray).  Boxes only cull; a ray that would have
+		// failed the instance-space root box now visits the root node and fails its children's boxes.
+		if (leafRoot != kNullIndex && (out->wide[leafRoot].flags & kNodeEntry))
+			leafRoot = out->wide[leafRoot].child[0];
+		out->leafRootWide.push_back(leafRoot);
 		out->leafStackNeed.push_back(need);
 		// root box of the leaf tree in instance space: its node 0, or the lone triangle's build box
 		float lb[6] = { kInfF, kInfF, kInfF, -kInfF, -kInfF, -kInfF };      // empty tree: never entered anyway
