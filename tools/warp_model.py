@@ -23,7 +23,10 @@ import helpers as H
 import tree_stats as TS
 from luxcore_b200 import hostapi
 
-# warp instructions per executed section (SASS of TracePersistent<0,1,0>, sm_100a, this tree)
+# Warp instructions per EXECUTED section: counted by hand along the common path through the SASS of
+# TracePersistent<0,1,0,0> (sm_100a).  tools/sass_costs.py attributes the same SASS to source functions
+# automatically (static counts: node phase 186 + 67 for the rarely taken spilling push, triangle phase
+# incl. gate 126, pop loop 31 over both its paths, re-fill 126) -- run it after touching the kernel.
 COST = {"inner_fixed": 30,      # Resolve entry test, __syncwarp, two ballots, vote, loop branch
         "pop_trip": 16,         # one trip of the pop loop (longest lane decides)
         "node_phase": 164,      # fetch + decode + 4 slab tests + network + predicated pushes
