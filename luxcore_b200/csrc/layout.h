@@ -15,8 +15,9 @@
 //       * MBVH root leaf : world-space bounds of the instance (its leaf tree's root box through the
 //                          inverse of mInv, grown; relayout.cpp InstanceWorldBox) -- the reference
 //                          enters every instance of a visited root node (mbvhaccel.cpp:312) and then
-//                          tests that root box in instance space; motion-blurred instances take the
-//                          whole grid of the node; reference = kTagInstance | index;
+//                          tests that root box in instance space; motion-blurred instances get the
+//                          bounds of that box over all times (relayout.cpp MotionWorldBox);
+//                          reference = kTagInstance | index;
 //       * unused slot    : an inverted box (lo = 255, hi = 0) and kNullIndex.
 //     The four boxes are stored on a per-node grid: origin = min corner of the union of the slot
 //     boxes, one power-of-two step per axis, 8 bits per plane, lo rounded down and hi rounded up,

@@ -5,6 +5,7 @@
 // upload (bvhaccelhw.cpp:126-145, mbvhaccelhw.cpp:380-427).
 
 #include "relayout.h"
+#include "traverse.h"       // MotionSample: the kernels' own MotionSystem::Sample, compiled for the host
 
 #include <algorithm>
 #include <cmath>
@@ -63,6 +64,8 @@ struct TreeInput {
 	uint32_t nTransforms, nMotions;
 	const std::vector<float> *leafBox;      // 6 floats per unique leaf: its tree's root box (instance space)
 	const float *minv;                      // 16 floats per transform
+	const std::vector<uint32_t> *motionFirst, *motionLast;
+	const std::vector<DevInterp> *interps;
 };
 
 static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr) {
@@ -275,14 +278,18 @@ static bool Invert4x4(const float *m, double out[16]) {
 // inverse of mInv, grown generously.  The reference enters every instance of a visited root node and
 // then tests the same root box in instance space (mbvhaccel.cpp:312-333 -> bvhaccel.cpp:245-255); a ray
 // that misses the world-space bounds of that box misses the box itself, so skipping the instance
-// changes nothing.  Returns false (=> the slot takes the whole grid) for motion-blurred instances,
-// singular or projective matrices and non-finite results.
+// changes nothing.  Motion-blurred instances: MotionWorldBox below.  Returns false (=> the slot takes the
+// whole grid) for singular or projective matrices and non-finite results.
+static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const float *lb, float lo[3], float hi[3]);
+
 static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float lo[3], float hi[3]) {
-	if (!in.leafBox || nd.bvhLeaf.motionIndex != kNullIndex)
+	if (!in.leafBox)
 		return false;
 	const float *lb = in.leafBox->data() + 6 * (size_t)nd.bvhLeaf.leafIndex;
 	for (int k = 0; k < 6; ++k)
 		if (!std::isfinite(lb[k])) return false;
+	if (nd.bvhLeaf.motionIndex != kNullIndex)
+		return MotionWorldBox(in, nd, lb, lo, hi);
 	double M[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
 	if (nd.bvhLeaf.transformIndex != kNullIndex) {
 		if (!in.minv || !Invert4x4(in.minv + 16 * (size_t)nd.bvhLeaf.transformIndex, M))
@@ -302,6 +309,78 @@ static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float 
 	}
 	const double diag = std::max(std::max(whi[0] - wlo[0], whi[1] - wlo[1]), whi[2] - wlo[2]);
 	const double grow = 1e-4 * diag + 4e-6 * mag + 1e-6;    // far above the float rounding of the reference's ray transform
+	for (int r = 0; r < 3; ++r) {
+		lo[r] = (float)(wlo[r] - grow);
+		hi[r] = (float)(whi[r] + grow);
+		if (!std::isfinite(lo[r]) || !std::isfinite(hi[r])) return false;
+		lo[r] = std::nextafter(lo[r], -kInfF);
+		hi[r] = std::nextafter(hi[r], kInfF);
+	}
+	return true;
+}
+
+// World-space bounds of a motion-blurred instance over ALL times: the leaf tree's root box taken through
+// the inverse of the sampled world->instance matrix (the kernels' own MotionSample) at 256 times per
+// interpolation segment plus every segment boundary, grown by 1.25 x the largest displacement of a box
+// corner between two consecutive samples -- a point of the moving box at a time between two samples is
+// never farther from its sampled positions than the path it travels between them -- plus the margins
+// of InstanceWorldBox.  (The reference's own root-tree boxes are unions over 1 025 samples with no margin,
+// motionsystem.cpp:75-88.)  Times outside the motion system's range clamp to its first / last key.
+static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const float *lb, float lo[3], float hi[3]) {
+	if (!in.motionFirst || !in.motionLast || !in.interps || nd.bvhLeaf.motionIndex >= in.motionFirst->size())
+		return false;
+	SceneView sv;
+	memset(&sv, 0, sizeof(sv));
+	sv.motionFirst = in.motionFirst->data();
+	sv.motionLast = in.motionLast->data();
+	sv.interps = in.interps->data();
+	const uint32_t first = (*in.motionFirst)[nd.bvhLeaf.motionIndex], last = (*in.motionLast)[nd.bvhLeaf.motionIndex];
+	std::vector<float> times;
+	for (uint32_t i = first; i <= last && i < in.interps->size(); ++i) {
+		const DevInterp &it = (*in.interps)[i];
+		if (std::isfinite(it.startTime)) times.push_back(it.startTime);
+		if (std::isfinite(it.endTime)) times.push_back(it.endTime);
+	}
+	if (times.empty())
+		times.push_back(0.f);
+	std::sort(times.begin(), times.end());
+	times.erase(std::unique(times.begin(), times.end()), times.end());
+	const size_t nKeys = times.size();
+	const int perSegment = 256;
+	for (size_t k = 0; k + 1 < nKeys; ++k)
+		for (int j = 1; j < perSegment; ++j)
+			times.push_back((float)((double)times[k] + ((double)times[k + 1] - (double)times[k]) * j / perSegment));
+	std::sort(times.begin(), times.end());
+
+	double wlo[3] = { 1e300, 1e300, 1e300 }, whi[3] = { -1e300, -1e300, -1e300 }, mag = 0.0, step = 0.0;
+	double prev[8][3];
+	bool havePrev = false;
+	for (size_t ti = 0; ti < times.size(); ++ti) {
+		float m[16];
+		MotionSample(sv, nd.bvhLeaf.motionIndex, times[ti], m);
+		double M[16];
+		if (!Invert4x4(m, M))
+			return false;
+		if (fabs(M[12]) > 1e-12 || fabs(M[13]) > 1e-12 || fabs(M[14]) > 1e-12 || fabs(M[15] - 1.0) > 1e-9)
+			return false;
+		for (int corner = 0; corner < 8; ++corner) {
+			const double p[3] = { lb[(corner & 1) ? 3 : 0], lb[(corner & 2) ? 4 : 1], lb[(corner & 4) ? 5 : 2] };
+			double w[3], d2 = 0.0;
+			for (int r = 0; r < 3; ++r) {
+				w[r] = M[4 * r] * p[0] + M[4 * r + 1] * p[1] + M[4 * r + 2] * p[2] + M[4 * r + 3];
+				if (!std::isfinite(w[r])) return false;
+				wlo[r] = std::min(wlo[r], w[r]);
+				whi[r] = std::max(whi[r], w[r]);
+				mag = std::max(mag, fabs(w[r]));
+				if (havePrev) d2 += (w[r] - prev[corner][r]) * (w[r] - prev[corner][r]);
+				prev[corner][r] = w[r];
+			}
+			step = std::max(step, sqrt(d2));
+		}
+		havePrev = true;
+	}
+	const double diag = std::max(std::max(whi[0] - wlo[0], whi[1] - wlo[1]), whi[2] - wlo[2]);
+	const double grow = 1.25 * step + 1e-4 * diag + 4e-6 * mag + 1e-6;
 	for (int r = 0; r < 3; ++r) {
 		lo[r] = (float)(wlo[r] - grow);
 		hi[r] = (float)(whi[r] + grow);
@@ -607,6 +686,9 @@ static void ConvertRoot(const lrb_bvh_node *rootNodes, uint32_t nRootNodes, uint
 	in.nMotions = nMotions;
 	in.leafBox = &out->leafBox;
 	in.minv = out->minv.empty() ? nullptr : out->minv.data();
+	in.motionFirst = &out->motionFirst;
+	in.motionLast = &out->motionLast;
+	in.interps = &out->interps;
 	const size_t before = out->wide.size();
 	uint32_t need = 0;
 	out->rootWide = ConvertTree(in, out, &need);
