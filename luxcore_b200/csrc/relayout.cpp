@@ -320,7 +320,7 @@ static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float 
 }
 
 // World-space bounds of a motion-blurred instance over ALL times: the leaf tree's root box taken through
-// the inverse of the sampled world->instance matrix (the kernels' own MotionSample) at 256 times per
+// the inverse of the sampled world->instance matrix (the kernels' own MotionSample) at 32 times per
 // interpolation segment plus every segment boundary, grown by 1.25 x the largest displacement of a box
 // corner between two consecutive samples -- a point of the moving box at a time between two samples is
 // never farther from its sampled positions than the path it travels between them -- plus the margins
@@ -346,7 +346,7 @@ static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const fl
 	std::sort(times.begin(), times.end());
 	times.erase(std::unique(times.begin(), times.end()), times.end());
 	const size_t nKeys = times.size();
-	const int perSegment = 256;
+	const int perSegment = 32;
 	for (size_t k = 0; k + 1 < nKeys; ++k)
 		for (int j = 1; j < perSegment; ++j)
 			times.push_back((float)((double)times[k] + ((double)times[k + 1] - (double)times[k]) * j / perSegment));
