@@ -306,6 +306,14 @@ void emu_warp_sim(void *wp, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, u
 	else WarpSim<false>(*w, rays, hits, n, nWarps, refillBelow, triBias, out16);
 }
 
+// The SceneView of the re-laid-out scene (plain struct of host pointers into the handle's arrays), for
+// the lockstep harness of the real kernel source (kernel_lockstep.cpp, a separate library).
+uint32_t emu_scene_view_size() { return (uint32_t)sizeof(SceneView); }
+void emu_scene_view(void *wp, void *out) {
+	const SceneView v = View(*(const WideScene *)wp);
+	memcpy(out, &v, sizeof(v));
+}
+
 int emu_validate_tree(const lrb_bvh_node *nodes, uint32_t n) {
 	std::string e;
 	if (ValidateTree(nodes, n, &e)) return 0;

@@ -203,6 +203,8 @@ class Emu:
             for f in (L.emu_copy_nodes, L.emu_copy_tris, L.emu_copy_gates):
                 f.argtypes = [C.c_void_p, C.c_void_p]
             L.emu_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+            L.emu_scene_view_size.restype = C.c_uint32
+            L.emu_scene_view.argtypes = [C.c_void_p, C.c_void_p]
             L.emu_validate_tree.restype = C.c_int
             L.emu_validate_tree.argtypes = [C.c_void_p, C.c_uint32]
             cls._lib = L
@@ -272,6 +274,49 @@ class Emu:
         if want_stats:
             return hits, dict(zip(["rays", "wide_nodes", "triangles", "instances", "motion_samples", "max_stack"], [int(x) for x in st]))
         return hits
+
+
+class Lockstep:
+    """The product's REAL kernel source (luxcore_b200/csrc/trace_kernels.cuh) compiled for the host against a
+    stand-in <cuda_runtime.h> and run with one OS thread per lane (tests/cpp/kernel_lockstep.cpp)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            d = os.path.join(ROOT, "tests", "cpp")
+            so = os.path.join(d, "libkernel_lockstep.so")
+            csrc = os.path.join(ROOT, "luxcore_b200", "csrc")
+            deps = [os.path.join(d, "kernel_lockstep.cpp"), os.path.join(d, "fakecuda", "cuda_runtime.h")] + \
+                   [os.path.join(csrc, f) for f in ("trace_kernels.cuh", "traverse.h", "layout.h")]
+            if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-msse", "-msse2", "-mfma", "-ffp-contract=off",
+                                       "-D__CUDACC__", "-I" + os.path.join(d, "fakecuda"), "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
+                                       "-o", so, deps[0]])
+            L = C.CDLL(so)
+            L.ks_trace.restype = C.c_int
+            L.ks_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def trace(cls, emu, rays, kernel="persistent", n_warps=1, smem_depth=16, refill_below=24, tri_bias=8, inst_bias=8,
+              prefetch=False, hits=None, want_stats=False):
+        """-> hits (and TraceStatic's counters with want_stats).  `hits` pre-loads the RayHit buffer (masked rays)."""
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.shape[0], dtype=HIT_DTYPE) if hits is None else np.ascontiguousarray(hits).copy()
+        E = Emu.lib()
+        view = (C.c_uint8 * int(E.emu_scene_view_size()))()
+        E.emu_scene_view(emu.h, view)
+        st = np.zeros(6, dtype=np.uint64)
+        rc = cls.lib().ks_trace(view, rays.ctypes.data, out.ctypes.data, rays.shape[0], 0 if kernel == "persistent" else 1, n_warps,
+                                smem_depth, emu.info()["stack_need"], refill_below, tri_bias, inst_bias, 1 if prefetch else 0, st.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("ks_trace failed: %d" % rc)
+        if want_stats:
+            return out, dict(zip(["rays", "wide_nodes", "triangles", "instances", "motion_samples", "max_stack"], [int(x) for x in st]))
+        return out
 
 
 WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_phases", "node_lanes", "tri_lanes", "pop_trips",
