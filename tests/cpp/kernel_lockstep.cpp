@@ -6,6 +6,7 @@
 // written in the kernel, the shared-memory stack with its global spill (SmemStack), TraceStatic's
 // local stack.  The arithmetic is the host variant of traverse.h (same as the emulation), so results
 // must equal the emulation's bit for bit.
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -68,6 +69,7 @@ uint32_t __reduce_min_sync(unsigned mask, uint32_t v) {
 		for (int i = 0; i < 32; ++i) r[i] = m;
 	});
 }
+void __nanosleep(unsigned ns) { std::this_thread::sleep_for(std::chrono::nanoseconds(ns < 200000u ? 200000u : ns)); }
 void __syncwarp() {
 	t_warp->rendezvous(t_lane, 0u, [](const uint32_t *, uint32_t *) { });
 }
@@ -102,6 +104,9 @@ extern "C" {
 // Runs one block (nWarps <= 4 warps) of TracePersistent / TraceStatic over the batch.
 //   view: SceneView of a re-laid-out scene (emu_scene_view of libwide_emulation.so)
 //   kernel: 0 = TracePersistent, 1 = TraceStatic (stats6 receives its counters when non-null)
+int ks_trace_signal(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, lrb_rayhit *hitsPeer, uint32_t n, int nWarps,
+		uint32_t smemDepth, uint32_t stackNeed, uint32_t chunkShift, uint32_t epoch, uint32_t *chunkFlags, uint32_t *flagOrderOk);
+
 int ks_trace(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, int kernel, int nWarps,
 		uint32_t smemDepth, uint32_t stackNeed, uint32_t refillBelow, uint32_t triBias, uint32_t instBias, int prefetch,
 		unsigned long long *stats6) {
@@ -151,6 +156,81 @@ int ks_trace(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, uint3
 			stats6[3] = st.instances; stats6[4] = st.motionSamples; stats6[5] = st.maxStack;
 		}
 	}
+	return 0;
+}
+
+// SIGNAL kernels (the multi-GPU gather's trace): warp 0 is the detector, the other warps trace and publish
+// watermarks; `hitsPeer` stands for the peer-mapped gather slice (dual stores).  A watcher thread plays the
+// copy stream: whenever a chunk flag shows `epoch`, every RayHit of that chunk must already be final --
+// it snapshots the chunk at that moment; the caller compares the snapshots with the final buffer.
+int ks_trace_signal(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, lrb_rayhit *hitsPeer, uint32_t n, int nWarps,
+		uint32_t smemDepth, uint32_t stackNeed, uint32_t chunkShift, uint32_t epoch, uint32_t *chunkFlags, uint32_t *flagOrderOk) {
+	if (nWarps != 4 || smemDepth < 1 || smemDepth > 64)
+		return 1;       // the detector waits for a watermark from every warp of the block: all four must run
+	gridDim.x = 1; gridDim.y = gridDim.z = 1;
+	blockDim.x = kTraceBlock; blockDim.y = blockDim.z = 1;
+	TraceArgs a;
+	memset(&a, 0, sizeof(a));
+	a.sc = *view;
+	a.rays = rays;
+	a.hits = hits;
+	a.hitsPeer = hitsPeer;
+	a.rayCount = n;
+	uint32_t counter[2] = { 0, 0 };
+	a.counter = counter;
+	const uint32_t spillDepth = stackNeed + 4;
+	std::vector<uint32_t> spillNode((size_t)spillDepth * kTraceBlock);
+	std::vector<float> spillT((size_t)spillDepth * kTraceBlock);
+	a.spillNode = spillNode.data();
+	a.spillT = spillT.data();
+	a.smemDepth = smemDepth;
+	a.refillBelow = 24;
+	a.triBias = 8;
+	a.instBias = 8;
+	std::vector<uint32_t> watermark(kTraceBlock / 32, 0u);
+	a.watermark = watermark.data();
+	a.chunkFlag = chunkFlags;
+	a.chunkShift = chunkShift;
+	a.epoch = epoch;
+	const uint32_t chunkRays = 1u << chunkShift, nChunks = (n + chunkRays - 1) >> chunkShift;
+	// the copy stream's stand-in
+	std::vector<lrb_rayhit> snap(n);
+	std::vector<char> taken(nChunks, 0);
+	volatile bool stop = false;
+	std::thread watcher([&]() {
+		uint32_t left = nChunks;
+		while (left && !stop) {
+			for (uint32_t c = 0; c < nChunks; ++c) {
+				if (taken[c]) continue;
+				if (__atomic_load_n(chunkFlags + c, __ATOMIC_ACQUIRE) == epoch) {
+					const uint32_t b = c << chunkShift, e = std::min(n, b + chunkRays);
+					memcpy(&snap[b], (const void *)(hits + b), (size_t)(e - b) * sizeof(lrb_rayhit));
+					taken[c] = 1;
+					--left;
+				}
+			}
+			std::this_thread::sleep_for(std::chrono::microseconds(200));
+		}
+	});
+	const bool two = view->twoLevel != 0;
+	const bool spill = stackNeed > smemDepth;
+	if (two) {
+		if (spill) RunBlock(TracePersistent<true, true, true>, a, nWarps);
+		else RunBlock(TracePersistent<true, false, true>, a, nWarps);
+	} else if (spill) RunBlock(TracePersistent<false, true, true>, a, nWarps);
+	else RunBlock(TracePersistent<false, false, true>, a, nWarps);
+	stop = true;
+	watcher.join();
+	// flags raised while the kernel ran: their snapshots must equal the final records
+	uint32_t ok = 1, raised = 0;
+	for (uint32_t c = 0; c < nChunks; ++c) {
+		if (!taken[c]) continue;
+		++raised;
+		const uint32_t b = c << chunkShift, e = std::min(n, b + chunkRays);
+		if (memcmp(&snap[b], hits + b, (size_t)(e - b) * sizeof(lrb_rayhit)) != 0) ok = 0;
+	}
+	flagOrderOk[0] = ok;
+	flagOrderOk[1] = raised;
 	return 0;
 }
 

@@ -297,8 +297,30 @@ class Lockstep:
             L.ks_trace.restype = C.c_int
             L.ks_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+            L.ks_trace_signal.restype = C.c_int
+            L.ks_trace_signal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
             cls._lib = L
         return cls._lib
+
+    @classmethod
+    def trace_signal(cls, emu, rays, n_warps=4, smem_depth=16, chunk_shift=7, epoch=5, hits=None):
+        """The SIGNAL kernel (trace of the multi-GPU gather): -> (hits, peer copy, chunk flags, flags raised while the
+        kernel ran, snapshots-at-flag == final records)."""
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.shape[0], dtype=HIT_DTYPE) if hits is None else np.ascontiguousarray(hits).copy()
+        peer = out.copy()
+        E = Emu.lib()
+        view = (C.c_uint8 * int(E.emu_scene_view_size()))()
+        E.emu_scene_view(emu.h, view)
+        n_chunks = (rays.shape[0] + (1 << chunk_shift) - 1) >> chunk_shift
+        flags = np.zeros(max(1, n_chunks), dtype=np.uint32)
+        res = np.zeros(2, dtype=np.uint32)
+        rc = cls.lib().ks_trace_signal(view, rays.ctypes.data, out.ctypes.data, peer.ctypes.data, rays.shape[0], n_warps, smem_depth,
+                                       emu.info()["stack_need"], chunk_shift, epoch, flags.ctypes.data, res.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("ks_trace_signal failed: %d" % rc)
+        return out, peer, flags[:n_chunks], int(res[1]), bool(res[0])
 
     @classmethod
     def trace(cls, emu, rays, kernel="persistent", n_warps=1, smem_depth=16, refill_below=24, tri_bias=8, inst_bias=8,

@@ -105,3 +105,20 @@ def test_empty_scene_and_tiny_batches():
     empty = H.Emu.bvh(np.zeros(0, dtype=bvh.nodes().dtype), np.zeros((0, 3), np.float32), np.zeros(1, np.uint32))
     got = H.Lockstep.trace(empty, rays)
     assert (got["meshIndex"] == H.NULL).all() and (got["t"] == rays["maxt"]).all()
+
+
+@pytest.mark.parametrize("n_warps,chunk_shift", [(4, 5), (4, 7), (4, 10)])
+def test_signalled_gather_kernel_in_lockstep(kitchen, n_warps, chunk_shift):
+    """TracePersistent<*, *, SIGNAL>: warp 0 watches the other warps' watermarks and raises a chunk's flag when
+    every ray index below the chunk's end is finished; the copy stream (here: a watcher thread) may then read
+    the chunk.  Hits (local and peer copy) must equal the plain kernel's, every flag raised during the run must
+    have been raised only after all of its chunk's records were final, and flags must not be raised early."""
+    emu, rays = kitchen
+    pre = _preloaded(rays.shape[0], 6)
+    want = _expect(emu, rays, pre)
+    got, peer, flags, raised, order_ok = H.Lockstep.trace_signal(emu, rays, n_warps=n_warps, chunk_shift=chunk_shift, epoch=9, hits=pre)
+    assert got.tobytes() == want.tobytes()
+    assert peer.tobytes() == want.tobytes()         # dual stores + forwarded masked records
+    assert order_ok
+    assert set(np.unique(flags).tolist()) <= {0, 9}
+    assert raised == int((flags == 9).sum()) == len(flags)     # the detector itself raised every chunk (on the GPU the host's memset is only the safety net)
