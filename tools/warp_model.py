@@ -46,8 +46,59 @@ def model(c):
     return instr, lanes
 
 
+ENTER_INSTANCE = 110    # EnterInstance: record + matrix fetch, ray transform, three IEEE reciprocals, sentinel push
+
+MBVH_SCENES = ("lightinstances", "bigmonkey-instances", "bigmonkey-motion")
+
+
+def main_two_level(scene, n, refill, bias):
+    """Two-level scenes: host-layer SAH trees (root + leaves) inside the oracle's array set, camera and
+    first-bounce rays, instance entry as a voted phase (inst_bias sweep)."""
+    import torch
+    from luxcore_b200 import rays as R, scenes as S
+    from oracle import oracle as O
+    desc = S.load_fixture(scene)
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=4)
+    arr = H.mbvh_arrays(desc, mb)
+    s = hostapi.Session({"accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": 4}, desc)
+    s.build_accelerator("MBVH")
+    arr["root_nodes"] = s.mbvh_root_nodes().copy()
+    for i in range(s.mbvh_leaf_count()):
+        arr["leaf_nodes"][i] = s.mbvh_leaf_nodes(i).copy()
+    emu = H.Emu.mbvh(arr)
+    th = O.hardware_threads()
+    time_range = (0.0, 1.0) if "motion" in scene else None
+
+    def trace_fn(rays_u8):
+        h = mb.intersect(R.to_numpy_rays(rays_u8), nthreads=th)
+        return torch.from_numpy(h.view(np.uint8).reshape(-1, 20).copy())
+    for kind, depth in (("camera", 0), ("bounce-1", 1)):
+        if time_range is not None:
+            if depth:
+                continue
+            side = int(n ** 0.5)
+            rays = R.to_numpy_rays(R.camera_rays(desc.cam, side, side, seed=1, time_range=time_range))
+        else:
+            rays = R.to_numpy_rays(B.make_bounce_batch(trace_fn, desc, n, seed=2, device="cpu", depth=depth))
+        ref, st = emu.trace(rays, want_stats=True)
+        r = st["rays"]
+        print("scene %s %s: per ray nodes %.2f tris %.2f instance entries %.2f motion samples %.2f" % (
+            scene, kind, st["wide_nodes"] / r, st["triangles"] / r, st["instances"] / r, st["motion_samples"] / r))
+        for ib in (0, 4, 8, 16):
+            hits, c = H.warp_sim(emu, rays, n_warps=128, refill_below=refill, tri_bias=bias, inst_bias=ib)
+            assert hits.tobytes() == ref.tobytes(), "scheduling model and per-ray emulation disagree"
+            instr, _ = model(c)
+            enter = ENTER_INSTANCE * c["instance_trips"] / r
+            print("  inst_bias %2d: MODEL warp instructions / ray %.1f (+ %.1f entering instances = %.1f) | entry executions %.3f per ray at %.1f lanes" % (
+                ib, instr / r, enter, instr / r + enter, c["instance_trips"] / r, c["instance_lanes"] / max(1, c["instance_trips"])))
+
+
 def main():
     scene = sys.argv[1] if len(sys.argv) > 1 else "kitchen"
+    if scene in MBVH_SCENES:
+        return main_two_level(scene, int(sys.argv[2]) if len(sys.argv) > 2 else 100000,
+                              int(sys.argv[4]) if len(sys.argv) > 4 else 24, int(sys.argv[5]) if len(sys.argv) > 5 else 8)
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
     depth = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     refill = int(sys.argv[4]) if len(sys.argv) > 4 else 24
