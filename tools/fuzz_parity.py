@@ -1,0 +1,157 @@
+"""Randomised differential test of the product's re-layout + traversal body (CPU emulation of the same
+traverse.h / relayout.cpp the kernels use) against the oracle, on scenes and rays the fixed tests do not
+enumerate: random scales (1e-3 ... 1e4) and offsets (up to 1e5) of the geometry, slivers, degenerate and
+duplicated triangles, coplanar sheets, every builder and arity, one- and two-level scenes with random
+(rotating, mirroring, non-uniformly scaling) instances, and ray batches that mix uniform rays, rays starting
+on / within 2 eps of surfaces, axis-parallel directions, finite and tiny maxt, zero and negative mint.
+
+    python tools/fuzz_parity.py [seconds] [seed]
+
+Prints one line per scene; any disagreement that is not a t-tie within the stated epsilon raises.
+CPU only (test infrastructure: imports oracle/)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+
+import helpers as H
+import scene_zoo as Z
+from luxcore_b200 import hostapi, rays as R, scenes as S
+from oracle import oracle as O
+
+
+def random_mesh(rng, n_tris, scale, offset):
+    kind = rng.integers(0, 5)
+    if kind == 0:       # soup of small triangles
+        c = rng.uniform(-1, 1, (n_tris, 1, 3))
+        v = c + rng.uniform(-0.15, 0.15, (n_tris, 3, 3))
+    elif kind == 1:     # slivers: long and thin
+        c = rng.uniform(-1, 1, (n_tris, 1, 3))
+        d = rng.normal(size=(n_tris, 1, 3))
+        v = c + d * rng.uniform(-1, 1, (n_tris, 3, 1)) + rng.normal(scale=1e-4, size=(n_tris, 3, 3))
+    elif kind == 2:     # coplanar sheets (axis-aligned planes: zero-thickness boxes)
+        c = rng.uniform(-1, 1, (n_tris, 1, 3))
+        v = c + rng.uniform(-0.2, 0.2, (n_tris, 3, 3))
+        ax = rng.integers(0, 3)
+        v[:, :, ax] = np.round(v[:, :1, ax] * 4) / 4
+    elif kind == 3:     # a grid surface plus duplicates of some triangles
+        gv, gt = S.grid_mesh(max(2, int(np.sqrt(n_tris / 2))), max(2, int(np.sqrt(n_tris / 2))), z=0.1, size=1.0)
+        v = gv[gt].astype(np.float64)
+        v = np.concatenate([v, v[rng.integers(0, v.shape[0], max(1, v.shape[0] // 10))]])
+    else:               # mixed sizes over five decades, some degenerate (two equal vertices / a point)
+        c = rng.uniform(-1, 1, (n_tris, 1, 3))
+        v = c + rng.normal(size=(n_tris, 3, 3)) * (10.0 ** rng.uniform(-5, -0.5, (n_tris, 1, 1)))
+        deg = rng.random(n_tris) < 0.05
+        v[deg, 1] = v[deg, 0]
+        pt = rng.random(n_tris) < 0.02
+        v[pt, 1] = v[pt, 0]
+        v[pt, 2] = v[pt, 0]
+    v = (v * scale + offset).astype(np.float32).reshape(-1, 3)
+    return v, np.arange(v.shape[0], dtype=np.uint32).reshape(-1, 3)
+
+
+def random_rays(rng, desc, n, seed):
+    lo, hi = desc.bbox()
+    ext = np.maximum(hi - lo, 1e-6)
+    a = R.to_numpy_rays(R.uniform_rays(lo - 0.3 * ext, hi + 0.3 * ext, n, seed=seed))
+    p0, e1, e2, _ = S.world_triangles(desc)
+    b = R.to_numpy_rays(R.surface_rays(p0, e1, e2, n, seed=seed + 1, axis_fraction=0.3))
+    rays = np.concatenate([a, b])
+    m = rays.shape[0]
+    r = rng.random(m)
+    diag = float(np.linalg.norm(ext))
+    rays["maxt"] = np.where(r < 0.15, rng.uniform(0, diag, m), rays["maxt"]).astype(np.float32)
+    rays["maxt"] = np.where((r >= 0.15) & (r < 0.2), rays["mint"] * 4, rays["maxt"]).astype(np.float32)
+    r2 = rng.random(m)
+    rays["mint"] = np.where(r2 < 0.1, 0.0, rays["mint"]).astype(np.float32)
+    rays["mint"] = np.where((r2 >= 0.1) & (r2 < 0.15), -rng.uniform(0, diag, m), rays["mint"]).astype(np.float32)
+    # unnormalised directions (the reference does not require unit length, ray.h)
+    s = np.where(rng.random(m) < 0.2, 10.0 ** rng.uniform(-3, 3, m), 1.0).astype(np.float32)
+    rays["d"] = (rays["d"] * s[:, None]).astype(np.float32)
+    if "time" in rays.dtype.names:
+        rays["time"] = rng.uniform(-0.1, 1.1, m).astype(np.float32)
+    return rays
+
+
+def one_level(rng, it):
+    scale = 10.0 ** rng.uniform(-3, 4)
+    offset = rng.uniform(-1, 1, 3) * (10.0 ** rng.uniform(-2, 5)) * (rng.random() < 0.6)
+    desc = S.SceneDesc("fuzz%d" % it)
+    for _ in range(int(rng.integers(1, 4))):
+        desc.add_plain(desc.add_shape(*random_mesh(rng, int(rng.integers(1, 900)), scale, offset)))
+    builder = ["CLASSIC", "EMBREE_BINNED_SAH"][int(rng.integers(0, 2))]
+    tree_type = [2, 4, 8][int(rng.integers(0, 3))]
+    s = hostapi.Session({"accelerator.bvh.builder.type": builder, "accelerator.bvh.treetype": tree_type}, desc)
+    s.build_accelerator("BVH")
+    nodes = s.bvh_nodes().copy()
+    osc = H.oracle_scene(desc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(nodes, verts, offs)
+    rays = random_rays(rng, desc, 3000, int(rng.integers(1, 1 << 30)))
+    ref = O.BVH(osc, nodes=nodes).intersect(rays)
+    rep = H.compare_hits_tie_aware(emu.trace(rays), ref, rays, osc, what="fuzz %d %s k=%d" % (it, builder, tree_type), max_ties=40)
+    return "BVH  %-18s k=%d scale %8.2e |offset| %8.2e tris %5d: hits %5d bit-exact %5d ties %d" % (
+        builder, tree_type, scale, float(np.abs(offset).max()), desc.triangle_count(), rep["hits"], rep["bit_exact_hits"], rep["tie_exempt"])
+
+
+def two_level(rng, it):
+    scale = 10.0 ** rng.uniform(-2, 3)
+    desc = S.SceneDesc("fuzz2l%d" % it)
+    shapes = [desc.add_shape(*random_mesh(rng, int(rng.integers(1, 300)), 1.0, np.zeros(3))) for _ in range(int(rng.integers(1, 4)))]
+    if rng.random() < 0.5:
+        desc.add_plain(shapes[0])
+    for _ in range(int(rng.integers(1, 25))):
+        m = Z.translate(*(rng.uniform(-4, 4, 3) * scale)) @ Z.rot_z(rng.uniform(0, 360)) @ Z.rot_x(rng.uniform(0, 360)) @ \
+            Z.scale(*(rng.uniform(0.3, 2.0, 3) * scale))
+        if rng.random() < 0.2:
+            m = m @ Z.scale(-1, 1, 1)
+        desc.add_instance(shapes[int(rng.integers(0, len(shapes)))], m)
+    motion = rng.random() < 0.5
+    if motion:
+        for _ in range(int(rng.integers(1, 5))):
+            m0 = Z.translate(*(rng.uniform(-4, 4, 3) * scale)) @ Z.rot_z(rng.uniform(0, 360)) @ Z.scale(scale, scale, scale)
+            m1 = m0 @ Z.translate(*rng.uniform(-0.5, 0.5, 3)) @ Z.rot_x(rng.uniform(-170, 170))
+            desc.add_motion(shapes[int(rng.integers(0, len(shapes)))], [0.0, 1.0], [Z.inv(m0), Z.inv(m1)])
+    desc.cam = np.asarray([0, -12 * scale, 3 * scale, 0, 0, 0, 0, 0, 1, 50], dtype=np.float32)
+    tree_type = [2, 4, 8][int(rng.integers(0, 3))]
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=tree_type)
+    arr = H.mbvh_arrays(desc, mb)
+    if rng.random() < 0.5:      # the host layer's SAH trees instead of the oracle's CLASSIC ones
+        s = hostapi.Session({"accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": tree_type}, desc)
+        s.build_accelerator("MBVH")
+        arr["root_nodes"] = s.mbvh_root_nodes().copy()
+        for i in range(s.mbvh_leaf_count()):
+            arr["leaf_nodes"][i] = s.mbvh_leaf_nodes(i).copy()
+        # the oracle walks the SAME arrays: exact ties (duplicated triangles) go to the first leaf in array order
+        mb.set_root_nodes(arr["root_nodes"])
+        for i in range(s.mbvh_leaf_count()):
+            mb.set_leaf_nodes(i, arr["leaf_nodes"][i])
+    emu = H.Emu.mbvh(arr)
+    rays = random_rays(rng, desc, 2500, int(rng.integers(1, 1 << 30)))      # incl. rays starting on the instanced surfaces
+    ref = mb.intersect(rays)
+    kw = dict(libm_outlier_frac=0.0)
+    rep = H.compare_hits_tie_aware(emu.trace(rays), ref, rays, osc, what="fuzz2l %d k=%d" % (it, tree_type), two_level=True, max_ties=40, **kw)
+    return "MBVH k=%d scale %8.2e objects %3d motion %d: hits %5d bit-exact %5d ties %d" % (
+        tree_type, scale, len(desc.meshes), int(motion), rep["hits"], rep["bit_exact_hits"], rep["tie_exempt"])
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    it = 0
+    while time.time() - t0 < seconds:
+        line = (one_level if it % 3 else two_level)(rng, it)
+        print("%4d %s" % (it, line), flush=True)
+        it += 1
+    print("fuzz: %d scenes, no disagreement" % it)
+
+
+if __name__ == "__main__":
+    main()
