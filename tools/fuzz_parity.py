@@ -5,7 +5,10 @@ duplicated triangles, coplanar sheets, every builder and arity, one- and two-lev
 (rotating, mirroring, non-uniformly scaling) instances, and ray batches that mix uniform rays, rays starting
 on / within 2 eps of surfaces, axis-parallel directions, finite and tiny maxt, zero and negative mint.
 
-    python tools/fuzz_parity.py [seconds] [seed]
+    python tools/fuzz_parity.py [seconds] [seed] [--lockstep]
+
+--lockstep also runs the REAL kernel source (trace_kernels.cuh compiled for the host, one OS thread per lane)
+on a slice of every batch with random warp counts, stack depths and vote settings.
 
 Prints one line per scene; any disagreement that is not a t-tie within the stated epsilon raises.
 CPU only (test infrastructure: imports oracle/)."""
@@ -77,6 +80,24 @@ def random_rays(rng, desc, n, seed):
     return rays
 
 
+LOCKSTEP = False        # --lockstep: also run the REAL kernel source (tests/cpp/kernel_lockstep.cpp) on a slice of every batch
+
+
+def lockstep_check(rng, emu, rays, got, what):
+    if not LOCKSTEP:
+        return
+    pick = np.sort(rng.choice(rays.shape[0], size=min(500, rays.shape[0]), replace=False))
+    sub = np.ascontiguousarray(rays[pick])
+    kw = dict(n_warps=int(rng.integers(1, 5)), smem_depth=int(rng.choice([2, 4, 16, 64])), refill_below=int(rng.choice([1, 16, 24, 32])),
+              tri_bias=int(rng.choice([1, 8, 64])), inst_bias=int(rng.choice([0, 8, 64])))
+    if rng.random() < 0.25:
+        kw = dict(kernel="static", n_warps=4)
+    ks = H.Lockstep.trace(emu, sub, **kw)
+    if ks.tobytes() != got[pick].tobytes():
+        bad = np.nonzero(ks != got[pick])[0]
+        raise AssertionError("%s: kernel source in lockstep %r differs from the emulation at rays %r" % (what, kw, pick[bad[:5]]))
+
+
 def one_level(rng, it):
     scale = 10.0 ** rng.uniform(-3, 4)
     offset = rng.uniform(-1, 1, 3) * (10.0 ** rng.uniform(-2, 5)) * (rng.random() < 0.6)
@@ -93,7 +114,9 @@ def one_level(rng, it):
     emu = H.Emu.bvh(nodes, verts, offs)
     rays = random_rays(rng, desc, 3000, int(rng.integers(1, 1 << 30)))
     ref = O.BVH(osc, nodes=nodes).intersect(rays)
-    rep = H.compare_hits_tie_aware(emu.trace(rays), ref, rays, osc, what="fuzz %d %s k=%d" % (it, builder, tree_type), max_ties=40)
+    got = emu.trace(rays)
+    lockstep_check(rng, emu, rays, got, "fuzz %d" % it)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="fuzz %d %s k=%d" % (it, builder, tree_type), max_ties=40)
     return "BVH  %-18s k=%d scale %8.2e |offset| %8.2e tris %5d: hits %5d bit-exact %5d ties %d" % (
         builder, tree_type, scale, float(np.abs(offset).max()), desc.triangle_count(), rep["hits"], rep["bit_exact_hits"], rep["tie_exempt"])
 
@@ -135,12 +158,18 @@ def two_level(rng, it):
     rays = random_rays(rng, desc, 2500, int(rng.integers(1, 1 << 30)))      # incl. rays starting on the instanced surfaces
     ref = mb.intersect(rays)
     kw = dict(libm_outlier_frac=0.0)
-    rep = H.compare_hits_tie_aware(emu.trace(rays), ref, rays, osc, what="fuzz2l %d k=%d" % (it, tree_type), two_level=True, max_ties=40, **kw)
+    got = emu.trace(rays)
+    lockstep_check(rng, emu, rays, got, "fuzz2l %d" % it)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="fuzz2l %d k=%d" % (it, tree_type), two_level=True, max_ties=40, **kw)
     return "MBVH k=%d scale %8.2e objects %3d motion %d: hits %5d bit-exact %5d ties %d" % (
         tree_type, scale, len(desc.meshes), int(motion), rep["hits"], rep["bit_exact_hits"], rep["tie_exempt"])
 
 
 def main():
+    global LOCKSTEP
+    if "--lockstep" in sys.argv:
+        LOCKSTEP = True
+        sys.argv.remove("--lockstep")
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
