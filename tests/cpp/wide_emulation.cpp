@@ -94,7 +94,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	std::vector<SimWarp> warps(nWarps);
 	uint32_t counter = 0;
 	unsigned long long outer = 0, inner = 0, nodePhases = 0, triPhases = 0, nodeLanes = 0, triLanes = 0,
-			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0, slowPhases = 0, slowLanes = 0, instTrips = 0, instLanes = 0;
+			popTrips = 0, popLanes = 0, gatePhases = 0, gateLanes = 0, storePhases = 0, refills = 0, traced = 0, idlePhaseLanes = 0, slowPhases = 0, slowLanes = 0, instTrips = 0, instLanes = 0, leaveTrips = 0, leaveLanes = 0;
 	const size_t smemDepth = 16;
 	uint32_t live = nWarps;
 	std::vector<char> done(nWarps, 0);
@@ -145,12 +145,15 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 			do {
 				++inner;
 				unsigned long long maxTrips = 0, maxInst = 0;
+				bool anyLeave = false;
 				for (int l = 0; l < 32; ++l) {
 					SimLane &L = W.lane[l];
 					if (L.state == 1 && NeedsResolve<TWO>(L.s.cur)) {
 						const size_t before = L.stk.n.size();
+						const bool wasInside = L.s.inInstance;
 						if (!Resolve<TWO, false>(v, rays[L.rayIdx], L.s, L.stk, nullptr))
 							L.state = 2;
+						if (TWO && wasInside && !L.s.inInstance) { ++leaveLanes; anyLeave = true; }
 						// pops performed (an entry into an instance pushes the sentinel: count at least one trip)
 						const size_t after = L.stk.n.size();
 						unsigned long long trips = before > after ? (unsigned long long)(before - after) : 1ull;
@@ -160,6 +163,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					}
 				}
 				popTrips += maxTrips;
+				if (anyLeave) ++leaveTrips;
 				// ---- from here on: the same statements as TracePersistent's loop body (trace_kernels.cuh), with
 				// ballots replaced by loops over the lanes; the votes are the kernels' own functions (traverse.h)
 				LaneWork work[32];
@@ -226,7 +230,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 	}
 	out16[0] = traced; out16[1] = outer; out16[2] = inner; out16[3] = nodePhases; out16[4] = triPhases;
 	out16[5] = nodeLanes; out16[6] = triLanes; out16[7] = popTrips; out16[8] = popLanes; out16[9] = gatePhases;
-	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes; out16[16] = instTrips; out16[17] = instLanes;
+	out16[10] = gateLanes; out16[11] = storePhases; out16[12] = refills; out16[13] = idlePhaseLanes; out16[14] = slowPhases; out16[15] = slowLanes; out16[16] = instTrips; out16[17] = instLanes; out16[18] = leaveTrips; out16[19] = leaveLanes;
 }
 
 }   // namespace

@@ -342,7 +342,7 @@ class Lockstep:
 
 
 WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_phases", "node_lanes", "tri_lanes", "pop_trips",
-                   "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes", "slow_push_phases", "slow_push_lanes", "instance_trips", "instance_lanes"]
+                   "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes", "slow_push_phases", "slow_push_lanes", "instance_trips", "instance_lanes", "leave_trips", "leave_lanes"]
 
 
 def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8):
@@ -350,7 +350,7 @@ def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8):
     tri_bias = (tri_bias & 0xFFFF) | (inst_bias << 16)
     rays = np.ascontiguousarray(rays)
     hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
-    out = np.zeros(18, dtype=np.uint64)
+    out = np.zeros(20, dtype=np.uint64)
     emu.lib().emu_warp_sim(emu.h, rays.ctypes.data, hits.ctypes.data, rays.shape[0], n_warps, refill_below, tri_bias, out.ctypes.data)
     return hits, dict(zip(WARP_SIM_FIELDS, [int(x) for x in out]))
 

@@ -90,8 +90,10 @@ def main_two_level(scene, n, refill, bias):
             assert hits.tobytes() == ref.tobytes(), "scheduling model and per-ray emulation disagree"
             instr, _ = model(c)
             enter = ENTER_INSTANCE * c["instance_trips"] / r
-            print("  inst_bias %2d: MODEL warp instructions / ray %.1f (+ %.1f entering instances = %.1f) | entry executions %.3f per ray at %.1f lanes" % (
-                ib, instr / r, enter, instr / r + enter, c["instance_trips"] / r, c["instance_lanes"] / max(1, c["instance_trips"])))
+            print("  inst_bias %2d: MODEL warp instructions / ray %.1f (+ %.1f entering instances = %.1f) | entry executions %.3f per ray at %.1f lanes"
+                  " | iterations in which a lane leaves an instance %.3f per ray (%.1f lanes)" % (
+                      ib, instr / r, enter, instr / r + enter, c["instance_trips"] / r, c["instance_lanes"] / max(1, c["instance_trips"]),
+                      c["leave_trips"] / r, c["leave_lanes"] / max(1, c["leave_trips"])))
 
 
 def main():
