@@ -15,6 +15,11 @@ from luxcore_b200 import rays as R, scenes as S
 from oracle import oracle as O
 
 
+# A kernel loop that fails to terminate would block its 32 lane threads for ever: give up after 15 minutes
+# (the whole file takes about one).  method="thread": the main thread sits inside the C call, a signal cannot fire.
+pytestmark = pytest.mark.timeout(900, method="thread")
+
+
 def _preloaded(n, seed):
     """A RayHit buffer with recognisable garbage: masked rays must leave it untouched."""
     rng = np.random.default_rng(seed)
