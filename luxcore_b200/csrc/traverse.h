@@ -333,7 +333,11 @@ LRB_HD void TransformRayLocal(RayState &s, const float *m, float ox, float oy, f
 // Initialise the state from a wire ray.  Returns false when there is nothing to traverse.
 LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	SetRay(s, ray.o[0], ray.o[1], ray.o[2], ray.d[0], ray.d[1], ray.d[2]);
-	s.mint = ray.mint;
+	// A NaN mint never rejects anything in the reference (`t < mint` and BBox::IntersectP's `tNear > t0` are
+	// both false): for the triangle test that is mint = -inf.  Kept as NaN it would poison the entry distance
+	// of a slot whose three slabs are NaN as well (the whole-grid slot of a lone instance), and a NaN key reads
+	// as "missed" (found by tools/fuzz_parity.py).
+	s.mint = (ray.mint != ray.mint) ? -LRB_INF : ray.mint;
 	s.maxt = ray.maxt;      // rayHit->t = ray->maxt
 	s.time = ray.time;
 	s.b1 = 0.f; s.b2 = 0.f;

@@ -208,3 +208,24 @@ def test_motion_bounds_cover_large_rotations():
     assert rep["bit_exact_hits"] == rep["hits"]
     # and the bounds do cull: far fewer instance entries than "every motion instance of every visited root node"
     assert st["instances"] / st["rays"] < 2.0
+
+
+def test_nan_mint_with_a_lone_instance():
+    """Regression (tools/fuzz_parity.py): a dataset of ONE instance has a root tree that is a single leaf; its
+    slot covers the whole grid, i.e. all three slabs decode to NaN.  With ray.mint = NaN as well the entry
+    distance was NaN and read as "missed", while the reference (NaN mint never rejects) enters the instance."""
+    desc = S.SceneDesc("lone")
+    desc.add_instance(desc.add_shape(*Z.blob(12, 4)), Z.translate(30, -20, 50) @ Z.rot_z(25) @ Z.scale(20, 20, 20))
+    desc.cam = np.asarray([30, -120, 50, 30, -20, 50, 0, 0, 1, 40], dtype=np.float32)
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=4)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = np.concatenate([R.to_numpy_rays(R.surface_rays(p0, e1, e2, 4000, seed=3)), R.to_numpy_rays(R.camera_rays(desc.cam, 50, 50, seed=2))])
+    for mint in (np.nan, 0.0, -np.inf, -3.0):
+        r = rays.copy()
+        r["mint"] = mint
+        rep = H.compare_hits_tie_aware(emu.trace(r), mb.intersect(r), r, osc, what="lone instance, mint %r" % mint, two_level=True)
+        assert rep["hits"] > 2000 and rep["bit_exact_hits"] == rep["hits"]
+        got = H.Lockstep.trace(emu, r[:600])
+        assert got.tobytes() == emu.trace(r[:600]).tobytes()
