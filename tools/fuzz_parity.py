@@ -5,10 +5,11 @@ duplicated triangles, coplanar sheets, every builder and arity, one- and two-lev
 (rotating, mirroring, non-uniformly scaling) instances, and ray batches that mix uniform rays, rays starting
 on / within 2 eps of surfaces, axis-parallel directions, finite and tiny maxt, zero and negative mint.
 
-    python tools/fuzz_parity.py [seconds] [seed] [--lockstep]
+    python tools/fuzz_parity.py [seconds] [seed] [--lockstep] [--reference]
 
 --lockstep also runs the REAL kernel source (trace_kernels.cuh compiled for the host, one OS thread per lane)
-on a slice of every batch with random warp counts, stack depths and vote settings.
+on a slice of every batch with random warp counts, stack depths and vote settings; --reference pins the oracle
+against the reference's own code (oracle/_ref) on every one-level scene, bit for bit.
 
 Prints one line per scene; any disagreement that is not a t-tie within the stated epsilon raises.
 CPU only (test infrastructure: imports oracle/)."""
@@ -89,6 +90,7 @@ def random_rays(rng, desc, n, seed):
     return rays
 
 
+REFERENCE = False       # --reference: also pin the oracle against the reference library on every one-level scene
 LOCKSTEP = False        # --lockstep: also run the REAL kernel source (tests/cpp/kernel_lockstep.cpp) on a slice of every batch
 
 
@@ -132,6 +134,18 @@ def one_level(rng, it):
     emu = H.Emu.bvh(nodes, verts, offs)
     rays = random_rays(rng, desc, 3000, int(rng.integers(1, 1 << 30)))
     ref = O.BVH(osc, nodes=nodes).intersect(rays)
+    if REFERENCE:
+        # the reference's own BVHAccel::Intersect (oracle/_ref, compiled from /root/reference) on the same array:
+        # the oracle must reproduce it bit for bit, non-finite rays included
+        from oracle import refapi as RF
+        theirs = RF.BVH(H.reference_scene(desc), nodes=nodes).intersect(rays)
+        same = (theirs["meshIndex"] == ref["meshIndex"]) & ((theirs["triangleIndex"] == ref["triangleIndex"]) | (ref["meshIndex"] == H.NULL))
+        hit = same & (ref["meshIndex"] != H.NULL)
+        same &= (theirs["t"].view(np.uint32) == ref["t"].view(np.uint32)) | ~hit
+        same[hit] &= (theirs["b1"][hit].view(np.uint32) == ref["b1"][hit].view(np.uint32)) & (theirs["b2"][hit].view(np.uint32) == ref["b2"][hit].view(np.uint32))
+        if not same.all():
+            i = int(np.nonzero(~same)[0][0])
+            raise AssertionError("fuzz %d: oracle %r != reference %r for ray %r" % (it, ref[i], theirs[i], rays[i]))
     got = emu.trace(rays)
     lockstep_check(rng, emu, rays, got, "fuzz %d" % it)
     ok = comparable(rays)
@@ -187,7 +201,10 @@ def two_level(rng, it):
 
 
 def main():
-    global LOCKSTEP
+    global LOCKSTEP, REFERENCE
+    if "--reference" in sys.argv:
+        REFERENCE = True
+        sys.argv.remove("--reference")
     if "--lockstep" in sys.argv:
         LOCKSTEP = True
         sys.argv.remove("--lockstep")
