@@ -43,3 +43,30 @@ def test_prefetch_variant_matches_oracle():
         scene.free()
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("inst_bias", [0, 4, 64])
+def test_instance_vote_settings_match_oracle(inst_bias):
+    """Two-level kernel: entering instances is a voted phase (`inst_bias`, default 8).  Any setting -- enter at
+    once (0), eager (4), wait until nothing else is left (64) -- must give the oracle's hits bit for bit."""
+    import scene_zoo as Z
+    dev = capi.Device(0)
+    try:
+        for desc in (Z.instances_scene(), S.load_fixture("lightinstances", max_objects=800)):
+            osc = H.oracle_scene(desc)
+            mb = O.MBVH(osc, tree_type=4)
+            a = H.mbvh_arrays(desc, mb)
+            scene = dev.upload_mbvh(a["root_nodes"], a["leaf_nodes"], a["leaf_verts"], a["transforms_minv"], a["motion_table"], a["interps"])
+            assert scene.info().two_level == 1
+            lo, hi = desc.bbox()
+            rays = np.concatenate([R.to_numpy_rays(R.uniform_rays(lo, hi, 200000, seed=71)),
+                                   R.to_numpy_rays(R.camera_rays(desc.cam, 400, 400, seed=72))])
+            ref = mb.intersect(rays)
+            dev.set_option("inst_bias", inst_bias)
+            got = scene.trace_host(rays)
+            dev.set_option("inst_bias", 8)
+            rep = H.compare_hits(got, ref, rays, what="%s inst_bias=%d" % (desc.name, inst_bias))
+            assert rep["bit_exact_hits"] == rep["hits"] and rep["hits"] > 0.1 * rep["n"]
+            scene.free()
+    finally:
+        dev.close()

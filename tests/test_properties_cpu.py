@@ -82,9 +82,9 @@ def test_property_checkers_catch_wrong_answers():
     with pytest.raises(AssertionError):
         P.check_minimality(ignores_maxt, rays, hits)
 
-    def too_eager(r):       # drops hits within a few ulp of maxt
+    def too_eager(r):       # drops hits in the last 0.2 % of the interval
         rr = r.clone()
-        R.rays_f32(rr)[:, 7] *= (1.0 - 1e-6)
+        R.rays_f32(rr)[:, 7] *= (1.0 - 2e-3)
         h = good(rr).clone()
         f = h.view(torch.float32).view(-1, 5)
         missed = h.view(torch.int32).view(-1, 5)[:, 3] == -1
