@@ -481,8 +481,9 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		AddSlot(in, wideOf, 0, nullptr, &b, out);
 		WideNode w;
 		QuantizeNode(b, kNullIndex, 0, &w);
+		*stackNeed = kWideSlots - 1;        // the unused slots "pass" for a NaN ray (see the sweep at the end)
 		if (in.instLeaves)
-			*stackNeed = 1 + (*in.leafStackNeed)[nodes[0].bvhLeaf.leafIndex];
+			*stackNeed += 1 + (*in.leafStackNeed)[nodes[0].bvhLeaf.leafIndex];
 		out->wide.push_back(w);
 		return wideStart;
 	}
@@ -573,13 +574,19 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 
 	// Worst-case live stack entries.  Children always have larger wide indices than their parent
 	// (depth-first pre-order), so one reverse sweep suffices.  Visiting w pushes every entry but the
-	// one it continues with:  D[w] = (entries of w) - 1 + max over entries D[entry];  entering an
-	// instance first pushes the sentinel.
+	// one it continues with:  D[w] = (slots of w) - 1 + max over entries D[entry];  entering an
+	// instance first pushes the sentinel.  ALL FOUR slots count, used or not: for a ray with a NaN
+	// origin / direction (or a NaN time, through the motion matrices) every comparison of the slab test is
+	// false, so every slot "passes" -- the unused ones too, whose kNullIndex references are pushed and
+	// dropped when popped.  Counting only the used slots under-estimated the depth such a ray reaches
+	// (binary trees: three pushes per level instead of one), and the kernels' spill buffers and the choice
+	// of the non-spilling kernel are sized by this number (found by tools/fuzz_parity.py --lockstep under
+	// AddressSanitizer).
 	std::vector<uint32_t> D(nWide, 0);
 	for (uint32_t r = nWide; r-- > 0;) {
 		const WideNode &w = out->wide[wideStart + r];
 		const uint32_t nChild = NodeSlots(w);
-		uint32_t k = nChild + (w.next != kNullIndex ? 1u : 0u);
+		uint32_t k = kWideSlots + (w.next != kNullIndex ? 1u : 0u);
 		uint32_t below = 0;
 		for (uint32_t c = 0; c < nChild; ++c) {
 			const uint32_t ref = w.child[c];

@@ -127,3 +127,33 @@ def test_signalled_gather_kernel_in_lockstep(kitchen, n_warps, chunk_shift):
     assert order_ok
     assert set(np.unique(flags).tolist()) <= {0, 9}
     assert raised == int((flags == 9).sum()) == len(flags)     # the detector itself raised every chunk (on the GPU the host's memset is only the safety net)
+
+
+@pytest.mark.parametrize("tree_type", [2, 4, 8])
+def test_non_finite_rays_stay_within_the_stack_bound(tree_type):
+    """Regression (tools/fuzz_parity.py --lockstep under AddressSanitizer): for a ray with a NaN origin or
+    direction every comparison of the slab test is false, so EVERY slot of every visited node passes -- the
+    unused ones too -- and the stack grows by three entries per level whatever the arity of the tree.  The
+    worst-case depth computed at upload (it sizes the kernels' spill buffers and selects the non-spilling
+    kernel) counted the used slots only: 17 against 29 reached.  Such rays must stay inside the bound, and
+    the real kernel source must survive them at any shared-memory depth (results: whatever the emulation says;
+    they are outside the parity contract)."""
+    desc = S.load_fixture("bigmonkey")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=tree_type)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(bvh.nodes(), verts, offs)
+    lo, hi = desc.bbox()
+    rays = R.to_numpy_rays(R.uniform_rays(lo, hi, 40, seed=3))
+    rays["o"][0::4] = np.nan            # all three slabs NaN: nothing is ever culled
+    rays["d"][1::4, 2] = np.nan
+    rays["d"][2::4, 1] = np.inf
+    rays["mint"][3::4] = np.nan
+    rays["maxt"][3::8] = np.nan
+    got, st = emu.trace(rays, want_stats=True)
+    need = emu.info()["stack_need"]
+    assert st["max_stack"] <= need, (st["max_stack"], need)
+    assert st["max_stack"] > need // 4          # the all-NaN rays do go deep (continuation nodes of 8-ary trees add slack)
+    for depth in (1, 16):
+        assert H.Lockstep.trace(emu, rays, smem_depth=depth, n_warps=2).tobytes() == got.tobytes()
+    assert H.Lockstep.trace(emu, rays, kernel="static", n_warps=4).tobytes() == got.tobytes()

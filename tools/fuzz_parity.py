@@ -90,6 +90,8 @@ def random_rays(rng, desc, n, seed):
     return rays
 
 
+SKIP_BELOW = int(os.environ.get("FUZZ_SKIP_BELOW", "0"))      # replay aid: scenes below this index only consume random numbers
+CURRENT = [0]
 REFERENCE = False       # --reference: also pin the oracle against the reference library on every one-level scene
 LOCKSTEP = False        # --lockstep: also run the REAL kernel source (tests/cpp/kernel_lockstep.cpp) on a slice of every batch
 
@@ -103,6 +105,11 @@ def lockstep_check(rng, emu, rays, got, what):
               tri_bias=int(rng.choice([1, 8, 64])), inst_bias=int(rng.choice([0, 8, 64])))
     if rng.random() < 0.25:
         kw = dict(kernel="static", n_warps=4)
+    if SKIP_BELOW > CURRENT[0]:
+        return
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("      lockstep", what, kw, "stack_need", emu.info()["stack_need"], "max stack of the per-ray emulation",
+              emu.trace(sub, want_stats=True)[1]["max_stack"], flush=True)
     ks = H.Lockstep.trace(emu, sub, **kw)
     if ks.tobytes() != got[pick].tobytes():
         bad = np.nonzero(ks != got[pick])[0]
@@ -134,7 +141,7 @@ def one_level(rng, it):
     emu = H.Emu.bvh(nodes, verts, offs)
     rays = random_rays(rng, desc, 3000, int(rng.integers(1, 1 << 30)))
     ref = O.BVH(osc, nodes=nodes).intersect(rays)
-    if REFERENCE:
+    if REFERENCE and SKIP_BELOW <= CURRENT[0]:
         # the reference's own BVHAccel::Intersect (oracle/_ref, compiled from /root/reference) on the same array:
         # the oracle must reproduce it bit for bit, non-finite rays included
         from oracle import refapi as RF
@@ -146,7 +153,8 @@ def one_level(rng, it):
         if not same.all():
             i = int(np.nonzero(~same)[0][0])
             raise AssertionError("fuzz %d: oracle %r != reference %r for ray %r" % (it, ref[i], theirs[i], rays[i]))
-    got = emu.trace(rays)
+    got, st = emu.trace(rays, want_stats=True)
+    assert st["max_stack"] <= emu.info()["stack_need"], ("stack bound", it, st["max_stack"], emu.info())    # non-finite rays included
     lockstep_check(rng, emu, rays, got, "fuzz %d" % it)
     ok = comparable(rays)
     rep = H.compare_hits_tie_aware(got[ok], ref[ok], rays[ok], osc, what="fuzz %d %s k=%d" % (it, builder, tree_type), max_ties=40)
@@ -191,7 +199,8 @@ def two_level(rng, it):
     rays = random_rays(rng, desc, 2500, int(rng.integers(1, 1 << 30)))      # incl. rays starting on the instanced surfaces
     ref = mb.intersect(rays)
     kw = dict(libm_outlier_frac=0.0)
-    got = emu.trace(rays)
+    got, st = emu.trace(rays, want_stats=True)
+    assert st["max_stack"] <= emu.info()["stack_need"], ("stack bound", it, st["max_stack"], emu.info())    # non-finite rays included
     lockstep_check(rng, emu, rays, got, "fuzz2l %d" % it)
     ok = comparable(rays)
     got, ref, rays = got[ok], ref[ok], rays[ok]
@@ -214,6 +223,7 @@ def main():
     t0 = time.time()
     it = 0
     while time.time() - t0 < seconds:
+        CURRENT[0] = it
         line = (one_level if it % 3 else two_level)(rng, it)
         print("%4d %s" % (it, line), flush=True)
         it += 1
