@@ -63,6 +63,7 @@ struct lrb_device {
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
 	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
+	int carveout;                   // preferred shared-memory carve-out of the trace kernels in percent (-1 = driver default)
 	int prefetch;                   // L2 prefetch of the children pushed on the stack: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
@@ -169,6 +170,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->instBias = 8;
 	dev->sortRays = 2;
 	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
+	dev->carveout = -1;
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
 	dev->gatherChunkShift = 19;
@@ -261,6 +263,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "wide_stores") {
 		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
 		dev->wideStores = iv;
+	} else if (k == "carveout") {
+		if (iv < -1 || iv > 100) return Fail(LRB_ERR_INVALID, "carveout must be -1 (default) or 0..100 percent of shared memory");
+		dev->carveout = iv;
 	} else if (k == "prefetch") {
 		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "prefetch must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
 		dev->prefetch = iv;
@@ -374,18 +379,29 @@ int lrb_reset_counters(lrb_device *dev) {
 
 }   // extern "C"
 
+// Eight independent 256-bit read-only loads (256 B) in flight per thread: 2 048 threads / SM x 256 B =
+// 512 KB in flight per SM, enough to cover the L2 / HBM latency-bandwidth product (round 1's probe kept
+// four 16-B loads in flight and under-measured L2).
 __global__ void __launch_bounds__(256) ReadProbeKernel(const uint4 *__restrict__ src, size_t n, unsigned *sink) {
 	unsigned acc = 0;
+	const size_t n32 = n / 2;       // 32-byte units
+	const char *base = reinterpret_cast<const char *>(src);
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	// four independent 16-B loads in flight per thread
-	for (; i + 3 * stride < n; i += 4 * stride) {
-		const uint4 a = __ldg(src + i), b = __ldg(src + i + stride), c = __ldg(src + i + 2 * stride), d = __ldg(src + i + 3 * stride);
-		acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+	for (; i + 7 * stride < n32; i += 8 * stride) {
+		F8 v[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+			v[k] = Ld256(base + ((i + k * stride) << 5));
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+			acc ^= __float_as_uint(v[k].v[0]) ^ __float_as_uint(v[k].v[1]) ^ __float_as_uint(v[k].v[2]) ^ __float_as_uint(v[k].v[3]) ^
+					__float_as_uint(v[k].v[4]) ^ __float_as_uint(v[k].v[5]) ^ __float_as_uint(v[k].v[6]) ^ __float_as_uint(v[k].v[7]);
 	}
-	for (; i < n; i += stride) {
-		const uint4 a = __ldg(src + i);
-		acc ^= a.x ^ a.y ^ a.z ^ a.w;
+	for (; i < n32; i += stride) {
+		const F8 v = Ld256(base + (i << 5));
+		acc ^= __float_as_uint(v.v[0]) ^ __float_as_uint(v.v[1]) ^ __float_as_uint(v.v[2]) ^ __float_as_uint(v.v[3]) ^
+				__float_as_uint(v.v[4]) ^ __float_as_uint(v.v[5]) ^ __float_as_uint(v.v[6]) ^ __float_as_uint(v.v[7]);
 	}
 	if (acc == 0x9e3779b9u)
 		*sink = acc;    // practically never: keeps the loads alive
@@ -405,7 +421,7 @@ int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double 
 	cudaEvent_t e0, e1;
 	LRB_CUDA(cudaEventCreate(&e0));
 	LRB_CUDA(cudaEventCreate(&e1));
-	const size_t n = bytes / 16;
+	const size_t n = (bytes / 32) * 2;      // 16-byte units, whole 32-byte records
 	const int grid = dev->prop.multiProcessorCount * 8;
 	for (int w = 0; w < 3; ++w)
 		ReadProbeKernel<<<grid, 256, 0, dev->stream>>>((const uint4 *)buf, n, sink);
@@ -625,7 +641,9 @@ int lrb_scene_get_info(lrb_scene *s, lrb_scene_info *out) {
 
 }   // extern "C"
 
-template <class K> static int Occupancy(K kernel, int block, int smemBytes, int *blocksPerSM) {
+template <class K> static int Occupancy(K kernel, int block, int smemBytes, int *blocksPerSM, int carveout = -1) {
+	if (carveout >= 0)
+		LRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
 	if (smemBytes > 48 * 1024)
 		LRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
 	LRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocksPerSM, kernel, block, smemBytes));
@@ -770,7 +788,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
 		const bool bigScene = sceneBytes > (size_t)dev->prop.l2CacheSize;
 		PersistentKernel kernel = PickPersistent(two, spill, signal, dev->prefetch == 1 || (dev->prefetch == 2 && bigScene));
-		if ((rc = Occupancy(kernel, block, smemBytes, &bps)) != LRB_OK) return rc;
+		if ((rc = Occupancy(kernel, block, smemBytes, &bps, dev->carveout)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
 		if (dev->blocksPerSM > 0) bps = std::min(bps, dev->blocksPerSM);
