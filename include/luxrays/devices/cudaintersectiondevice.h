@@ -107,6 +107,17 @@ public:
 	// accel->Intersect here; this build has no CPU intersection code).
 	virtual bool TraceRay(const Ray *ray, RayHit *rayHit);
 
+	// Extensions (not in the reference, which traces shadow rays as closest-hit and runs the pass-through
+	// loop of Scene::Intersect ray by ray, src/slg/scene/scene.cpp:556-690):
+	//  * shadow rays: any hit ends the ray; RayHit::Miss() is what EnqueueTraceRayBuffer would report;
+	//  * one round of the pass-through loop over a traced batch: rays that hit a mesh flagged in
+	//    passMeshBits (bit m = dataset mesh m; HardwareDeviceBuffer of u_int words, may be NULL) or flagged
+	//    by the caller in continueFlags (one byte per ray, may be NULL) get  mint = t + MachineEpsilon::E(t)
+	//    (scene.cpp:675), all the others RAY_FLAGS_MASKED; returns how many rays continue (blocks).
+	virtual void EnqueueTraceShadowRayBuffer(HardwareDeviceBuffer *rayBuff, HardwareDeviceBuffer *rayHitBuff, const unsigned int rayCount);
+	virtual unsigned int AdvancePassThroughRayBuffer(HardwareDeviceBuffer *rayBuff, HardwareDeviceBuffer *rayHitBuff, const unsigned int rayCount,
+			HardwareDeviceBuffer *passMeshBits, const unsigned int passMeshWords, HardwareDeviceBuffer *continueFlags);
+
 	// the C-ABI scene of the running kernel (nullptr before Start)
 	lrb_scene *GetNativeScene() const;
 

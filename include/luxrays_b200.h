@@ -121,7 +121,7 @@ typedef struct {
 
 typedef struct {
 	uint32_t n_ref_nodes;          /* BVHArrayNode count received */
-	uint32_t n_wide_nodes;         /* 128-B wide nodes after re-layout */
+	uint32_t n_wide_nodes;         /* 64-B quantized wide nodes after re-layout */
 	uint32_t n_triangles;          /* 64-B pre-gathered triangle records */
 	uint32_t n_instances;          /* 32-B instance records (MBVH) */
 	uint32_t stack_need;           /* worst-case traversal stack entries */
@@ -140,7 +140,7 @@ typedef struct {
 /* per-batch traversal statistics from the instrumented kernel (lrb_trace_stats) */
 typedef struct {
 	uint64_t rays;                 /* non-masked rays */
-	uint64_t wide_nodes;           /* 128-B node fetches */
+	uint64_t wide_nodes;           /* 64-B wide-node fetches */
 	uint64_t triangles;            /* 64-B triangle record fetches */
 	uint64_t instances;            /* instance entries (32-B record + 64-B matrix) */
 	uint64_t motion_samples;       /* motion leaves entered */
@@ -159,7 +159,9 @@ LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
 /* Tunables (strings): "kernel" = "persistent"|"simple", "blocks_per_sm", "smem_depth",
  * "refill_below", "tri_bias", "inst_bias", "host_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
  * "sort_bits", "sort_min_rays", "gather_stores", "gather_chunk_shift", "wide_stores",
- * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2). */
+ * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2),
+ * "compact" (1 = lrb_trace compacts the live rays first; default 0 = masked rays are skipped inside the kernel),
+ * "carveout" (preferred shared-memory carve-out of the trace kernels in percent, -1 = driver default). */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
 
 /* ---- memory + queue (cudadevice.cpp:407-540) ------------------------------------------- */
@@ -193,11 +195,51 @@ LRB_API int lrb_scene_get_info(lrb_scene *scene, lrb_scene_info *out);
  * memory included).  Asynchronous.  Rays with flags & LRB_RAY_FLAGS_MASKED are skipped and their
  * RayHit is left untouched (bvh.cl:242-244). */
 LRB_API int lrb_trace(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count);
+/* Shadow / visibility rays (any-hit).  Same buffers and masked-ray rule as lrb_trace; a ray stops at the FIRST
+ * triangle it is found to hit instead of the closest one.  Contract: RayHit::Miss() -- meshIndex ==
+ * 0xffffffff -- is exactly what lrb_trace (and the reference's Intersect, which SLG also uses for shadow
+ * rays: Scene::Intersect with SHADOW_RAY, src/slg/scene/scene.cpp:556-575) reports for that ray; for a hit
+ * the record describes SOME triangle the ray hits inside [mint, maxt] (t / b1 / b2 bit-exact for that
+ * triangle), not necessarily the nearest.  Misses carry the closest-hit miss payload. */
+LRB_API int lrb_trace_anyhit(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count);
+
+/* ---- between two traces of a batch (the path tracer's ray producer / consumer contract) ------------ */
+/* Dead-lane compaction (the reference re-launches a fixed-size Ray[taskCount] with dead lanes flagged
+ * RAY_FLAGS_MASKED, include/slg/engines/pathoclbase/kernels/pathoclbase_kernels_micro.cl:34-106,1029):
+ * builds the dense, increasing list of the indices of the non-masked rays.  The list and its length stay
+ * in device memory owned by the device object (valid until the next compaction on this device);
+ * live_count_host, when non-NULL, also receives the length (this blocks).  Device option "compact" = 1
+ * makes every lrb_trace do this first. */
+LRB_API int lrb_compact_rays(lrb_device *dev, const void *rays_dev, uint32_t ray_count,
+		const uint32_t **live_idx_dev, const uint32_t **live_count_dev, uint32_t *live_count_host);
+/* Traces only the rays listed in live_idx_dev[0 .. *live_count_dev) (ray_count entries when
+ * live_count_dev is NULL); RayHit records are written at the rays' own indices.  any_hit != 0: shadow rays. */
+LRB_API int lrb_trace_indexed(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
+		const uint32_t *live_idx_dev, const uint32_t *live_count_dev, int any_hit);
+/* One round of the reference's pass-through loop (Scene::Intersect, src/slg/scene/scene.cpp:556-690; GPU twin
+ * include/slg/scene/scene_funcs.cl:21-150) over a traced batch.  A ray "continues to trace" when it hit a
+ * mesh whose bit is set in pass_mesh_bits_dev (bit m of word m / 32: camera-invisible objects, fully
+ * transparent materials, scene.cpp:646-668) or when continue_flags_dev[i] != 0 (the caller's own material
+ * decision); either pointer may be NULL.  Such a ray is re-armed behind its hit -- ray.mint = hit.t +
+ * MachineEpsilon::E(hit.t), scene.cpp:675 -- unless that leaves no interval (scene.cpp:679-680), in which
+ * case it ends as a miss.  Every other ray gets RAY_FLAGS_MASKED, so that the next lrb_trace leaves its final
+ * RayHit untouched.  MODIFIES the ray buffer.  n_continuing_host (optional; blocks) receives the number of
+ * re-armed rays. */
+LRB_API int lrb_advance_rays(lrb_scene *scene, void *rays_dev, void *hits_dev, uint32_t ray_count,
+		const uint32_t *pass_mesh_bits_dev, uint32_t n_pass_words, const uint8_t *continue_flags_dev,
+		uint32_t *n_continuing_host);
+/* The whole loop: trace, advance, compact, re-trace ... until no ray continues or max_rounds (0 = 64)
+ * rounds were traced.  On return every RayHit holds the first hit on a mesh that is not pass-through (or a
+ * miss); the ray buffer has been consumed (see lrb_advance_rays).  Blocks. */
+LRB_API int lrb_trace_passthrough(lrb_scene *scene, void *rays_dev, void *hits_dev, uint32_t ray_count,
+		const uint32_t *pass_mesh_bits_dev, uint32_t n_pass_words, uint32_t max_rounds,
+		uint32_t *rounds_out, uint64_t *rays_traced_out);
+
 /* Host-buffer path (end to end): rays are copied in, traced and the hits copied out in chunks, with
  * the copies of neighbouring chunks overlapping the trace of the current one; synchronises before
  * returning.  preload_hits != 0 first uploads the caller's hit buffer, so that the RayHit of masked
  * rays keeps its previous content (what AllocBufferRW(&hits, hostHits, ...) does in the reference
- * sequence); with 0 the RayHit of a masked ray is unspecified. */
+ * sequence); with 0 the RayHit of a masked ray reads back as all-zero bytes. */
 LRB_API int lrb_trace_host(lrb_scene *scene, const lrb_ray *rays, lrb_rayhit *hits, uint32_t ray_count, int preload_hits);
 /* Same trace through the instrumented kernel; blocks and fills `stats`. hits_dev may be NULL. */
 LRB_API int lrb_trace_stats(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
@@ -216,10 +258,17 @@ LRB_API int lrb_ipc_close_handle(lrb_device *dev, void *devptr);
 /* Trace + gather, fused.  gather_dst_dev is this rank's slice of the gather buffer (local or
  * peer-mapped memory); hits_dev keeps the local copy (may be NULL with n_chunks == 0 when only the
  * gathered copy is wanted); gather_dst_dev == hits_dev is a plain trace.
- *   n_chunks == 0 (default): ONE kernel -- every lane stores its finished RayHit record into hits_dev
- *     and into gather_dst_dev (posted 4-byte stores over NVLink that ride along with the traversal;
- *     measured: no change in kernel time).  The records of masked rays are forwarded from hits_dev.
- *     No second launch, no copy engine, no NCCL.
+ *   n_chunks == 0 (default): ONE kernel launch.
+ *     - signalled pushes (device option gather_stores = 0, the default; needs hits_dev, the persistent
+ *       kernel and the driver entry points cuStreamWaitValue32 / cuMemsetD32Async): the kernel raises a
+ *       flag per finished chunk of 2^gather_chunk_shift ray indices and the copy engine pushes that chunk
+ *       of hits_dev into gather_dst_dev on a second stream while the kernel keeps tracing.  Batches of at
+ *       most 128 rays (one block: no room for the detector warp) take the dual-store form below.
+ *     - dual-destination stores (gather_stores = 1, or hits_dev == NULL, or kernel = simple): every lane
+ *       stores its finished RayHit record into hits_dev and into gather_dst_dev (posted stores over
+ *       NVLink).  No copy engine.
+ *     In both forms the records of masked rays are forwarded from hits_dev, so the gathered slice equals
+ *     the local buffer.  No NCCL.
  *   n_chunks >= 1: the batch is cut into n_chunks launches; each traced piece is pushed by the copy
  *     engine on a second stream while the next piece is traced.
  * Asynchronous: later work on the device's stream is ordered after the last store / push. */
@@ -231,7 +280,7 @@ LRB_API const char *lrb_last_error_string(void);
 LRB_API int lrb_get_counters(lrb_device *dev, lrb_counters *out);
 LRB_API int lrb_reset_counters(lrb_device *dev);
 LRB_API const char *lrb_version_string(void);
-/* Roofline denominator probe: streams `bytes` with 128-bit read-only loads `iters` times and reports
+/* Roofline denominator probe: streams `bytes` with 256-bit read-only loads (eight in flight per thread) `iters` times and reports
  * GB/s.  A buffer that fits in L2 (e.g. 32 MiB) measures L2 bandwidth, a multi-GiB one HBM.  Blocks. */
 LRB_API int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double *gb_per_s);
 

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libluxrays_b200.so")
+# LRB_LIB_DIR: development switch -- load a differently compiled build of the two libraries (A/B of kernel variants)
+LIB_PATH = os.path.join(os.environ.get("LRB_LIB_DIR") or os.path.join(_HERE, "lib"), "libluxrays_b200.so")
 
 LRB_OK = 0
 LRB_ERR_INVALID, LRB_ERR_CUDA, LRB_ERR_NO_DEVICE, LRB_ERR_OOM, LRB_ERR_INTERNAL = 1, 2, 3, 4, 5
@@ -29,6 +30,7 @@ EXPORTS = [
     "lrb_alloc", "lrb_free", "lrb_h2d", "lrb_d2h", "lrb_flush", "lrb_sync",
     "lrb_bvh_upload", "lrb_mbvh_upload", "lrb_mbvh_update", "lrb_scene_free", "lrb_scene_get_info",
     "lrb_trace", "lrb_trace_host", "lrb_trace_stats",
+    "lrb_trace_anyhit", "lrb_compact_rays", "lrb_trace_indexed", "lrb_advance_rays", "lrb_trace_passthrough",
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
     "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather",
@@ -105,6 +107,11 @@ def lib():
             "lrb_scene_get_info": (i32, [vp, C.POINTER(SceneInfo)]),
             "lrb_trace": (i32, [vp, vp, vp, u32]),
             "lrb_trace_host": (i32, [vp, vp, vp, u32, i32]),
+            "lrb_trace_anyhit": (i32, [vp, vp, vp, u32]),
+            "lrb_compact_rays": (i32, [vp, vp, u32, pvp, pvp, C.POINTER(u32)]),
+            "lrb_trace_indexed": (i32, [vp, vp, vp, u32, vp, vp, i32]),
+            "lrb_advance_rays": (i32, [vp, vp, vp, u32, vp, u32, vp, C.POINTER(u32)]),
+            "lrb_trace_passthrough": (i32, [vp, vp, vp, u32, vp, u32, u32, C.POINTER(u32), C.POINTER(u64)]),
             "lrb_trace_stats": (i32, [vp, vp, vp, u32, C.POINTER(TraceStats)]),
             "lrb_last_error_string": (C.c_char_p, []),
             "lrb_get_counters": (i32, [vp, C.POINTER(Counters)]),
@@ -211,13 +218,19 @@ class Device:
         return c
 
     def measure_read_bandwidth(self, nbytes, iters=20):
-        """GB/s of a streaming 128-bit read kernel over an nbytes buffer (L2-resident if it fits)."""
+        """GB/s of a streaming 256-bit read kernel over an nbytes buffer (L2-resident if it fits)."""
         g = C.c_double(0)
         _check(lib().lrb_measure_read_bandwidth(self.h, nbytes, iters, C.byref(g)))
         return g.value
 
     def reset_counters(self):
         _check(lib().lrb_reset_counters(self.h))
+
+    def compact_rays(self, rays_devptr, n, want_count=True):
+        """Dense list of the non-masked rays -> (device pointer of the index list, device pointer of its length, length or None)."""
+        idx, cnt, host = C.c_void_p(), C.c_void_p(), C.c_uint32(0)
+        _check(lib().lrb_compact_rays(self.h, C.c_void_p(rays_devptr), n, C.byref(idx), C.byref(cnt), C.byref(host) if want_count else None))
+        return idx.value or 0, cnt.value or 0, (int(host.value) if want_count else None)
 
     # ---- multi-GPU gather buffer sharing ----
     def ipc_get_handle(self, devptr):
@@ -317,6 +330,28 @@ class Scene:
         """Asynchronous EnqueueTraceRayBuffer on device pointers."""
         _check(lib().lrb_trace(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n))
 
+    def trace_anyhit(self, rays_devptr, hits_devptr, n):
+        """Shadow rays: first hit found, hit / miss identical to trace()."""
+        _check(lib().lrb_trace_anyhit(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n))
+
+    def trace_indexed(self, rays_devptr, hits_devptr, n, live_idx_devptr, live_count_devptr=0, any_hit=False):
+        _check(lib().lrb_trace_indexed(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n, C.c_void_p(live_idx_devptr),
+                                       C.c_void_p(live_count_devptr or 0), 1 if any_hit else 0))
+
+    def advance_rays(self, rays_devptr, hits_devptr, n, pass_mesh_bits_devptr=0, n_pass_words=0, continue_flags_devptr=0):
+        """One round of the pass-through loop; returns the number of rays that continue."""
+        c = C.c_uint32(0)
+        _check(lib().lrb_advance_rays(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n, C.c_void_p(pass_mesh_bits_devptr or 0),
+                                      n_pass_words, C.c_void_p(continue_flags_devptr or 0), C.byref(c)))
+        return int(c.value)
+
+    def trace_passthrough(self, rays_devptr, hits_devptr, n, pass_mesh_bits_devptr, n_pass_words, max_rounds=0):
+        """-> (rounds traced, rays traced over all rounds)."""
+        r, t = C.c_uint32(0), C.c_uint64(0)
+        _check(lib().lrb_trace_passthrough(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n, C.c_void_p(pass_mesh_bits_devptr or 0),
+                                           n_pass_words, max_rounds, C.byref(r), C.byref(t)))
+        return int(r.value), int(t.value)
+
     def trace_host(self, rays, hits=None):
         """Host arrays in, host array out (H2D + trace + D2H inside)."""
         rays = np.ascontiguousarray(rays)
@@ -331,7 +366,7 @@ class Scene:
     def trace_host_ptr(self, rays_hostptr, hits_hostptr, n, preload_hits=False):
         _check(lib().lrb_trace_host(self.h, C.c_void_p(rays_hostptr), C.c_void_p(hits_hostptr), n, 1 if preload_hits else 0))
 
-    def trace_gather(self, rays_devptr, hits_devptr, n, gather_dst_devptr, n_chunks=8):
+    def trace_gather(self, rays_devptr, hits_devptr, n, gather_dst_devptr, n_chunks=0):
         """Trace + overlapped push of the RayHit slice into the (possibly peer-mapped) gather buffer."""
         _check(lib().lrb_trace_gather(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n,
                                       C.c_void_p(gather_dst_devptr), n_chunks))

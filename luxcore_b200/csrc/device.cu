@@ -23,6 +23,7 @@
 #include "layout.h"
 #include "relayout.h"
 #include "trace_kernels.cuh"
+#include "batch_kernels.cuh"
 
 using namespace lrb;
 
@@ -63,6 +64,9 @@ struct lrb_device {
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
 	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
+	int compact;                    // 1: lrb_trace first builds the dense list of live (non-masked) rays and traces through it
+	uint32_t *compactIdx, *compactBlocks, *compactTotal;    // scratch of the compaction kernels
+	size_t compactCap;
 	int carveout;                   // preferred shared-memory carve-out of the trace kernels in percent (-1 = driver default)
 	int prefetch;                   // L2 prefetch of the children pushed on the stack: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
@@ -171,6 +175,9 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortRays = 2;
 	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
 	dev->carveout = -1;
+	dev->compact = 0;
+	dev->compactIdx = dev->compactBlocks = dev->compactTotal = nullptr;
+	dev->compactCap = 0;
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
 	dev->gatherChunkShift = 19;
@@ -194,6 +201,7 @@ int lrb_device_destroy(lrb_device *dev) {
 	if (dev->stageHits) cudaFree(dev->stageHits);
 	cudaFree(dev->sortKeys[0]); cudaFree(dev->sortKeys[1]); cudaFree(dev->sortVals[0]); cudaFree(dev->sortVals[1]);
 	cudaFree(dev->sortTemp);
+	cudaFree(dev->compactIdx); cudaFree(dev->compactBlocks); cudaFree(dev->compactTotal);
 	cudaStreamDestroy(dev->copyInStream);
 	cudaStreamDestroy(dev->copyOutStream);
 	cudaStreamDestroy(dev->ownStream);
@@ -263,6 +271,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "wide_stores") {
 		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
 		dev->wideStores = iv;
+	} else if (k == "compact") {
+		if (iv < 0 || iv > 1) return Fail(LRB_ERR_INVALID, "compact must be 0 (masked rays are skipped inside the trace kernel) or 1 (compacted before it)");
+		dev->compact = iv;
 	} else if (k == "carveout") {
 		if (iv < -1 || iv > 100) return Fail(LRB_ERR_INVALID, "carveout must be -1 (default) or 0..100 percent of shared memory");
 		dev->carveout = iv;
@@ -448,7 +459,11 @@ template <class T> static int UploadArray(lrb_device *dev, const std::vector<T> 
 	if (cap && *dst && *cap >= n) {
 		// re-use the allocation (Update path)
 	} else {
-		if (*dst) { LRB_CUDA(cudaFree(*dst)); *dst = nullptr; }
+		if (*dst) {
+			LRB_CUDA(cudaFree(*dst));
+			*dst = nullptr;
+			if (bytes && cap) *bytes -= *cap * sizeof(T);      // re-grown (Update): the old allocation is gone
+		}
 		if (n) {
 			LRB_CUDA(cudaMalloc((void **)dst, n * sizeof(T)));
 			if (bytes) *bytes += n * sizeof(T);
@@ -716,7 +731,11 @@ static int SortRays(lrb_scene *s, const void *rays, uint32_t n, cudaStream_t str
 	return LRB_OK;
 }
 
-static PersistentKernel PickPersistent(bool two, bool spill, bool signal, bool prefetch) {
+static PersistentKernel PickPersistent(bool two, bool spill, bool signal, bool prefetch, bool anyhit = false) {
+	if (anyhit) {       // shadow rays: no gather signalling, no prefetch twin
+		if (two) return spill ? TracePersistent<true, true, false, false, true> : TracePersistent<true, false, false, false, true>;
+		return spill ? TracePersistent<false, true, false, false, true> : TracePersistent<false, false, false, false, true>;
+	}
 	// the prefetching variant exists for one-level scenes with a spilling stack (large scenes are both)
 	if (prefetch && !two && spill)
 		return signal ? TracePersistent<false, true, true, true> : TracePersistent<false, true, false, true>;
@@ -749,8 +768,39 @@ static int ResolveDriverEntryPoints() {
 	return LRB_OK;
 }
 
+// Dense list of the live (non-masked) rays of a batch, in increasing index order (batch_kernels.cuh).  The
+// list and its length stay on the device: *idx / *count are device pointers owned by the device object.
+static int CompactRays(lrb_device *dev, const void *rays, uint32_t n, cudaStream_t stream, const uint32_t **idx, const uint32_t **count) {
+	const uint32_t nBlocks = (n + kCompactBlock - 1) / kCompactBlock;
+	if (dev->compactCap < n) {
+		LRB_CUDA(cudaStreamSynchronize(stream));
+		cudaFree(dev->compactIdx); cudaFree(dev->compactBlocks); cudaFree(dev->compactTotal);
+		dev->compactIdx = dev->compactBlocks = dev->compactTotal = nullptr;
+		dev->compactCap = 0;
+		LRB_CUDA(cudaMalloc((void **)&dev->compactIdx, (size_t)n * sizeof(uint32_t)));
+		LRB_CUDA(cudaMalloc((void **)&dev->compactBlocks, (size_t)nBlocks * sizeof(uint32_t)));
+		LRB_CUDA(cudaMalloc((void **)&dev->compactTotal, 64));
+		dev->compactCap = n;
+	}
+	CompactCountKernel<<<nBlocks, 256, 0, stream>>>((const lrb_ray *)rays, n, dev->compactBlocks);
+	CompactScanKernel<<<1, 1024, 0, stream>>>(dev->compactBlocks, nBlocks, dev->compactTotal);
+	CompactScatterKernel<<<nBlocks, 256, 0, stream>>>((const lrb_ray *)rays, n, dev->compactBlocks, dev->compactIdx);
+	LRB_CUDA(cudaGetLastError());
+	dev->counters.kernel_launches += 3;
+	*idx = dev->compactIdx;
+	*count = dev->compactTotal;
+	return LRB_OK;
+}
+
+struct TraceMode {
+	bool anyhit;                    // shadow rays: the first accepted hit ends the ray
+	const uint32_t *liveIdx;        // trace only the rays listed here (device pointer) ...
+	const uint32_t *liveCountDev;   // ... as many as this device word says (or n when NULL)
+	TraceMode() : anyhit(false), liveIdx(nullptr), liveCountDev(nullptr) { }
+};
+
 static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, bool stats, cudaStream_t stream,
-		lrb_rayhit *hitsPeer = nullptr, bool signal = false) {
+		lrb_rayhit *hitsPeer = nullptr, bool signal = false, TraceMode mode = TraceMode()) {
 	lrb_device *dev = s->dev;
 	if (n == 0)
 		return LRB_OK;
@@ -778,16 +828,21 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;
+	if (!mode.liveIdx && dev->compact && !signal && !stats) {
+		if ((rc = CompactRays(dev, rays, n, stream, &mode.liveIdx, &mode.liveCountDev)) != LRB_OK) return rc;
+	}
+	a.perm = mode.liveIdx;
+	a.rayCountDev = mode.liveCountDev;
 
 	if (dev->persistent && !stats) {
 		const int block = kTraceBlock;
 		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
-		const int smemBytes = depth * block * 8;
+		const int smemBytes = depth * block * 8 + (two ? 3 * block * 4 : 0);     // stack columns (+ the world ray's 1/d, SmemStack::stashInv)
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
 		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
 		const bool bigScene = sceneBytes > (size_t)dev->prop.l2CacheSize;
-		PersistentKernel kernel = PickPersistent(two, spill, signal, dev->prefetch == 1 || (dev->prefetch == 2 && bigScene));
+		PersistentKernel kernel = PickPersistent(two, spill, signal, dev->prefetch == 1 || (dev->prefetch == 2 && bigScene), mode.anyhit);
 		if ((rc = Occupancy(kernel, block, smemBytes, &bps, dev->carveout)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
@@ -838,7 +893,8 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 			if (two) rc = Occupancy(TraceStatic<true, true>, block, 0, &bps);
 			else rc = Occupancy(TraceStatic<false, true>, block, 0, &bps);
 		} else {
-			if (two) rc = Occupancy(TraceStatic<true, false>, block, 0, &bps);
+			if (mode.anyhit) rc = two ? Occupancy(TraceStatic<true, false, true>, block, 0, &bps) : Occupancy(TraceStatic<false, false, true>, block, 0, &bps);
+			else if (two) rc = Occupancy(TraceStatic<true, false>, block, 0, &bps);
 			else rc = Occupancy(TraceStatic<false, false>, block, 0, &bps);
 		}
 		if (rc != LRB_OK) return rc;
@@ -854,6 +910,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 			LRB_CUDA(cudaMemsetAsync(s->dStats, 0, sizeof(TraceStats), stream));
 			if (two) TraceStatic<true, true><<<(unsigned)grid, block, 0, stream>>>(a);
 			else TraceStatic<false, true><<<(unsigned)grid, block, 0, stream>>>(a);
+		} else if (mode.anyhit) {
+			if (two) TraceStatic<true, false, true><<<(unsigned)grid, block, 0, stream>>>(a);
+			else TraceStatic<false, false, true><<<(unsigned)grid, block, 0, stream>>>(a);
 		} else {
 			if (two) TraceStatic<true, false><<<(unsigned)grid, block, 0, stream>>>(a);
 			else TraceStatic<false, false><<<(unsigned)grid, block, 0, stream>>>(a);
@@ -873,6 +932,111 @@ int lrb_trace(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
 		return Fail(LRB_ERR_INVALID, "null scene");
 	LRB_SETDEV(s->dev);
 	return LaunchTrace(s, rays, hits, n, false, s->dev->stream);
+}
+
+int lrb_trace_anyhit(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	LRB_SETDEV(s->dev);
+	TraceMode mode;
+	mode.anyhit = true;
+	return LaunchTrace(s, rays, hits, n, false, s->dev->stream, nullptr, false, mode);
+}
+
+int lrb_compact_rays(lrb_device *dev, const void *rays, uint32_t n, const uint32_t **liveIdxDev, const uint32_t **liveCountDev, uint32_t *liveCountHost) {
+	if (!liveIdxDev || !liveCountDev)
+		return Fail(LRB_ERR_INVALID, "null out pointer");
+	LRB_SETDEV(dev);
+	*liveIdxDev = nullptr; *liveCountDev = nullptr;
+	if (liveCountHost) *liveCountHost = 0;
+	if (n == 0)
+		return LRB_OK;
+	if (!rays)
+		return Fail(LRB_ERR_INVALID, "null ray buffer");
+	const int rc = CompactRays(dev, rays, n, dev->stream, liveIdxDev, liveCountDev);
+	if (rc != LRB_OK)
+		return rc;
+	if (liveCountHost) {
+		LRB_CUDA(cudaMemcpyAsync(liveCountHost, *liveCountDev, sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+		dev->counters.d2h_bytes += 4;
+	}
+	return LRB_OK;
+}
+
+int lrb_trace_indexed(lrb_scene *s, const void *rays, void *hits, uint32_t n, const uint32_t *liveIdxDev, const uint32_t *liveCountDev, int anyhit) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	LRB_SETDEV(s->dev);
+	if (!liveIdxDev)
+		return Fail(LRB_ERR_INVALID, "null index list");
+	TraceMode mode;
+	mode.anyhit = anyhit != 0;
+	mode.liveIdx = liveIdxDev;
+	mode.liveCountDev = liveCountDev;
+	return LaunchTrace(s, rays, hits, n, false, s->dev->stream, nullptr, false, mode);
+}
+
+int lrb_advance_rays(lrb_scene *s, void *rays, void *hits, uint32_t n, const uint32_t *passMeshBitsDev, uint32_t nPassWords,
+		const uint8_t *continueFlagsDev, uint32_t *nContinuingHost) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	if (nContinuingHost) *nContinuingHost = 0;
+	if (n == 0)
+		return LRB_OK;
+	if (!rays || !hits)
+		return Fail(LRB_ERR_INVALID, "null ray/hit buffer");
+	uint32_t *cnt = s->dCounter + 8;        // a word of the scene's counter block the trace kernels do not use
+	LRB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), dev->stream));
+	AdvanceRaysKernel<<<(n + 255) / 256, 256, 0, dev->stream>>>((lrb_ray *)rays, (lrb_rayhit *)hits, n, passMeshBitsDev, nPassWords,
+			continueFlagsDev, cnt);
+	LRB_CUDA(cudaGetLastError());
+	dev->counters.kernel_launches += 1;
+	if (nContinuingHost) {
+		LRB_CUDA(cudaMemcpyAsync(nContinuingHost, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
+		LRB_CUDA(cudaStreamSynchronize(dev->stream));
+		dev->counters.d2h_bytes += 4;
+	}
+	return LRB_OK;
+}
+
+int lrb_trace_passthrough(lrb_scene *s, void *rays, void *hits, uint32_t n, const uint32_t *passMeshBitsDev, uint32_t nPassWords,
+		uint32_t maxRounds, uint32_t *roundsOut, uint64_t *raysTracedOut) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	if (roundsOut) *roundsOut = 0;
+	if (raysTracedOut) *raysTracedOut = 0;
+	if (n == 0)
+		return LRB_OK;
+	if (maxRounds == 0) maxRounds = 64;
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	uint32_t live = n, rounds = 0;
+	uint64_t traced = 0;
+	for (;;) {
+		// after the first round most lanes are dead: trace through the dense list of the live ones
+		int rc;
+		if (rounds == 0)
+			rc = LaunchTrace(s, rays, hits, n, false, dev->stream);
+		else {
+			TraceMode mode;
+			if ((rc = CompactRays(dev, rays, n, dev->stream, &mode.liveIdx, &mode.liveCountDev)) != LRB_OK) return rc;
+			rc = LaunchTrace(s, rays, hits, n, false, dev->stream, nullptr, false, mode);
+		}
+		if (rc != LRB_OK)
+			return rc;
+		traced += live;
+		++rounds;
+		if ((rc = lrb_advance_rays(s, rays, hits, n, passMeshBitsDev, nPassWords, nullptr, &live)) != LRB_OK)
+			return rc;
+		if (live == 0 || rounds >= maxRounds)
+			break;
+	}
+	if (roundsOut) *roundsOut = rounds;
+	if (raysTracedOut) *raysTracedOut = traced;
+	return LRB_OK;
 }
 
 int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {
@@ -940,7 +1104,8 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 	if (nChunks == 0) {
 		if (dst == hits)
 			return LaunchTrace(s, rays, hits, n, false, dev->stream);
-		if (dev->gatherStores || !hits || !dev->persistent) {
+		// a batch of at most one block has no room for the detector warp of the signalled form
+		if (dev->gatherStores || !hits || !dev->persistent || n <= (uint32_t)kTraceBlock) {
 			// ONE kernel; every lane stores its RayHit into the local buffer (if any) and into the gather slice
 			return LaunchTrace(s, rays, hits, n, false, dev->stream, (lrb_rayhit *)dst);
 		}
@@ -1036,6 +1201,8 @@ int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t
 		dev->stageHitsBytes = hb;
 	}
 	const bool anyMasked = preloadHits != 0;
+	if (!anyMasked)     // masked rays leave their record untouched: make what is read back for them deterministic
+		LRB_CUDA(cudaMemsetAsync(dev->stageHits, 0, hb, dev->stream));
 
 	const uint32_t chunk = (uint32_t)dev->hostChunk;
 	const uint32_t nChunks = (n + chunk - 1) / chunk;

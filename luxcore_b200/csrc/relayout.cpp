@@ -282,6 +282,37 @@ static bool Invert4x4(const float *m, double out[16]) {
 // whole grid) for singular or projective matrices and non-finite results.
 static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const float *lb, float lo[3], float hi[3]);
 
+// Rounding of the reference's own ray transform.  The reference tests the leaf tree's root box with the
+// float ray  mInv * o, mInv * d : each component carries an error of a few ulp of the terms it sums, i.e.
+// ~ eps * |mInv| * (|o| + |translation|) in instance space, which is  eps * cond(M) * (|o| + |t|)  back in
+// world space (cond = |M| |mInv|, infinity norms of the 3x3 parts).  A ray that misses the exact world
+// bounds by less than that can still reach a silhouette triangle in the reference, so the world box is
+// grown by it, taking for |o| and for the distance travelled four times the largest coordinate of the
+// dataset's root box: rays that start farther than that from the origin are outside what this margin
+// covers (supported range; stated in DESIGN.md "Parity").
+static double SceneMagnitude(const TreeInput &in) {
+	double m = 0.0;
+	if (in.n && !IsLeaf(in.nodes[0].nodeData))
+		for (int a = 0; a < 3; ++a) {
+			const double lo = in.nodes[0].bvhNode.bboxMin[a], hi = in.nodes[0].bvhNode.bboxMax[a];
+			if (std::isfinite(lo)) m = std::max(m, fabs(lo));
+			if (std::isfinite(hi)) m = std::max(m, fabs(hi));
+		}
+	return m;
+}
+
+static double Norm3x3(const double *M) {
+	double n = 0.0;
+	for (int r = 0; r < 3; ++r)
+		n = std::max(n, fabs(M[4 * r]) + fabs(M[4 * r + 1]) + fabs(M[4 * r + 2]));
+	return n;
+}
+
+static double TransformRoundingMargin(const TreeInput &in, const double *M, const double *Minv, const double mag) {
+	const double cond = std::min(Norm3x3(M) * Norm3x3(Minv), 1e12);
+	return 16.0 * 5.9604644775390625e-08 * cond * (4.0 * SceneMagnitude(in) + mag);
+}
+
 static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float lo[3], float hi[3]) {
 	if (!in.leafBox)
 		return false;
@@ -291,9 +322,11 @@ static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float 
 	if (nd.bvhLeaf.motionIndex != kNullIndex)
 		return MotionWorldBox(in, nd, lb, lo, hi);
 	double M[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+	double Minv[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
 	if (nd.bvhLeaf.transformIndex != kNullIndex) {
 		if (!in.minv || !Invert4x4(in.minv + 16 * (size_t)nd.bvhLeaf.transformIndex, M))
 			return false;
+		for (int k = 0; k < 16; ++k) Minv[k] = in.minv[16 * (size_t)nd.bvhLeaf.transformIndex + k];
 		if (fabs(M[12]) > 1e-12 || fabs(M[13]) > 1e-12 || fabs(M[14]) > 1e-12 || fabs(M[15] - 1.0) > 1e-9)
 			return false;       // projective: the bounds of the corners do not bound the box
 	}
@@ -308,7 +341,7 @@ static bool InstanceWorldBox(const TreeInput &in, const lrb_bvh_node &nd, float 
 		}
 	}
 	const double diag = std::max(std::max(whi[0] - wlo[0], whi[1] - wlo[1]), whi[2] - wlo[2]);
-	const double grow = 1e-4 * diag + 4e-6 * mag + 1e-6;    // far above the float rounding of the reference's ray transform
+	const double grow = 1e-4 * diag + 4e-6 * mag + 1e-6 + TransformRoundingMargin(in, M, Minv, mag);
 	for (int r = 0; r < 3; ++r) {
 		lo[r] = (float)(wlo[r] - grow);
 		hi[r] = (float)(whi[r] + grow);
@@ -352,7 +385,7 @@ static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const fl
 			times.push_back((float)((double)times[k] + ((double)times[k + 1] - (double)times[k]) * j / perSegment));
 	std::sort(times.begin(), times.end());
 
-	double wlo[3] = { 1e300, 1e300, 1e300 }, whi[3] = { -1e300, -1e300, -1e300 }, mag = 0.0, step = 0.0;
+	double wlo[3] = { 1e300, 1e300, 1e300 }, whi[3] = { -1e300, -1e300, -1e300 }, mag = 0.0, step = 0.0, rounding = 0.0;
 	double prev[8][3];
 	bool havePrev = false;
 	for (size_t ti = 0; ti < times.size(); ++ti) {
@@ -363,6 +396,11 @@ static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const fl
 			return false;
 		if (fabs(M[12]) > 1e-12 || fabs(M[13]) > 1e-12 || fabs(M[14]) > 1e-12 || fabs(M[15] - 1.0) > 1e-9)
 			return false;
+		{
+			double md[16];
+			for (int k = 0; k < 16; ++k) md[k] = m[k];
+			rounding = std::max(rounding, TransformRoundingMargin(in, M, md, 0.0));
+		}
 		for (int corner = 0; corner < 8; ++corner) {
 			const double p[3] = { lb[(corner & 1) ? 3 : 0], lb[(corner & 2) ? 4 : 1], lb[(corner & 4) ? 5 : 2] };
 			double w[3], d2 = 0.0;
@@ -380,7 +418,7 @@ static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const fl
 		havePrev = true;
 	}
 	const double diag = std::max(std::max(whi[0] - wlo[0], whi[1] - wlo[1]), whi[2] - wlo[2]);
-	const double grow = 1.25 * step + 1e-4 * diag + 4e-6 * mag + 1e-6;
+	const double grow = 1.25 * step + 1e-4 * diag + 4e-6 * mag + 1e-6 + rounding + 16.0 * 5.9604644775390625e-08 * mag;
 	for (int r = 0; r < 3; ++r) {
 		lo[r] = (float)(wlo[r] - grow);
 		hi[r] = (float)(whi[r] + grow);

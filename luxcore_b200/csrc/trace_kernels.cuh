@@ -23,6 +23,13 @@
 namespace lrb {
 
 static const int kTraceBlock = 128;     // threads per block of every trace kernel
+// Resident blocks per SM the persistent kernels are compiled for (register budget = 65 536 / (128 x blocks)).
+#ifndef LRB_MINBLOCKS_1L
+#define LRB_MINBLOCKS_1L 8
+#endif
+#ifndef LRB_MINBLOCKS_2L
+#define LRB_MINBLOCKS_2L 6
+#endif
 
 // ---- stacks ---------------------------------------------------------------------------------
 
@@ -78,6 +85,13 @@ template <bool SPILL> struct SmemStack {
 	}
 	__device__ __forceinline__ bool empty() const { return top == base; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)((top - base) / (2 * kTraceBlock) + over); }
+	// two-level kernels: three more words per thread behind the stack columns (the launch sizes shared memory for them)
+	__device__ __forceinline__ void stashInv(float x, float y, float z) {
+		limit[0] = __float_as_uint(x); limit[kTraceBlock] = __float_as_uint(y); limit[2 * kTraceBlock] = __float_as_uint(z);
+	}
+	__device__ __forceinline__ void loadInv(float &x, float &y, float &z) const {
+		x = __uint_as_float(limit[0]); y = __uint_as_float(limit[kTraceBlock]); z = __uint_as_float(limit[2 * kTraceBlock]);
+	}
 };
 
 // Local-memory stack + global spill.
@@ -116,6 +130,9 @@ template <int CAP> struct LocalStack {
 	}
 	__device__ __forceinline__ bool empty() const { return sp == 0; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
+	float inv[3];
+	__device__ __forceinline__ void stashInv(float x, float y, float z) { inv[0] = x; inv[1] = y; inv[2] = z; }
+	__device__ __forceinline__ void loadInv(float &x, float &y, float &z) const { x = inv[0]; y = inv[1]; z = inv[2]; }
 };
 
 struct TraceArgs {
@@ -124,7 +141,10 @@ struct TraceArgs {
 	lrb_rayhit *hits;
 	uint32_t rayCount;
 	uint32_t *counter;          // persistent kernel: next unassigned ray (zeroed before launch)
-	const uint32_t *perm;       // optional processing order (ray indices sorted for coherence), or NULL
+	const uint32_t *perm;       // optional processing order (ray indices sorted for coherence, or the dense list of
+	                            // live rays left by the compaction kernels), or NULL
+	const uint32_t *rayCountDev;    // optional: number of entries of perm to process, read on the device (compaction
+	                            // leaves it there; no host round trip between the compaction and the trace)
 	uint32_t *spillNode;        // global stack spill, [spillDepth][totalThreads]
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
@@ -268,9 +288,13 @@ __device__ __forceinline__ void DetectorLoop(const TraceArgs &a, const uint32_t 
 	}
 }
 
-template <bool TWO_LEVEL, bool SPILL, bool SIGNAL, bool PREFETCH = false>
-__global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersistent(const TraceArgs a) {
+// ANYHIT (shadow / visibility rays, lrb_trace_anyhit): the first accepted hit finishes the ray -- its stack is
+// dropped and the lane stores that hit at the next re-fill.  Hit / miss is the closest-hit kernel's (and the
+// reference's Intersect's): a ray is a hit exactly when at least one triangle passes the test and its gate.
+template <bool TWO_LEVEL, bool SPILL, bool SIGNAL, bool PREFETCH = false, bool ANYHIT = false>
+__global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LRB_MINBLOCKS_1L) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
+	const uint32_t rayCount = a.rayCountDev ? __ldg(a.rayCountDev) : a.rayCount;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warpId = (blockIdx.x * kTraceBlock + threadIdx.x) >> 5;
 	if (SIGNAL && warpId == 0) {
@@ -317,7 +341,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersisten
 			base = __shfl_sync(0xffffffffu, base, leader);
 			if (state == kIdle) {
 				const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
-				if (slot < a.rayCount) {
+				if (slot < rayCount) {
 					const uint32_t idx = a.perm ? __ldg(a.perm + slot) : slot;
 					lrb_ray r;
 					LoadRay(a.rays, idx, r);
@@ -336,7 +360,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersisten
 			}
 			if (SIGNAL)
 				lowBound = base + (uint32_t)nIdle;
-			if (base + (uint32_t)nIdle >= a.rayCount)
+			if (base + (uint32_t)nIdle >= rayCount)
 				exhausted = 1;
 		}
 		if (__ballot_sync(0xffffffffu, state == kActive) == 0) {
@@ -385,8 +409,13 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? 6 : 8) TracePersisten
 				}
 			}
 			if (VoteTrianglePhase(nTri, nNode, a.triBias)) {
-				if (work == kWorkTri)
+				if (work == kWorkTri) {
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+					if (ANYHIT && s.hitMesh != kNullIndex) {
+						stk.reset();        // s.cur is already kNullIndex: the next Resolve finds the ray finished
+						s.inInstance = false;
+					}
+				}
 			} else {
 				if (work == kWorkNode)
 					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(256) RayKeyKernel(const lrb_ray *__restrict__ 
 
 // ---- static grid-stride kernel (simple variant + instrumented variant) -----------------------
 
-template <bool TWO_LEVEL, bool STATS>
+template <bool TWO_LEVEL, bool STATS, bool ANYHIT = false>
 __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 	const uint32_t totalThreads = gridDim.x * blockDim.x;
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,16 +474,23 @@ __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 	local.rays = local.wideNodes = local.triangles = local.instances = local.motionSamples = local.maxStack = 0;
 	unsigned long long nRays = 0;
 
-	for (uint32_t i = gtid; i < a.rayCount; i += totalThreads) {
+	const uint32_t rayCount = a.rayCountDev ? __ldg(a.rayCountDev) : a.rayCount;
+	for (uint32_t slot = gtid; slot < rayCount; slot += totalThreads) {
+		const uint32_t i = a.perm ? __ldg(a.perm + slot) : slot;
 		lrb_ray r;
 		LoadRay(a.rays, i, r);
-		if (r.flags & LRB_RAY_FLAGS_MASKED)
+		if (r.flags & LRB_RAY_FLAGS_MASKED) {
+			ForwardMaskedHit(a, i);
 			continue;
+		}
 		++nRays;
 		RayState s;
 		stk.sp = 0;
 		if (InitRay(a.sc, r, s)) {
-			while (Step<TWO_LEVEL, STATS>(a.sc, a.rays[i], s, stk, &local)) { }
+			while (Step<TWO_LEVEL, STATS>(a.sc, a.rays[i], s, stk, &local)) {
+				if (ANYHIT && s.hitMesh != kNullIndex)
+					break;
+			}
 		}
 		StoreHit(a, i, s, r.maxt);
 	}

@@ -330,6 +330,30 @@ LRB_HD void TransformRayLocal(RayState &s, const float *m, float ox, float oy, f
 	SetRay(s, px, py, pz, vx, vy, vz);
 }
 
+// Motion-blurred instance: the ray in instance space at the ray's time.  On the device this is ONE out-of-line
+// function: MotionSample carries double-precision sin / acos (see LRB_SINF) and a 16-float matrix, several hundred
+// instructions that would otherwise be inlined into the hot loop of every two-level kernel (instruction-cache
+// misses showed up as `no_instruction` stalls in the round-2 profile of lightinstances, which has no motion at all).
+struct Ray6 { float ox, oy, oz, dx, dy, dz; };
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+Ray6 MotionRay(const uint32_t *motionFirst, const uint32_t *motionLast, const DevInterp *interps, const uint32_t motionIndex,
+		const float time, const float ox, const float oy, const float oz, const float dx, const float dy, const float dz) {
+	SceneView sc = SceneView();
+	sc.motionFirst = motionFirst;
+	sc.motionLast = motionLast;
+	sc.interps = interps;
+	float m[16];
+	MotionSample(sc, motionIndex, time, m);
+	RayState t;
+	TransformRayLocal(t, m, ox, oy, oz, dx, dy, dz);
+	Ray6 r = { t.ox, t.oy, t.oz, t.dx, t.dy, t.dz };
+	return r;
+}
+
 // Initialise the state from a wire ray.  Returns false when there is nothing to traverse.
 LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	SetRay(s, ray.o[0], ray.o[1], ray.o[2], ray.d[0], ray.d[1], ray.d[2]);
@@ -403,15 +427,17 @@ LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState
 		s.cur = kNullIndex;     // empty leaf tree
 		return;
 	}
+	// s holds the world ray here (instances do not nest): keep its 1/d for the way back (Resolve), which would
+	// otherwise recompute three IEEE reciprocals inside its divergent pop loop
+	stk.stashInv(s.ix, s.iy, s.iz);
 	if (ir.y != kNullIndex) {
 		TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
 				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
 	} else if (ir.z != kNullIndex) {
-		float m[16];
-		MotionSample(sc, ir.z, s.time, m);
-		if (STATS) stats->motionSamples++;
-		TransformRayLocal(s, m, worldRay.o[0], worldRay.o[1], worldRay.o[2],
+		const Ray6 r = MotionRay(sc.motionFirst, sc.motionLast, sc.interps, ir.z, s.time, worldRay.o[0], worldRay.o[1], worldRay.o[2],
 				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+		if (STATS) stats->motionSamples++;
+		SetRay(s, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
 	}
 	s.curMeshOffset = ir.w;
 	s.curInstOrder = ir2.x;
@@ -423,7 +449,8 @@ LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState
 // Turns s.cur into a wide-node, triangle or instance reference: pops the stack while there is nothing
 // to do or the popped entry lies behind the best hit, and leaves leaf trees (sentinel).  An instance
 // reference is returned as it is (EnterInstance follows).  Returns false when the ray is finished.
-// STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n).
+// STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n) and a
+// three-float side slot stashInv(ix, iy, iz) / loadInv(ix&, iy&, iz&) (the world ray's 1/d while inside an instance).
 template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
 	uint32_t cur = s.cur;
@@ -452,8 +479,10 @@ LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, S
 		}
 		if (TWO_LEVEL) {
 			if (cur == kStackSentinel) {
-				// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283)
-				SetRay(s, worldRay.o[0], worldRay.o[1], worldRay.o[2], worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+				// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), its 1/d from the stash
+				s.ox = worldRay.o[0]; s.oy = worldRay.o[1]; s.oz = worldRay.o[2];
+				s.dx = worldRay.d[0]; s.dy = worldRay.d[1]; s.dz = worldRay.d[2];
+				stk.loadInv(s.ix, s.iy, s.iz);
 				s.inInstance = false;
 				cur = kNullIndex;
 				continue;

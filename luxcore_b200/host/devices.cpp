@@ -286,6 +286,36 @@ void CUDAIntersectionDevice::EnqueueTraceRayBuffer(HardwareDeviceBuffer *rayBuff
 	statsTotalDataParallelRayCount += rayCount;
 }
 
+static void *DevicePointerOf(HardwareDeviceBuffer *b, const char *what, const bool optional = false) {
+	if (!b && optional)
+		return nullptr;
+	CUDADeviceBuffer *cb = dynamic_cast<CUDADeviceBuffer *>(b);
+	if (!cb || cb->IsNull())
+		throw std::runtime_error(std::string("Null or foreign buffer passed as ") + what);
+	return cb->GetDevicePointer();
+}
+
+void CUDAIntersectionDevice::EnqueueTraceShadowRayBuffer(HardwareDeviceBuffer *rayBuff, HardwareDeviceBuffer *rayHitBuff, const unsigned int rayCount) {
+	if (!kernel)
+		throw std::runtime_error("EnqueueTraceShadowRayBuffer() on a device that was not started");
+	if (rayCount == 0)
+		return;
+	Check(lrb_trace_anyhit(GetNativeScene(), DevicePointerOf(rayBuff, "ray buffer"), DevicePointerOf(rayHitBuff, "ray hit buffer"), rayCount),
+			"shadow ray trace");
+	statsTotalDataParallelRayCount += rayCount;
+}
+
+unsigned int CUDAIntersectionDevice::AdvancePassThroughRayBuffer(HardwareDeviceBuffer *rayBuff, HardwareDeviceBuffer *rayHitBuff,
+		const unsigned int rayCount, HardwareDeviceBuffer *passMeshBits, const unsigned int passMeshWords, HardwareDeviceBuffer *continueFlags) {
+	if (!kernel)
+		throw std::runtime_error("AdvancePassThroughRayBuffer() on a device that was not started");
+	uint32_t n = 0;
+	Check(lrb_advance_rays(GetNativeScene(), DevicePointerOf(rayBuff, "ray buffer"), DevicePointerOf(rayHitBuff, "ray hit buffer"), rayCount,
+			(const uint32_t *)DevicePointerOf(passMeshBits, "pass-through mesh bits", true), passMeshWords,
+			(const uint8_t *)DevicePointerOf(continueFlags, "continue flags", true), &n), "pass-through advance");
+	return n;
+}
+
 bool CUDAIntersectionDevice::TraceRay(const Ray *ray, RayHit *rayHit) {
 	if (!kernel)
 		throw std::runtime_error("TraceRay() on a device that was not started");

@@ -294,6 +294,25 @@ LRH_API int lrh_trace_device(void *sp, void *raysDev, void *hitsDev, uint32_t n)
 	LRH_CATCH
 }
 
+// shadow rays on caller-owned device memory (extension, see cudaintersectiondevice.h)
+LRH_API int lrh_trace_device_shadow(void *sp, void *raysDev, void *hitsDev, uint32_t n) {
+	Session *s = (Session *)sp;
+	LRH_TRY
+	if (!s->device)
+		throw std::runtime_error("session not started");
+	HardwareDeviceBuffer *r = s->device->AdoptBuffer(raysDev, (size_t)n * sizeof(Ray));
+	HardwareDeviceBuffer *h = s->device->AdoptBuffer(hitsDev, (size_t)n * sizeof(RayHit));
+	try {
+		s->device->EnqueueTraceShadowRayBuffer(r, h, n);
+	} catch (...) {
+		delete r; delete h;
+		throw;
+	}
+	delete r;
+	delete h;
+	LRH_CATCH
+}
+
 LRH_API int lrh_finish(void *sp) {
 	Session *s = (Session *)sp;
 	LRH_TRY

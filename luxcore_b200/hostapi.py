@@ -14,14 +14,15 @@ from . import capi
 from . import scenes as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libluxrays_b200_host.so")
+# LRB_LIB_DIR: development switch -- load a differently compiled build of the two libraries (A/B of kernel variants)
+LIB_PATH = os.path.join(os.environ.get("LRB_LIB_DIR") or os.path.join(_HERE, "lib"), "libluxrays_b200_host.so")
 
 EXPORTS = [
     "lrh_last_error", "lrh_create", "lrh_destroy", "lrh_device_description_count", "lrh_add_shape", "lrh_add_plain",
     "lrh_add_instance", "lrh_add_motion", "lrh_preprocess", "lrh_build_accelerator", "lrh_bvh_node_count",
     "lrh_bvh_nodes", "lrh_mbvh_root_node_count", "lrh_mbvh_root_nodes", "lrh_mbvh_leaf_count",
     "lrh_mbvh_leaf_node_count", "lrh_mbvh_leaf_nodes", "lrh_mesh_bbox", "lrh_dataset_bounds", "lrh_start", "lrh_stop", "lrh_native_device", "lrh_native_scene",
-    "lrh_accelerator_type", "lrh_trace_host", "lrh_trace_device", "lrh_finish", "lrh_trace_ray",
+    "lrh_accelerator_type", "lrh_trace_host", "lrh_trace_device", "lrh_trace_device_shadow", "lrh_finish", "lrh_trace_ray",
     "lrh_set_instance_transform", "lrh_update", "lrh_stats_total_rays", "lrh_used_memory", "lrh_machine_epsilon",
     "lrh_matrix_inverse",
 ]
@@ -64,6 +65,7 @@ def lib():
             "lrh_accelerator_type": (i32, [vp]),
             "lrh_trace_host": (i32, [vp, vp, vp, u32, i32]),
             "lrh_trace_device": (i32, [vp, vp, vp, u32]),
+            "lrh_trace_device_shadow": (i32, [vp, vp, vp, u32]),
             "lrh_finish": (i32, [vp]),
             "lrh_trace_ray": (i32, [vp, vp, vp]),
             "lrh_set_instance_transform": (i32, [vp, i32, vp]),
@@ -244,6 +246,10 @@ class Session:
     def trace_device(self, rays_devptr, hits_devptr, n):
         """EnqueueTraceRayBuffer on caller-owned device memory (asynchronous)."""
         _check(lib().lrh_trace_device(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n))
+
+    def trace_device_shadow(self, rays_devptr, hits_devptr, n):
+        """EnqueueTraceShadowRayBuffer (any-hit) on caller-owned device memory (asynchronous)."""
+        _check(lib().lrh_trace_device_shadow(self.h, C.c_void_p(rays_devptr), C.c_void_p(hits_devptr), n))
 
     def finish(self):
         _check(lib().lrh_finish(self.h))

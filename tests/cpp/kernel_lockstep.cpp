@@ -77,7 +77,7 @@ void __syncwarp() {
 #include "trace_kernels.cuh"
 
 namespace lrb {
-uint32_t smem[kTraceBlock * 2 * 64];        // `extern __shared__ uint32_t smem[]` of the kernels: one block at a time
+uint32_t smem[kTraceBlock * (2 * 64 + 3)];        // `extern __shared__ uint32_t smem[]` of the kernels: one block at a time
 }
 
 using namespace lrb;
@@ -104,6 +104,7 @@ extern "C" {
 // Runs one block (nWarps <= 4 warps) of TracePersistent / TraceStatic over the batch.
 //   view: SceneView of a re-laid-out scene (emu_scene_view of libwide_emulation.so)
 //   kernel: 0 = TracePersistent, 1 = TraceStatic (stats6 receives its counters when non-null)
+//   prefetch: bit 0 = the prefetching twin, bit 1 = the any-hit (shadow ray) kernels
 int ks_trace_signal(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, lrb_rayhit *hitsPeer, uint32_t n, int nWarps,
 		uint32_t smemDepth, uint32_t stackNeed, uint32_t chunkShift, uint32_t epoch, uint32_t *chunkFlags, uint32_t *flagOrderOk);
 
@@ -137,6 +138,22 @@ int ks_trace(const SceneView *view, const lrb_ray *rays, lrb_rayhit *hits, uint3
 	a.stats = &st;
 	const bool two = view->twoLevel != 0;
 	const bool spill = stackNeed > smemDepth;
+	const bool anyhit = (prefetch & 2) != 0;
+	prefetch &= 1;
+	if (anyhit) {
+		if (kernel == 0) {
+			if (two) {
+				if (spill) RunBlock(TracePersistent<true, true, false, false, true>, a, nWarps);
+				else RunBlock(TracePersistent<true, false, false, false, true>, a, nWarps);
+			} else if (spill) RunBlock(TracePersistent<false, true, false, false, true>, a, nWarps);
+			else RunBlock(TracePersistent<false, false, false, false, true>, a, nWarps);
+		} else {
+			if (nWarps != 4) return 2;
+			if (two) RunBlock(TraceStatic<true, false, true>, a, 4);
+			else RunBlock(TraceStatic<false, false, true>, a, 4);
+		}
+		return 0;
+	}
 	if (kernel == 0) {
 		if (two) {
 			if (spill) RunBlock(TracePersistent<true, true, false>, a, nWarps);

@@ -27,6 +27,9 @@ struct HostStack {
 	void pop(uint32_t &a, float &b) { a = n.back(); b = t.back(); n.pop_back(); t.pop_back(); }
 	bool empty() const { return n.empty(); }
 	unsigned long long depth() const { return n.size(); }
+	float inv[3] = { 0.f, 0.f, 0.f };
+	void stashInv(float x, float y, float z) { inv[0] = x; inv[1] = y; inv[2] = z; }
+	void loadInv(float &x, float &y, float &z) const { x = inv[0]; y = inv[1]; z = inv[2]; }
 };
 
 static std::string g_err;

@@ -324,7 +324,7 @@ class Lockstep:
 
     @classmethod
     def trace(cls, emu, rays, kernel="persistent", n_warps=1, smem_depth=16, refill_below=24, tri_bias=8, inst_bias=8,
-              prefetch=False, hits=None, want_stats=False):
+              prefetch=False, hits=None, want_stats=False, anyhit=False):
         """-> hits (and TraceStatic's counters with want_stats).  `hits` pre-loads the RayHit buffer (masked rays)."""
         rays = np.ascontiguousarray(rays)
         out = np.zeros(rays.shape[0], dtype=HIT_DTYPE) if hits is None else np.ascontiguousarray(hits).copy()
@@ -333,7 +333,7 @@ class Lockstep:
         E.emu_scene_view(emu.h, view)
         st = np.zeros(6, dtype=np.uint64)
         rc = cls.lib().ks_trace(view, rays.ctypes.data, out.ctypes.data, rays.shape[0], 0 if kernel == "persistent" else 1, n_warps,
-                                smem_depth, emu.info()["stack_need"], refill_below, tri_bias, inst_bias, 1 if prefetch else 0, st.ctypes.data)
+                                smem_depth, emu.info()["stack_need"], refill_below, tri_bias, inst_bias, (1 if prefetch else 0) | (2 if anyhit else 0), st.ctypes.data)
         if rc != 0:
             raise RuntimeError("ks_trace failed: %d" % rc)
         if want_stats:
@@ -355,6 +355,44 @@ def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8):
     return hits, dict(zip(WARP_SIM_FIELDS, [int(x) for x in out]))
 
 
+def triangle_intersect_np(rays, p0, e1, e2):
+    """Triangle::Intersect (include/luxrays/core/geometry/triangle.h:55-89) for ray i against triangle i, in
+    float32 numpy arithmetic (every operation rounded to float32, none fused: the reference's own floats).
+    p0 / e1 / e2: [n,3] float32 (e1 = p1 - p0, e2 = p2 - p0 as float32 differences).  -> (hit, t, b1, b2)."""
+    f = np.float32
+    o, d = np.asarray(rays["o"], f), np.asarray(rays["d"], f)
+    p0 = np.asarray(p0, f); e1 = np.asarray(e1, f); e2 = np.asarray(e2, f)
+
+    def cross(a, b):
+        return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2], a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], 1)
+
+    def dot(a, b):
+        return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+
+    with np.errstate(all="ignore"):
+        s1 = cross(d, e2)
+        div = dot(s1, e1)
+        inv = f(1.0) / div
+        dd = o - p0
+        b1 = dot(dd, s1) * inv
+        s2 = cross(dd, e1)
+        b2 = dot(d, s2) * inv
+        b0 = (f(1.0) - b1) - b2
+        t = dot(e2, s2) * inv
+        mint = np.where(np.isnan(rays["mint"]), f(-np.inf), rays["mint"]).astype(f)
+        hit = (div != 0) & ~(b1 < 0) & ~(b2 < 0) & ~(b0 < 0) & ~(t < mint) & ~(t > rays["maxt"])
+    return hit, t.astype(f), b1.astype(f), b2.astype(f)
+
+
+def machine_epsilon_np(v):
+    """MachineEpsilon::E(float) (include/luxrays/core/epsilon.h:48-53,75-82) on a float32 array."""
+    v = np.asarray(v, np.float32)
+    with np.errstate(all="ignore"):
+        nxt = (v.view(np.uint32) + np.uint32(0x80)).view(np.float32)
+        e = np.abs(nxt - v)
+    return np.where(e < np.float32(1e-5), np.float32(1e-5), np.where(e > np.float32(1e-1), np.float32(1e-1), e)).astype(np.float32)
+
+
 def reference_scene(desc):
     """SceneDesc -> the REFERENCE's own mesh objects (oracle/_ref, oracle/refapi.py), same dataset order."""
     from oracle import refapi as RF
@@ -369,3 +407,22 @@ def reference_scene(desc):
         else:
             sc.add_motion(m.shape, m.times, m.motion_xforms)
     return sc
+
+
+def check_anyhit(got, closest, rays, desc=None, what=""):
+    """Contract of lrb_trace_anyhit: hit / miss identical to the closest-hit answer; a miss carries the closest-hit
+    miss payload; a hit names a triangle the ray really hits inside [mint, maxt] at exactly the reported t / b1 / b2
+    (checked with the reference's own arithmetic when `desc` is a one-level scene), never closer than the closest hit."""
+    miss_g, miss_c = got["meshIndex"] == NULL, closest["meshIndex"] == NULL
+    assert (miss_g == miss_c).all(), "%s: any-hit hit/miss differs from closest-hit on %d rays" % (what, int((miss_g != miss_c).sum()))
+    assert got[miss_g].tobytes() == closest[miss_c].tobytes(), "%s: miss payload" % what
+    h = ~miss_g
+    assert (got["t"][h] >= closest["t"][h]).all(), "%s: any-hit closer than the closest hit" % what
+    if desc is not None and h.any():
+        p0, e1, e2, offs = S.world_triangles(desc)
+        flat = offs[got["meshIndex"][h].astype(np.int64)] + got["triangleIndex"][h].astype(np.int64)
+        ok, t, b1, b2 = triangle_intersect_np(rays[h], p0[flat], e1[flat], e2[flat])
+        assert ok.all(), "%s: %d any-hit records name a triangle the ray does not hit" % (what, int((~ok).sum()))
+        assert (t.view(np.uint32) == got["t"][h].view(np.uint32)).all() and (b1.view(np.uint32) == got["b1"][h].view(np.uint32)).all() \
+            and (b2.view(np.uint32) == got["b2"][h].view(np.uint32)).all(), "%s: any-hit t / b1 / b2 not bit-exact" % what
+    return {"rays": int(got.shape[0]), "hits": int(h.sum()), "same_as_closest": int((got[h] == closest[h]).sum())}

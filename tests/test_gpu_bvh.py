@@ -79,13 +79,17 @@ def test_masked_rays_leave_hits_untouched(dev):
     scene.free()
 
 
+@pytest.mark.parametrize("kernel", ["persistent", "simple"])
 @pytest.mark.parametrize("chunks", [0, -1, 1, 5])
-@pytest.mark.parametrize("n", [1000, 32768 * 3 + 1234, 500000])
-def test_trace_gather_pushes_every_hit(dev, chunks, n):
+@pytest.mark.parametrize("n", [1, 128, 129, 1000, 32768 * 3 + 1234, 500000])
+def test_trace_gather_pushes_every_hit(dev, chunks, n, kernel):
     """lrb_trace_gather: chunks == 0 -> one kernel + copy-engine pushes triggered by the kernel's
     chunk-completion flags (here with 16 Ki-ray chunks so that several are in flight); chunks == -1 ->
     one kernel with dual-destination RayHit stores; chunks >= 1 -> chunked launches + copy engine.
     The gather slice must end up byte-identical to the local RayHit buffer, masked rays' records included."""
+    if kernel == "simple" and n > 1000 and chunks != 0:
+        pytest.skip("the static kernel's gather path is covered by the small batches")
+    dev.set_option("kernel", kernel)
     dev.set_option("gather_stores", "1" if chunks < 0 else "0")
     dev.set_option("gather_chunk_shift", "14")
     chunks = max(chunks, 0)
@@ -94,8 +98,8 @@ def test_trace_gather_pushes_every_hit(dev, chunks, n):
     bvh = O.BVH(osc)
     verts, offs = H.flattened_from_oracle(desc, osc)
     scene = dev.upload_bvh(bvh.nodes(), verts, offs)
-    rays = _rays_for(desc, n, seed=33)[:n]
-    mask = np.random.default_rng(1).random(n) < 0.1
+    rays = _rays_for(desc, max(n, 1000), seed=33)[:n]
+    mask = np.random.default_rng(1).random(n) < (0.1 if n > 1 else 0.0)
     rays["flags"][mask] = capi.RAY_FLAGS_MASKED
     d_rays = dev.alloc(n * 48)
     d_hits = dev.alloc(n * 20)
@@ -120,6 +124,25 @@ def test_trace_gather_pushes_every_hit(dev, chunks, n):
     scene.free()
     dev.set_option("gather_stores", "0")
     dev.set_option("gather_chunk_shift", "19")
+    dev.set_option("kernel", "persistent")
+
+
+def test_trace_host_without_hit_buffer_zeroes_masked_records(dev):
+    """Scene.trace_host(rays) with no caller buffer: the records of masked rays read back as zeros, never as
+    what an earlier trace left in the staging buffer."""
+    desc = S.load_fixture("cornell")
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    scene = dev.upload_bvh(bvh.nodes(), verts, offs)
+    rays = _rays_for(desc, 20000, seed=5)
+    scene.trace_host(rays)                      # fills the staging buffer with real hits
+    mask = np.random.default_rng(2).random(rays.shape[0]) < 0.5
+    rays["flags"][mask] = capi.RAY_FLAGS_MASKED
+    hits = scene.trace_host(rays)
+    assert (hits.view(np.uint8).reshape(-1, 20)[mask] == 0).all()
+    H.compare_hits(hits[~mask], bvh.intersect(rays)[~mask], rays[~mask], what="trace_host/no buffer")
+    scene.free()
 
 
 @pytest.mark.parametrize("name,n,bits", [("kitchen", 600000, 5), ("cornell", 300000, 3), ("bigmonkey", 400000, 9)])

@@ -157,3 +157,33 @@ def test_non_finite_rays_stay_within_the_stack_bound(tree_type):
     for depth in (1, 16):
         assert H.Lockstep.trace(emu, rays, smem_depth=depth, n_warps=2).tobytes() == got.tobytes()
     assert H.Lockstep.trace(emu, rays, kernel="static", n_warps=4).tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n_warps=4, smem_depth=4), dict(kernel="static", n_warps=4)],
+                         ids=lambda kw: ",".join("%s=%s" % kv for kv in kw.items()) or "default")
+def test_anyhit_kernels_in_lockstep(kitchen, kw):
+    """Shadow-ray kernels (ANYHIT): same hit / miss as the closest-hit traversal, every reported hit is a real one
+    (the reference's own triangle arithmetic, bit for bit), masked rays untouched."""
+    emu, rays = kitchen
+    desc = S.load_fixture("kitchen")
+    pre = _preloaded(rays.shape[0], 5)
+    got = H.Lockstep.trace(emu, rays, hits=pre, anyhit=True, **kw)
+    masked = (rays["flags"] & 1) != 0
+    assert got[masked].tobytes() == pre[masked].tobytes()
+    rep = H.check_anyhit(got[~masked], emu.trace(rays)[~masked], rays[~masked], desc, what="lockstep any-hit")
+    assert rep["hits"] > 500
+
+
+def test_anyhit_two_level_in_lockstep():
+    desc = Z.instances_scene()
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc, tree_type=4)
+    emu = H.Emu.mbvh(H.mbvh_arrays(desc, mb))
+    lo, hi = desc.bbox()
+    rays = np.concatenate([R.to_numpy_rays(R.uniform_rays(lo - 0.2, hi + 0.2, 1500, seed=5)),
+                           R.to_numpy_rays(R.camera_rays(desc.cam, 36, 36, seed=6))])
+    want = emu.trace(rays)
+    for kw in (dict(), dict(inst_bias=0, n_warps=4), dict(kernel="static", n_warps=4)):
+        got = H.Lockstep.trace(emu, rays, anyhit=True, **kw)
+        rep = H.check_anyhit(got, want, rays, None, what="lockstep any-hit two-level %s" % kw)
+        assert rep["hits"] > 100

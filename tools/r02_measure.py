@@ -21,14 +21,21 @@ ap.add_argument("section")
 ap.add_argument("--rays", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--no-parity", action="store_true")
+ap.add_argument("--quick", action="store_true", help="default options only (A/B of differently compiled libraries, LRB_LIB_DIR)")
+ap.add_argument("--opt", action="append", default=[], help="device option key=value applied to every variant")
+ap.add_argument("--tag", default="")
 ARGS = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 rows = []
-DEFAULTS = {"smem_depth": 16, "refill_below": 24, "tri_bias": 8, "inst_bias": 8, "sort_rays": 2, "prefetch": 0,
+DEFAULTS0 = {"smem_depth": 16, "refill_below": 24, "tri_bias": 8, "inst_bias": 8, "sort_rays": 2, "prefetch": 0,
             "blocks_per_sm": 0, "carveout": -1, "sort_bits": 5, "kernel": "persistent"}
+DEFAULTS = dict(DEFAULTS0)
+for kv in ARGS.opt:
+    k, v = kv.split("=", 1)
+    DEFAULTS[k] = v
 
 
 def emit(row):
@@ -58,6 +65,8 @@ def sweep(sess, name, kind, rays, variants, orc=None, sample=50000):
     base = {"scene": name, "rays": kind, "n": m, "nodes_per_ray": round(st.wide_nodes / max(1, st.rays), 2),
             "tris_per_ray": round(st.triangles / max(1, st.rays), 2), "instances_per_ray": round(st.instances / max(1, st.rays), 3),
             "max_stack": int(st.max_stack)}
+    if ARGS.quick:
+        variants = variants[:1]
     for label, opts in variants:
         full = dict(DEFAULTS); full.update(opts)
         try:
@@ -119,6 +128,9 @@ def section_kitchen():
         n = ARGS.rays or (16 << 20)
         rays = B.make_bounce_batch(trace_fn_of(sess), desc, n, seed=2, device=dev, depth=2)
         orc = O.BVH(H.oracle_scene(desc), nodes=sess.bvh_nodes())
+        if ARGS.quick and name != "kitchen":
+            sess.stop(); sess.close()
+            continue
         if name == "kitchen":
             v = [("default", {})]
             v += [("smem_depth=%d" % d, {"smem_depth": d}) for d in (8, 12, 24)]
@@ -139,6 +151,8 @@ def section_kitchen():
 def section_mbvh():
     for name, kinds, tr in (("lightinstances", ["camera", "bounce-1"], None), ("bigmonkey-instances", ["bounce-1"], None),
                             ("bigmonkey-motion", ["camera"], (0.0, 1.0))):
+        if ARGS.quick and name != "lightinstances":
+            continue
         desc = S.load_fixture(name)
         sess = open_session(desc, "MBVH")
         orc = O.MBVH(H.oracle_scene(desc))
@@ -160,7 +174,7 @@ def section_mbvh():
             sweep(sess, name, kind, rays, v, orc, sample=30000)
             del rays
         # Update() cost: move every instance a little, time the host-side refit + re-layout + upload
-        if name == "lightinstances":
+        if name == "lightinstances" and not ARGS.quick:
             inst = [i for i, m in enumerate(desc.meshes) if m.kind == S.INSTANCE]
             t0 = time.perf_counter()
             for i in inst:
@@ -208,8 +222,68 @@ def section_soup(n_tris):
     sess.stop(); sess.close()
 
 
+def section_masked():
+    """f1: dead lanes between bounces -- masked rays skipped inside the trace kernel vs compacted before it, and
+    f3: shadow rays through the any-hit kernels vs the closest-hit kernels on the same batch."""
+    desc = S.load_fixture("kitchen")
+    sess = open_session(desc, "BVH")
+    scene = sess.native_scene()
+    n = ARGS.rays or (16 << 20)
+    rays = B.make_bounce_batch(trace_fn_of(sess), desc, n, seed=2, device=dev, depth=2)
+    hits = torch.empty((n, 20), dtype=torch.uint8, device=dev)
+    flags = rays.view(torch.int32)[:, 9]
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    u = torch.rand(n, generator=g, device=dev)
+    for frac in (0.0, 0.3, 0.5, 0.7, 0.9):
+        flags.copy_((u < frac).to(torch.int32))
+        row = {"scene": "kitchen", "rays": "bounce-2", "n": n, "masked_fraction": frac}
+        ref = None
+        for label, opt in (("skip_in_kernel", 0), ("compacted", 1)):
+            sess.set_option("compact", opt)
+            hits.zero_()
+            med, best = time_trace(sess, rays, hits, ARGS.reps)
+            row[label + "_ms"] = round(med, 4)
+            row[label + "_live_mrays_per_s"] = round(n * (1.0 - frac) / med / 1e3, 1)
+            if ref is None:
+                ref = hits.clone()
+            else:
+                row["identical"] = bool(torch.equal(ref, hits))
+        sess.set_option("compact", 0)
+        emit(row)
+    flags.zero_()
+    # shadow rays: from the surface points of the bounce batch towards uniform points of the scene box (d = target - o,
+    # maxt = 1 - 1e-4: the segment up to the target, the way the reference builds its shadow rays)
+    lo, hi = desc.bbox()
+    lo_t, hi_t = torch.from_numpy(lo).to(dev), torch.from_numpy(hi).to(dev)
+    rf = rays.view(torch.float32).clone()
+    target = lo_t + (hi_t - lo_t) * torch.rand((n, 3), generator=g, device=dev)
+    rf[:, 3:6] = target - rf[:, 0:3]
+    rf[:, 7] = 1.0 - 1e-4
+    shadow = rf.view(torch.uint8).reshape(n, 48).contiguous()
+    def run(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ARGS.reps)]
+        for a, b in ev:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+    for label, batch in (("bounce-2 (infinite maxt)", rays), ("shadow segments", shadow)):
+        h1 = torch.empty((n, 20), dtype=torch.uint8, device=dev); h2 = torch.empty((n, 20), dtype=torch.uint8, device=dev)
+        ms_c = run(lambda: scene.trace(batch.data_ptr(), h1.data_ptr(), n))
+        ms_a = run(lambda: scene.trace_anyhit(batch.data_ptr(), h2.data_ptr(), n))
+        m1 = h1.view(torch.int32)[:, 3] == -1; m2 = h2.view(torch.int32)[:, 3] == -1
+        emit({"scene": "kitchen", "rays": label, "n": n, "closest_ms": round(ms_c, 4), "closest_mrays_per_s": round(n / ms_c / 1e3, 1),
+              "anyhit_ms": round(ms_a, 4), "anyhit_mrays_per_s": round(n / ms_a / 1e3, 1), "hit_fraction": round(1.0 - float(m1.float().mean()), 4),
+              "hit_miss_identical": bool(torch.equal(m1, m2))})
+    sess.stop(); sess.close()
+
+
 sec = ARGS.section
-if sec == "kitchen":
+if sec == "masked":
+    section_masked()
+elif sec == "kitchen":
     section_kitchen()
 elif sec == "mbvh":
     section_mbvh()
@@ -218,4 +292,4 @@ elif sec.startswith("soup"):
 else:
     raise SystemExit("unknown section")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "r02_measure_%s.json" % sec.replace(":", "_")), "w"), indent=1)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "r02_measure_%s%s.json" % (sec.replace(":", "_"), ARGS.tag)), "w"), indent=1)
