@@ -10,9 +10,11 @@ accelerator built by the product's host layer with the reference's defaults (bui
 EMBREE_BINNED_SAH -> this tree's binned-SAH builder, 4-ary, one triangle per leaf), and batches of
 16 Mi INCOHERENT rays: second-bounce diffuse path rays generated on the GPU the way the reference's
 path tracer emits them (camera ray -> hit -> cosine-weighted bounce -> hit -> bounce).
-One step = one EnqueueTraceRayBuffer over one batch per GPU (weak scaling: every rank owns a 16 Mi
-batch of its own seed; the BVH is replicated); with N > 1 the step also gathers the RayHit buffers
-onto rank 0 (the only exchange the path has).
+One step = one EnqueueTraceRayBuffer over one batch per GPU (weak scaling, the default: every rank owns a
+16 Mi batch of its own seed; `--scaling strong`: ONE 16 Mi batch cut into the contiguous per-rank slices of
+SURVEY.md 8e; the BVH is replicated); with N > 1 the step also gathers the RayHit buffers onto rank 0 (the only
+exchange the path has).  `--scene soup` is BASELINE.json configs[4] (50 M-triangle soup, HBM-resident),
+`--scene lightinstances --accel MBVH --depth 1 --rays 4194304` configs[2] (two-level traversal).
 
 The JSON line follows the driver contract; see DESIGN.md "Measurement" for every field.
 """
@@ -50,17 +52,13 @@ def read_peaks():
 
 
 def read_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the traversal kernel on this workload,
-    from the committed `ncu --set full` capture (profiles/traffic.json); None if no capture matches."""
+    """Per-launch counters of the traversal kernel on this workload from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_roofline.py); None if no capture matches."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)
-        e = t.get(workload)
-        if e:
-            return float(e["dram_bytes_per_launch"]), e.get("source")
+            return json.load(f).get(workload)
     except Exception:
-        pass
-    return None, None
+        return None
 
 
 class ClockSampler:
@@ -178,27 +176,38 @@ def make_bounce_batch(trace_fn, desc, n_rays, seed, device, depth=2):
     return rays
 
 
-def oracle_for(desc, nodes):
+def oracle_for(desc, nodes, accel="BVH"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
     from oracle import oracle as O
     osc = H.oracle_scene(desc)
+    if accel == "MBVH":
+        return O, O.MBVH(osc)      # the oracle's own (CLASSIC) trees: closest-hit results do not depend on the topology
     return O, O.BVH(osc, nodes=nodes)
 
 
-def reference_for(desc, nodes):
-    """The reference's own BVHAccel (oracle/_ref: its C++ sources compiled from /root/reference) walking the
-    same BVHArrayNode array, or None where the prebuilt library is absent (then the oracle port is used)."""
+def reference_for(desc, nodes, accel="BVH"):
+    """The reference's own BVHAccel / MBVHAccel (oracle/_ref: its C++ sources compiled from /root/reference) --
+    BVH: walking the same BVHArrayNode array; MBVH: its own CLASSIC-built trees -- or None where the prebuilt
+    library is absent (then the oracle port is used)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     try:
         import helpers as H
         from oracle import refapi as RF
         if not RF.available():
             return None
+        if accel == "MBVH":
+            return RF.MBVH(H.reference_scene(desc))
         return RF.BVH(H.reference_scene(desc), nodes=nodes)
     except Exception as e:      # a broken checker must not take the benchmark down
         log("reference library unavailable:", repr(e))
         return None
+
+
+def embree_status():
+    """the Embree CPU baseline is only timed where libembree3 exists on the box."""
+    import ctypes.util
+    return "available" if ctypes.util.find_library("embree3") else "unavailable (no libembree3 on this box; the CPU arm is the reference's native BVH/MBVH Intersect)"
 
 
 def cpu_time_sample(O, bvh, rays_np, target_s, threads):
@@ -211,6 +220,10 @@ def cpu_time_sample(O, bvh, rays_np, target_s, threads):
     return n, dt
 
 
+def accel_config(args):
+    return {"accelerator.type": args.accel, "accelerator.bvh.builder.type": args.builder, "accelerator.bvh.treetype": 4}
+
+
 # ---------------------------------------------------------------------------------------------
 
 def main():
@@ -220,11 +233,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="kitchen")
-    ap.add_argument("--rays", type=int, default=RAYS_PER_BATCH, help="rays per batch per GPU")
+    ap.add_argument("--accel", default="BVH", choices=["BVH", "MBVH"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_BATCH, help="rays per batch per GPU (weak) / per batch (strong)")
     ap.add_argument("--depth", type=int, default=2, help="bounce depth of the ray batch")
     ap.add_argument("--builder", default="EMBREE_BINNED_SAH")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "direct", "none"])
     ap.add_argument("--chunks", type=int, default=0, help="0 = fused in-kernel push; >= 1 = launches per batch for the copy-engine push")
+    ap.add_argument("--no-pipeline", action="store_true", help="p2p gather: every step waits for its own pushes and completion signal "
+                    "(default: the tail of step k's pushes and its signal overlap the trace of step k + 1; two RayHit buffers)")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: CUDA-event breakdown of un-pipelined steps per rank (kernel / tail of the pushes / signal)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="device option key=value")
@@ -234,21 +252,25 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = args.gpus
+    strong = args.scaling == "strong" and world > 1
     kind = "uniform" if is_soup(args.scene) else "bounce%d" % args.depth
     workload = "%s-%dM-%s" % (args.scene, args.rays >> 20, kind) if args.rays >= (1 << 20) else "%s-%d-%s" % (args.scene, args.rays, kind)
     config = {"workload": workload,
               "scene": ("synthetic random triangle soup, seed 4 (BASELINE.json configs[4])" if is_soup(args.scene)
                         else "scenes/%s (fixture tests/golden/scenes/%s.npz)" % (args.scene, args.scene)),
-              "accelerator": "BVH", "builder": args.builder, "treetype": 4, "rays_per_batch_per_gpu": args.rays,
+              "accelerator": args.accel, "builder": args.builder, "treetype": 4,
+              "rays_per_batch_per_gpu": args.rays if not strong else None, "rays_per_batch_total": args.rays if strong else args.rays * max(1, n_gpus),
               "ray_kind": ("incoherent: origins uniform in the unit cube, directions uniform on the sphere" if is_soup(args.scene)
                            else "incoherent diffuse bounce, path depth %d" % args.depth),
-              "parallelism": "replicated BVH, one %d-ray batch per GPU x%d, RayHit gathered on rank 0 (%s)" % (args.rays, n_gpus, args.gather if n_gpus > 1 else "n/a"),
+              "parallelism": ("replicated BVH, ONE %d-ray batch cut into %d contiguous slices, RayHit gathered on rank 0 (%s)" % (args.rays, n_gpus, args.gather)
+                              if strong else
+                              "replicated BVH, one %d-ray batch per GPU x%d, RayHit gathered on rank 0 (%s)" % (args.rays, n_gpus, args.gather if n_gpus > 1 else "n/a")),
               "l2_policy": "inputs larger than L2 (48 B x rays + 20 B x rays per step >> 126 MB)"}
 
     if args.impl == "reference":
         return run_reference(args, rank, world, config)
 
-    from luxcore_b200 import capi, hostapi, rays as R
+    from luxcore_b200 import capi, hostapi, rays as R, shard
 
     if world > 1:
         import torch.distributed as dist
@@ -260,10 +282,12 @@ def main():
 
     desc = build_scene_arrays(args.scene)
     t0 = time.perf_counter()
-    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": args.builder, "accelerator.bvh.treetype": 4}, desc)
-    sess.build_accelerator("BVH")
+    sess = hostapi.Session(accel_config(args), desc)
+    sess.build_accelerator(args.accel)
     build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
     sess.start(local_rank)
+    upload_s = time.perf_counter() - t0         # host-side re-layout (relayout.cpp) + H2D of the scene
     sess.set_stream(stream.cuda_stream)
     for kv in args.opt:
         k, v = kv.split("=", 1)
@@ -276,53 +300,97 @@ def main():
         sess.trace_device(rays_u8.data_ptr(), hits.data_ptr(), rays_u8.shape[0])
         return hits
 
-    n = args.rays
-    rays = make_batch(trace_fn, desc, args, n, seed=2 + rank, device=device)
+    if strong:
+        # ONE batch (the rank-0 batch of the weak run), every rank regenerates it and keeps its slice [g N/G, (g+1) N/G)
+        full = make_batch(trace_fn, desc, args, args.rays, seed=2, device=device)
+        first, n = shard.rank_slice(args.rays, world, rank)
+        rays = full[first:first + n].clone()
+        del full
+        counts = [shard.rank_slice(args.rays, world, r)[1] for r in range(world)]
+    else:
+        n = args.rays
+        rays = make_batch(trace_fn, desc, args, n, seed=2 + rank, device=device)
+        counts = [n] * world
+    offsets = [sum(counts[:r]) for r in range(world)]
+    total_rays = sum(counts)
     torch.cuda.synchronize()
     hits = torch.empty((n, 20), dtype=torch.uint8, device=device)
 
     # ---- multi-GPU: RayHit gather onto rank 0 ----
-    #   p2p  : rank 0 owns the gather buffer; the other ranks map it over NVLink (CUDA IPC) and
-    #          lrb_trace_gather pushes each traced chunk into it while the next chunk is traced
+    #   p2p  : rank 0 owns the gather buffer; the other ranks map it over NVLink (CUDA IPC) and lrb_trace_gather
+    #          pushes each finished chunk into it with the copy engine while the kernel keeps tracing.  Pipelined
+    #          (default): the pushes of step k and its completion signal are not waited for before step k + 1 traces.
     #   nccl : trace, then torch.distributed gather (the baseline way)
-    from luxcore_b200 import shard
     dev_view = capi.Device.borrow(sess.native_device())
     gather_mode = args.gather if world > 1 else "none"
-    gbuf_local, gbuf_peer, my_dst, glist = 0, 0, 0, None
+    pipeline = gather_mode == "p2p" and args.chunks == 0 and not args.no_pipeline
+    n_buf = 2 if pipeline else 1
+    gbuf_local, gbuf_peer, my_dst, glist = [], [], [], None
+    hits_buf = [hits] + ([torch.empty((n, 20), dtype=torch.uint8, device=device)] if pipeline else [])
+    side = torch.cuda.Stream(device=device) if pipeline else None
     if gather_mode in ("p2p", "direct"):
         import torch.distributed as dist
         if rank == 0:
-            gbuf_local = dev_view.alloc(world * n * 20)
-            handle = [dev_view.ipc_get_handle(gbuf_local)]
+            gbuf_local = [dev_view.alloc(total_rays * 20) for _ in range(n_buf)]
+            handle = [[dev_view.ipc_get_handle(p) for p in gbuf_local]]
         else:
             handle = [None]
         dist.broadcast_object_list(handle, src=0)
         if rank == 0:
-            my_dst = gbuf_local
+            my_dst = list(gbuf_local)
         else:
-            gbuf_peer = dev_view.ipc_open_handle(handle[0])
-            my_dst = gbuf_peer + rank * n * 20
+            gbuf_peer = [dev_view.ipc_open_handle(h) for h in handle[0]]
+            my_dst = [p + offsets[rank] * 20 for p in gbuf_peer]
         flag = torch.zeros(1, dtype=torch.int32, device=device)
+        if pipeline:
+            sess.set_option("gather_defer", 1)
     elif gather_mode == "nccl":
-        gathered = torch.empty((world * n, 20), dtype=torch.uint8, device=device) if rank == 0 else None
-        glist = [gathered[i * n:(i + 1) * n] for i in range(world)] if rank == 0 else None
+        gathered = torch.empty((total_rays, 20), dtype=torch.uint8, device=device) if rank == 0 else None
+        glist = [gathered[offsets[i]:offsets[i] + counts[i]] for i in range(world)] if rank == 0 else None
+
+    pending = []        # async completion signals of the pipelined gather
+    step_no = [0]
 
     def step():
+        k = step_no[0]
+        step_no[0] += 1
         if gather_mode == "direct":
             import torch.distributed as dist
             # every rank's tracer lanes store their RayHit records straight into rank 0's buffer (NVLink stores)
-            sess.trace_device(rays.data_ptr(), my_dst, n)
+            sess.trace_device(rays.data_ptr(), my_dst[0], n)
             dist.all_reduce(flag)
         elif gather_mode == "p2p":
             import torch.distributed as dist
+            b = k % n_buf
             # rank 0 traces straight into its slice of the gather buffer (no copy at all)
-            scene.trace_gather(rays.data_ptr(), my_dst if rank == 0 else hits.data_ptr(), n, my_dst, args.chunks)
-            dist.all_reduce(flag)           # 4-byte "batch complete" signal, ordered after the pushes
+            scene.trace_gather(rays.data_ptr(), my_dst[b] if rank == 0 else hits_buf[b].data_ptr(), n, my_dst[b], args.chunks)
+            if not pipeline:
+                dist.all_reduce(flag)           # 4-byte "batch complete" signal, ordered after the pushes
+            else:
+                # the signal of step k rides on a side stream behind this step's kernel and pushes; the queue goes on
+                done = torch.cuda.Event()
+                done.record(stream)
+                side.wait_event(done)
+                dev_view.gather_wait(side.cuda_stream, 0)
+                with torch.cuda.stream(side):
+                    pending.append(dist.all_reduce(flag, async_op=True))
         else:
             sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
             if gather_mode == "nccl":
                 import torch.distributed as dist
-                dist.gather(hits, glist, dst=0)
+                if len(set(counts)) == 1:
+                    dist.gather(hits, glist, dst=0)
+                else:
+                    shard.gather_hits(hits, dst=0, counts=counts)
+
+    def drain():
+        """Everything the steps left in flight joins the queue (inside the timed region)."""
+        if pipeline:
+            dev_view.gather_wait(0, -1)
+            for w in pending:
+                w.wait()
+            del pending[:]
+            stream.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -335,6 +403,7 @@ def main():
         sampler.start()         # started before the warm-up so that nvidia-smi is already streaming samples
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
 
     # ---- timed region: device-resident inputs ----
@@ -345,6 +414,7 @@ def main():
     e_start.record()
     for i in range(args.steps):
         step()
+    drain()
     e_stop.record()
     barrier()
     t_end = time.time()
@@ -352,8 +422,9 @@ def main():
     c1 = sess.counters()
     total_ms = shard.max_over_ranks(e_start.elapsed_time(e_stop), device)
     ms_per_step = total_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e6
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
     launches = int(shard.sum_over_ranks(c1.trace_launches - c0.trace_launches, device)) if world > 1 else int(c1.trace_launches - c0.trace_launches)
+    last_buf = (step_no[0] - 1) % n_buf
 
     # kernel-only time of one whole-batch launch (roofline numerator), measured live with CUDA events
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
@@ -364,17 +435,50 @@ def main():
     torch.cuda.synchronize()
     kern_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in kev]))
 
+    # ---- N > 1: where a step's time goes (CUDA events, un-pipelined steps; not part of the timed region) ----
+    timeline = None
+    if args.timeline and gather_mode == "p2p" and args.chunks == 0:
+        import torch.distributed as dist
+        sess.set_option("gather_defer", 1)
+        rows = []
+        for it in range(6):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            barrier()
+            ev[0].record()
+            scene.trace_gather(rays.data_ptr(), my_dst[0] if rank == 0 else hits_buf[0].data_ptr(), n, my_dst[0], 0)
+            ev[1].record()                      # the kernel (and the flag memset behind it) has finished
+            dev_view.gather_wait(0, -1)
+            ev[2].record()                      # ... and so have this rank's pushes
+            dist.all_reduce(flag)
+            ev[3].record()                      # ... and every rank's (completion signal)
+            torch.cuda.synchronize()
+            if it:
+                rows.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        med = [float(np.median([r[i] for r in rows])) for i in range(3)]
+        allr = [None] * world
+        dist.all_gather_object(allr, med)
+        timeline = {"what": "median over 5 un-pipelined steps, per rank: ms of [trace kernel incl. in-flight pushes, tail of the pushes after the kernel, completion all-reduce incl. waiting for the slowest rank]",
+                    "per_rank_ms": [[round(x, 4) for x in r] for r in allr], "kernel_alone_ms_rank0": round(kern_ms, 4)}
+        if not pipeline:
+            sess.set_option("gather_defer", 0)
+
     # ---- gather verification (not timed): rank 0's buffer == every rank's local hits ----
     gather_ok = None
     if gather_mode in ("p2p", "nccl", "direct"):
         import torch.distributed as dist
+        if gather_mode == "p2p":
+            # one more gathered step into buffer 0, waited for, so that the check sees a complete, known state
+            scene.trace_gather(rays.data_ptr(), my_dst[0] if rank == 0 else hits_buf[0].data_ptr(), n, my_dst[0], args.chunks)
+            dev_view.gather_wait(0, -1)
+            torch.cuda.synchronize()
+            dist.barrier()
         sess.trace_device(rays.data_ptr(), hits.data_ptr(), n)
         torch.cuda.synchronize()
-        ref_all = shard.gather_hits(hits, dst=0, counts=[n] * world)
+        ref_all = shard.gather_hits(hits, dst=0, counts=counts)
         if rank == 0:
             if gather_mode in ("p2p", "direct"):
-                got = np.empty(world * n * 20, dtype=np.uint8)
-                dev_view.d2h(got, gbuf_local, blocking=True)
+                got = np.empty(total_rays * 20, dtype=np.uint8)
+                dev_view.d2h(got, gbuf_local[0], blocking=True)
                 gather_ok = bool(got.tobytes() == ref_all.cpu().numpy().tobytes())
             else:
                 gather_ok = bool(torch.equal(gathered, ref_all))
@@ -399,93 +503,158 @@ def main():
         t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * n / e2e_s / 1e6
+    e2e_value = total_rays / e2e_s / 1e6
     # same batch through the reference-facing plugin sequence (AllocBufferRW/Enqueue/Read/Finish)
     sess.trace_host_ptr(h_rays.data_ptr(), h_hits.data_ptr(), n)
     t0 = time.perf_counter()
     sess.trace_host_ptr(h_rays.data_ptr(), h_hits.data_ptr(), n)
     plugin_s = time.perf_counter() - t0
 
-    # ---- roofline of the traversal kernel ----
+    # ---- what the implementation itself asks memory for (instrumented kernel) ----
     st = scene.trace_stats(rays.data_ptr(), 0, n)
     nodes_per_ray = st.wide_nodes / max(1, st.rays)
     tris_per_ray = st.triangles / max(1, st.rays)
-    a_impl = 48 + 20 + 64 * nodes_per_ray + 64 * tris_per_ray      # 64-B quantized wide nodes, 64-B triangle records
-    peak, peak_src = read_peaks()
-    traffic, traffic_src = read_traffic(workload)
+    inst_per_ray = st.instances / max(1, st.rays)
+    # 64-B quantized wide nodes, 64-B triangle records, 32-B instance record + 64-B matrix per instance entry
+    a_impl = 48 + 20 + 64 * nodes_per_ray + 64 * tris_per_ray + 96 * inst_per_ray
+
+    # ---- spot parity of the timed batch (not timed) on every rank: device hits == reference / oracle hits ----
+    parity = None
+    a_ref = None
+    cpu = None
+    if not args.no_cpu_baseline:
+        k = min(n, 200000 if world == 1 else 50000)
+        nodes = sess.bvh_nodes() if args.accel == "BVH" else None
+        O, bvh = oracle_for(desc, nodes, args.accel)
+        threads = max(1, O.hardware_threads() // max(1, world))
+        refbvh = reference_for(desc, nodes, args.accel) if rank == 0 else None
+        rays_np = R.to_numpy_rays(rays[:k]) if world > 1 or rank != 0 else R.to_numpy_rays(rays)
+        checker = refbvh or bvh
+        ref = checker.intersect(rays_np[:k], nthreads=threads)
+        got = hits[:k].cpu().numpy().reshape(-1).view(capi.HIT_DTYPE)
+        same = (got["meshIndex"] == ref["meshIndex"]) & ((got["triangleIndex"] == ref["triangleIndex"]) | (ref["meshIndex"] == 0xFFFFFFFF))
+        mism = int((~same).sum())
+        t_exact = bool((got["t"][same] == ref["t"][same]).all())
+        if world > 1:
+            mism = int(shard.sum_over_ranks(mism, device))
+            t_exact = shard.sum_over_ranks(0 if t_exact else 1, device) == 0
+        parity = {"rays": int(k) * world, "ranks_checked": world, "index_mismatch": mism, "t_bit_exact": bool(t_exact),
+                  "against": "reference library (oracle/_ref)" if refbvh else "oracle port"}
+        if rank == 0 and world == 1:
+            cn, cdt = cpu_time_sample(O, checker, rays_np, args.cpu_seconds, threads)
+            what = ("the reference's own %sAccel::Intersect (oracle/_ref, compiled from the reference sources)" % args.accel) if refbvh \
+                else "oracle %sAccel::Intersect restatement" % args.accel
+            cpu = {"value": round(cn / cdt / 1e6, 3), "unit": UNIT, "cores": threads, "kind": "reference" if refbvh else "port",
+                   "embree": embree_status(),
+                   "sample": "first %d rays of the same batch, %s%s, %d threads, %.1f s" % (
+                       cn, what, " walking the same BVHArrayNode array" if args.accel == "BVH" else " on its own CLASSIC-built trees", threads, cdt)}
+        if rank == 0:
+            # reference-traversal visit counts (canonical algorithmic bytes)
+            _, cnt = bvh.intersect(rays_np[:k], nthreads=threads, count=True)
+            a_ref = 48 + 20 + 32.0 * cnt[0] / k + 68.0 * cnt[1] / k
 
     out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-           "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic rays (seeded, generated on the GPU) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": launches,
-           "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "verified": gather_ok,
-                      "bytes_per_step_into_rank0": (world - 1) * n * 20 if world > 1 else 0},
+           "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "pipelined": pipeline, "verified": gather_ok,
+                      "bytes_per_step_into_rank0": (total_rays - counts[0]) * 20 if world > 1 else 0},
            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 20,
                    "api": "lrb_trace_host (C ABI, pinned host buffers, chunked copy/trace overlap)",
                    "plugin_sequence_mrays_per_s": round(n / plugin_s / 1e6, 2)}}
+    if parity:
+        out["parity_check"] = parity
+    if timeline:
+        out["timeline"] = timeline
 
     if rank == 0:
-        cpu = None
-        a_ref = None
-        if not args.no_cpu_baseline and world == 1:
-            O, bvh = oracle_for(desc, sess.bvh_nodes())
-            rays_np = R.to_numpy_rays(rays)
-            threads = O.hardware_threads()
-            refbvh = reference_for(desc, sess.bvh_nodes())
-            cn, cdt = cpu_time_sample(O, refbvh or bvh, rays_np, args.cpu_seconds, threads)
-            cpu = {"value": round(cn / cdt / 1e6, 3), "unit": UNIT, "cores": threads, "kind": "reference" if refbvh else "port",
-                   "sample": "first %d rays of the same batch, %s walking the same BVHArrayNode array, %d threads, %.1f s" % (
-                       cn, "the reference's own BVHAccel::Intersect (oracle/_ref, compiled from the reference sources)" if refbvh
-                       else "oracle BVHAccel::Intersect restatement", threads, cdt)}
-            # reference-traversal visit counts on the same tree (canonical algorithmic bytes)
-            k = min(rays_np.shape[0], 200000)
-            _, cnt = bvh.intersect(rays_np[:k], nthreads=threads, count=True)
-            a_ref = 48 + 20 + 32.0 * cnt[0] / k + 68.0 * cnt[1] / k
-            # spot parity of the timed batch (not timed): device hits == oracle hits on a slice
-            ref = (refbvh or bvh).intersect(rays_np[:k], nthreads=threads)
-            got = hits[:k].cpu().numpy().reshape(-1).view(capi.HIT_DTYPE)
-            same = (got["meshIndex"] == ref["meshIndex"]) & ((got["triangleIndex"] == ref["triangleIndex"]) | (ref["meshIndex"] == 0xFFFFFFFF))
-            out["parity_check"] = {"rays": int(k), "index_mismatch": int((~same).sum()),
-                                   "t_bit_exact": bool((got["t"][same] == ref["t"][same]).all()),
-                                   "against": "reference library (oracle/_ref)" if refbvh else "oracle port"}
-        alg = a_ref if a_ref is not None else a_impl
-        achieved = alg * n / (kern_ms * 1e-3) / 1e9
+        peak, peak_src = read_peaks()
+        cap = read_traffic(workload)
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        sms = dev_view.props().sm_count
         try:
-            l2_bw = dev_view.measure_read_bandwidth(32 << 20, 20)
+            l2_bw = max(dev_view.measure_read_bandwidth(64 << 20, 30), dev_view.measure_read_bandwidth(32 << 20, 30))
         except Exception:
             l2_bw = None
-        out["roofline"] = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                           "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                           "note": (("scene (nodes + triangles = %.1f MB) is L2-resident: the algorithmic bytes are served by L1/L2, DRAM only sees "
-                                     "the compulsory ray/hit streams (see traffic); frac is algorithmic bytes / HBM peak as the contract defines it "
-                                     "and can exceed 1" % (info.device_bytes / 1e6)) if info.device_bytes < 100e6 else
-                                    ("scene (%.1f GB on the device) does not fit L2: node / triangle fetches of incoherent rays go to HBM"
-                                     % (info.device_bytes / 1e9))),
-                           "algorithmic_bytes_per_ray": round(alg, 1),
-                           "algorithmic_bytes_definition": ("A_ref = 68 + 32*N_inner + 68*N_leaf of the REFERENCE traversal on the same tree (SURVEY 8d)"
-                                                            if a_ref is not None else "A_impl (reference visit counts unavailable at N>1)"),
-                           "kernel_ms": round(kern_ms, 4), "units_per_launch": n,
-                           "impl_bytes_per_ray": round(a_impl, 1), "impl_wide_nodes_per_ray": round(nodes_per_ray, 2),
-                           "impl_triangles_per_ray": round(tris_per_ray, 2),
-                           "impl_requested_gbs": round(a_impl * n / (kern_ms * 1e-3) / 1e9, 1),
-                           "l2_read_peak_gbs_measured": round(l2_bw, 1) if l2_bw else None,
-                           "impl_frac_of_l2_peak": round(a_impl * n / (kern_ms * 1e-3) / 1e9 / l2_bw, 4) if l2_bw else None}
+        kern_s = kern_ms * 1e-3
+        resident = info.device_bytes < 100e6
+        roof = {}
+        if cap and cap.get("dram_bytes_per_launch"):
+            scale = n / float(cap.get("rays_in_launch") or n)        # capture and bench launch of the same size: 1
+            dram = cap["dram_bytes_per_launch"] * scale
+            hbm_gbs = dram / kern_s / 1e9
+            memory = {"hbm": {"achieved_gbs": round(hbm_gbs, 1), "peak_gbs": peak, "frac": round(hbm_gbs / peak, 4),
+                              "bytes_per_ray": round(dram / n, 1)}}
+            if cap.get("lts_bytes_per_launch"):
+                l2_gbs = cap["lts_bytes_per_launch"] * scale / kern_s / 1e9
+                memory["l2"] = {"achieved_gbs": round(l2_gbs, 1), "peak_gbs_measured": round(l2_bw, 1) if l2_bw else None,
+                                "frac": round(l2_gbs / l2_bw, 4) if l2_bw else None, "ncu_lts_throughput_pct": cap.get("lts_throughput_pct"),
+                                "hit_rate_pct": cap.get("lts_hit_rate_pct")}
+            if cap.get("l1_global_load_bytes_per_launch"):
+                l1b = cap["l1_global_load_bytes_per_launch"] * scale
+                memory["l1_requests"] = {"ncu_sector_bytes_per_ray": round(l1b / n, 1), "a_impl_bytes_per_ray": round(a_impl, 1),
+                                         "a_impl_over_ncu": round(a_impl * n / l1b, 3),
+                                         "note": "A_impl counts every lane's 64-B node / triangle fetch; ncu counts the distinct 32-B sectors of a warp's "
+                                                 "request, so lanes of a warp that fetch the same node (all of them near the root) are counted once",
+                                         "l1_data_pipe_pct": cap.get("l1_data_pipe_pct"), "hit_rate_pct": cap.get("l1_hit_rate_pct")}
+            if resident and cap.get("warp_instructions_per_ray"):
+                # L2-resident scene: the kernel is bound by the SMs' issue slots, not by a memory level
+                ginst = cap["warp_instructions_per_ray"] * n / kern_s / 1e9
+                ipeak = sms * 4 * sm_clock * 1e6 / 1e9
+                roof = {"bound": "issue", "achieved": round(ginst, 1), "peak": round(ipeak, 1), "unit": "Gwarp-inst/s", "frac": round(ginst / ipeak, 4),
+                        "traffic": dram, "peak_source": "%d SMs x 4 schedulers x %.0f MHz (SM clock sampled during the timed region)" % (sms, sm_clock),
+                        "warp_instructions_per_ray": cap["warp_instructions_per_ray"], "threads_per_instruction": cap.get("threads_per_instruction"),
+                        "ncu_issue_active_pct": cap.get("issue_active_pct"), "ncu_alu_pipe_pct": cap.get("alu_pipe_pct"),
+                        "note": "scene (%.1f MB) is L2-resident; ncu: issue slots %.0f %%, ALU pipe %.0f %%, L1 data pipe %.0f %% busy, DRAM %.1f %% "
+                                "and L2 %.1f %% of their peaks -- the bound is instruction issue at %.1f of 32 lanes per instruction" % (
+                                    info.device_bytes / 1e6, cap.get("issue_active_pct") or 0, cap.get("alu_pipe_pct") or 0, cap.get("l1_data_pipe_pct") or 0,
+                                    100.0 * hbm_gbs / peak, cap.get("lts_throughput_pct") or 0, cap.get("threads_per_instruction") or 0)}
+            else:
+                roof = {"bound": "hbm", "achieved": round(hbm_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(hbm_gbs / peak, 4), "traffic": dram,
+                        "peak_source": peak_src,
+                        "note": "scene (%.1f GB on the device) does not fit L2; achieved = ncu-measured DRAM bytes of one launch / live kernel time. "
+                                "ncu: L2 hit rate %.0f %%, issue slots %.0f %% busy, top stall long_scoreboard %.1f warps per issue: the walk is bound by the "
+                                "latency of dependent node fetches, not by HBM bandwidth" % (
+                                    info.device_bytes / 1e9, cap.get("lts_hit_rate_pct") or 0, cap.get("issue_active_pct") or 0,
+                                    (cap.get("top_stalls_warps_per_issue") or {}).get("long_scoreboard", 0))}
+            roof["memory"] = memory
+            roof["traffic_source"] = cap.get("source")
+            roof["captured_at_commit"] = cap.get("captured_at_commit")
+        else:
+            # no capture of this workload under profiles/: only the implementation's own requested bytes can be stated
+            req = a_impl * n / kern_s / 1e9
+            roof = {"bound": "hbm" if not resident else "issue", "achieved": round(req, 1), "peak": peak, "unit": "GB/s", "frac": round(req / peak, 4),
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "no ncu capture of this workload is committed: achieved = bytes requested by the implementation (A_impl) / kernel time"}
+        alg = a_ref if a_ref is not None else a_impl
+        roof.update({"kernel_ms": round(kern_ms, 4), "units_per_launch": n,
+                     "impl_bytes_per_ray": round(a_impl, 1), "impl_wide_nodes_per_ray": round(nodes_per_ray, 2),
+                     "impl_triangles_per_ray": round(tris_per_ray, 2), "impl_instance_entries_per_ray": round(inst_per_ray, 2),
+                     "impl_requested_gbs": round(a_impl * n / kern_s / 1e9, 1),
+                     "canonical": {"algorithmic_bytes_per_ray": round(alg, 1),
+                                   "definition": ("A_ref = 68 + 32*N_inner + 68*N_leaf of the REFERENCE traversal (SURVEY 8d)" if a_ref is not None
+                                                  else "A_impl (reference visit counts not computed in this run)"),
+                                   "achieved_gbs": round(alg * n / kern_s / 1e9, 1), "frac_of_hbm_peak": round(alg * n / kern_s / 1e9 / peak, 4),
+                                   "note": "SURVEY 8d's implementation-independent figure: bytes the REFERENCE's stackless walk would fetch for these rays "
+                                           "per second of this kernel; it is served by L1/L2 and says how much less this traversal touches, not how busy HBM is"}})
+        out["roofline"] = roof
         if cpu:
             out["cpu_baseline"] = cpu
         out["clocks"] = clocks
         out["scene"] = {"triangles": int(info.n_triangles), "ref_nodes": int(info.n_ref_nodes), "wide_nodes": int(info.n_wide_nodes),
-                        "device_bytes": int(info.device_bytes), "host_build_s": round(build_s, 3)}
+                        "instances": int(info.n_instances), "device_bytes": int(info.device_bytes), "host_build_s": round(build_s, 3),
+                        "relayout_and_upload_s": round(upload_s, 3)}
         print(json.dumps(out), flush=True)
 
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         torch.cuda.synchronize()
-        if gbuf_peer:
-            dev_view.ipc_close_handle(gbuf_peer)
+        for p_ in gbuf_peer:
+            dev_view.ipc_close_handle(p_)
         dist.barrier()
-        if gbuf_local:
-            dev_view.free(gbuf_local)
+        for p_ in gbuf_local:
+            dev_view.free(p_)
     sess.stop()
     sess.close()
     if world > 1:
@@ -494,18 +663,19 @@ def main():
 
 
 def run_reference(args, rank, world, config):
-    """The reference's own CPU algorithm (oracle port: the reference cannot be compiled here) on the
-    host cores, same scene / ray kind / metric; each step is a bounded sample of the workload."""
+    """The reference's own CPU implementation of the path (oracle/_ref: BVHAccel / MBVHAccel::Intersect compiled from the
+    reference's sources; the oracle port where that library is absent) on the host cores, same scene / ray kind / metric;
+    each step is a bounded sample of the workload."""
     if rank != 0:
         return
     from luxcore_b200 import hostapi, rays as R
     desc = build_scene_arrays(args.scene)
-    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": args.builder, "accelerator.bvh.treetype": 4}, desc)
-    sess.build_accelerator("BVH")       # host-only build, no GPU involved
-    nodes = sess.bvh_nodes()
-    O, bvh = oracle_for(desc, nodes)
+    sess = hostapi.Session(accel_config(args), desc)
+    sess.build_accelerator(args.accel)       # host-only build, no GPU involved
+    nodes = sess.bvh_nodes() if args.accel == "BVH" else None
+    O, bvh = oracle_for(desc, nodes, args.accel)
     threads = O.hardware_threads()
-    refbvh = reference_for(desc, nodes)
+    refbvh = reference_for(desc, nodes, args.accel)
     if refbvh is not None:
         bvh = refbvh        # the reference's own code; same intersect(rays, nthreads=) call
     sample = int(os.environ.get("LRB_REF_SAMPLE", "1048576"))
@@ -524,14 +694,14 @@ def run_reference(args, rank, world, config):
         bvh.intersect(rays_np, nthreads=threads)
     dt = (time.perf_counter() - t0) / args.steps
     v = round(sample / dt / 1e6, 3)
+    what = ("the reference's own %sAccel::Intersect (oracle/_ref)%s" % (args.accel, " on the product's binned-SAH BVHArrayNode array" if args.accel == "BVH" else "")
+            if refbvh is not None else "oracle restatement of %sAccel::Intersect" % args.accel)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "strong" if args.scaling == "strong" and world > 1 else "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic rays (seeded) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": 0,
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference" if refbvh is not None else "port",
-                            "sample": "%d rays of the same ray kind per step (bounded sample of the %d-ray batch), %s, %d threads"
-                                      % (sample, args.rays, "the reference's own BVHAccel::Intersect (oracle/_ref) on the product's binned-SAH BVHArrayNode array"
-                                         if refbvh is not None else "oracle restatement of BVHAccel::Intersect", threads)},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference" if refbvh is not None else "port", "embree": embree_status(),
+                            "sample": "%d rays of the same ray kind per step (bounded sample of the %d-ray batch), %s, %d threads" % (sample, args.rays, what, threads)},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -158,9 +158,10 @@ LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
 LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
 /* Tunables (strings): "kernel" = "persistent"|"simple", "blocks_per_sm", "smem_depth",
  * "refill_below", "tri_bias", "inst_bias", "host_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
- * "sort_bits", "sort_min_rays", "gather_stores", "gather_chunk_shift", "wide_stores",
+ * "sort_bits", "sort_min_rays", "gather_stores", "gather_chunk_shift", "gather_defer", "wide_stores",
  * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2),
- * "compact" (1 = lrb_trace compacts the live rays first; default 0 = masked rays are skipped inside the kernel),
+ * "compact" (0 = default: masked rays are skipped inside the kernel | 1 = lrb_trace compacts the live rays first |
+ * 2 = counts them first and compacts when fewer than 60 % are live),
  * "carveout" (preferred shared-memory carve-out of the trace kernels in percent, -1 = driver default). */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
 
@@ -274,6 +275,13 @@ LRB_API int lrb_ipc_close_handle(lrb_device *dev, void *devptr);
  * Asynchronous: later work on the device's stream is ordered after the last store / push. */
 LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_dev, uint32_t ray_count,
 		void *gather_dst_dev, uint32_t n_chunks);
+/* Deferred completion (device option "gather_defer" = 1, signalled pushes only): lrb_trace_gather then does
+ * NOT make the queue wait for its pushes, so the next batch is traced while the tail of this one's RayHit
+ * records is still on the wire.  The caller alternates two hits_dev buffers; the pushes of call k are waited
+ * for automatically before call k + 2 traces, by lrb_sync, or explicitly here: makes cuda_stream (NULL = the
+ * device's queue) wait for the pushes of the most recent call (which = 0), the one before it (1) or both (-1).
+ * A completion signal for the gathering rank belongs behind this wait. */
+LRB_API int lrb_gather_wait(lrb_device *dev, void *cuda_stream, int which);
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 LRB_API const char *lrb_last_error_string(void);

@@ -33,7 +33,7 @@ EXPORTS = [
     "lrb_trace_anyhit", "lrb_compact_rays", "lrb_trace_indexed", "lrb_advance_rays", "lrb_trace_passthrough",
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
-    "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather",
+    "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait",
 ]
 
 
@@ -122,6 +122,7 @@ def lib():
             "lrb_ipc_open_handle": (i32, [vp, C.c_char_p, pvp]),
             "lrb_ipc_close_handle": (i32, [vp, vp]),
             "lrb_trace_gather": (i32, [vp, vp, vp, u32, vp, u32]),
+            "lrb_gather_wait": (i32, [vp, vp, i32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -231,6 +232,10 @@ class Device:
         idx, cnt, host = C.c_void_p(), C.c_void_p(), C.c_uint32(0)
         _check(lib().lrb_compact_rays(self.h, C.c_void_p(rays_devptr), n, C.byref(idx), C.byref(cnt), C.byref(host) if want_count else None))
         return idx.value or 0, cnt.value or 0, (int(host.value) if want_count else None)
+
+    def gather_wait(self, cuda_stream_handle=0, which=-1):
+        """Deferred gathers (option gather_defer): make a stream wait for the pushes of the last (0) / previous (1) / both (-1) calls."""
+        _check(lib().lrb_gather_wait(self.h, C.c_void_p(cuda_stream_handle or 0), which))
 
     # ---- multi-GPU gather buffer sharing ----
     def ipc_get_handle(self, devptr):

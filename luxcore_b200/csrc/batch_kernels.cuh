@@ -138,9 +138,13 @@ __global__ void __launch_bounds__(1024) CompactScanKernel(uint32_t *__restrict__
 	if (threadIdx.x == 0) total[0] = carry;
 }
 
+// autoTotal (compaction in "auto" mode): the live count left by the scan; when most rays are live the list is not
+// worth its scatter pass -- the trace kernels take the same decision from the same word (TraceArgs::permAuto).
 __global__ void __launch_bounds__(256) CompactScatterKernel(const lrb_ray *__restrict__ rays, const uint32_t n,
-		const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ liveIdx) {
+		const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ liveIdx, const uint32_t *__restrict__ autoTotal) {
 	__shared__ uint32_t warpBase[33];
+	if (autoTotal && (unsigned long long)autoTotal[0] * kCompactAutoDen > (unsigned long long)n * kCompactAutoNum)
+		return;
 	const uint32_t base = blockIdx.x * kCompactBlock;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	// ray k * 256 + threadIdx.x of the block: row k, warp `warp` -> 32 (row, warp) groups in index order

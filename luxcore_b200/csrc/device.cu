@@ -63,6 +63,10 @@ struct lrb_device {
 	int triBias;
 	int gatherStores;               // 1: lrb_trace_gather(n_chunks = 0) uses dual-destination stores instead of signalled DMA pushes
 	int gatherChunkShift;           // log2(rays per signalled chunk)
+	int gatherDefer;                // 1: lrb_trace_gather does not make the queue wait for its pushes (see lrb_gather_wait)
+	cudaEvent_t gatherDone[2];      // end of the pushes of the last two lrb_trace_gather calls (alternating)
+	bool gatherPending[2];
+	unsigned gatherSeq;
 	int wideStores;                 // bit 0: vector RayHit stores to the local buffer, bit 1: to the peer buffer
 	int compact;                    // 1: lrb_trace first builds the dense list of live (non-masked) rays and traces through it
 	uint32_t *compactIdx, *compactBlocks, *compactTotal;    // scratch of the compaction kernels
@@ -181,6 +185,10 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->wideStores = 2;
 	dev->gatherStores = 0;
 	dev->gatherChunkShift = 19;
+	dev->gatherDefer = 0;
+	dev->gatherDone[0] = dev->gatherDone[1] = nullptr;
+	dev->gatherPending[0] = dev->gatherPending[1] = false;
+	dev->gatherSeq = 0;
 	dev->sortBitsPerAxis = 5;
 	dev->sortMinRays = 1 << 18;
 	dev->sortKeys[0] = dev->sortKeys[1] = dev->sortVals[0] = dev->sortVals[1] = nullptr;
@@ -197,6 +205,7 @@ int lrb_device_destroy(lrb_device *dev) {
 	LRB_SETDEV(dev);
 	cudaStreamSynchronize(dev->stream);
 	for (size_t i = 0; i < dev->events.size(); ++i) cudaEventDestroy(dev->events[i]);
+	for (int i = 0; i < 2; ++i) if (dev->gatherDone[i]) cudaEventDestroy(dev->gatherDone[i]);
 	if (dev->stageRays) cudaFree(dev->stageRays);
 	if (dev->stageHits) cudaFree(dev->stageHits);
 	cudaFree(dev->sortKeys[0]); cudaFree(dev->sortKeys[1]); cudaFree(dev->sortVals[0]); cudaFree(dev->sortVals[1]);
@@ -265,6 +274,8 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 		dev->instBias = iv;
 	} else if (k == "gather_stores") {
 		dev->gatherStores = iv ? 1 : 0;
+	} else if (k == "gather_defer") {
+		dev->gatherDefer = iv ? 1 : 0;
 	} else if (k == "gather_chunk_shift") {
 		if (iv < 12 || iv > 28) return Fail(LRB_ERR_INVALID, "gather_chunk_shift must be 12..28");
 		dev->gatherChunkShift = iv;
@@ -272,7 +283,7 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 		if (iv < 0 || iv > 3) return Fail(LRB_ERR_INVALID, "wide_stores must be 0..3");
 		dev->wideStores = iv;
 	} else if (k == "compact") {
-		if (iv < 0 || iv > 1) return Fail(LRB_ERR_INVALID, "compact must be 0 (masked rays are skipped inside the trace kernel) or 1 (compacted before it)");
+		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "compact must be 0 (masked rays are skipped inside the trace kernel), 1 (compacted before it) or 2 (counted; compacted when fewer than 60 % are live)");
 		dev->compact = iv;
 	} else if (k == "carveout") {
 		if (iv < -1 || iv > 100) return Fail(LRB_ERR_INVALID, "carveout must be -1 (default) or 0..100 percent of shared memory");
@@ -366,6 +377,10 @@ int lrb_flush(lrb_device *dev) {
 
 int lrb_sync(lrb_device *dev) {
 	LRB_SETDEV(dev);
+	if (dev->gatherPending[0] || dev->gatherPending[1]) {      // deferred gather pushes (gather_defer)
+		LRB_CUDA(cudaStreamSynchronize(dev->copyOutStream));
+		dev->gatherPending[0] = dev->gatherPending[1] = false;
+	}
 	LRB_CUDA(cudaStreamSynchronize(dev->stream));
 	return LRB_OK;
 }
@@ -770,7 +785,8 @@ static int ResolveDriverEntryPoints() {
 
 // Dense list of the live (non-masked) rays of a batch, in increasing index order (batch_kernels.cuh).  The
 // list and its length stay on the device: *idx / *count are device pointers owned by the device object.
-static int CompactRays(lrb_device *dev, const void *rays, uint32_t n, cudaStream_t stream, const uint32_t **idx, const uint32_t **count) {
+static int CompactRays(lrb_device *dev, const void *rays, uint32_t n, cudaStream_t stream, const uint32_t **idx, const uint32_t **count,
+		bool autoMode = false) {
 	const uint32_t nBlocks = (n + kCompactBlock - 1) / kCompactBlock;
 	if (dev->compactCap < n) {
 		LRB_CUDA(cudaStreamSynchronize(stream));
@@ -784,7 +800,8 @@ static int CompactRays(lrb_device *dev, const void *rays, uint32_t n, cudaStream
 	}
 	CompactCountKernel<<<nBlocks, 256, 0, stream>>>((const lrb_ray *)rays, n, dev->compactBlocks);
 	CompactScanKernel<<<1, 1024, 0, stream>>>(dev->compactBlocks, nBlocks, dev->compactTotal);
-	CompactScatterKernel<<<nBlocks, 256, 0, stream>>>((const lrb_ray *)rays, n, dev->compactBlocks, dev->compactIdx);
+	CompactScatterKernel<<<nBlocks, 256, 0, stream>>>((const lrb_ray *)rays, n, dev->compactBlocks, dev->compactIdx,
+			autoMode ? dev->compactTotal : nullptr);
 	LRB_CUDA(cudaGetLastError());
 	dev->counters.kernel_launches += 3;
 	*idx = dev->compactIdx;
@@ -828,8 +845,9 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;
-	if (!mode.liveIdx && dev->compact && !signal && !stats) {
-		if ((rc = CompactRays(dev, rays, n, stream, &mode.liveIdx, &mode.liveCountDev)) != LRB_OK) return rc;
+	if (!mode.liveIdx && dev->compact && !signal && !stats && n >= 4096) {
+		if ((rc = CompactRays(dev, rays, n, stream, &mode.liveIdx, &mode.liveCountDev, dev->compact == 2)) != LRB_OK) return rc;
+		a.permAuto = dev->compact == 2 ? 1u : 0u;
 	}
 	a.perm = mode.liveIdx;
 	a.rayCountDev = mode.liveCountDev;
@@ -843,7 +861,15 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);
 		const bool bigScene = sceneBytes > (size_t)dev->prop.l2CacheSize;
 		PersistentKernel kernel = PickPersistent(two, spill, signal, dev->prefetch == 1 || (dev->prefetch == 2 && bigScene), mode.anyhit);
-		if ((rc = Occupancy(kernel, block, smemBytes, &bps, dev->carveout)) != LRB_OK) return rc;
+		// shared-memory carve-out: enough for the resident blocks the kernel was compiled for (stack columns + 1 KB
+		// reserved per block); measured: a larger L1 does not help this kernel (carveout sweep, profiles/r02_kitchen_sweeps.json)
+		int carve = dev->carveout;
+		if (carve < 0) {
+			const long long want = (long long)(two ? LRB_MINBLOCKS_2L : LRB_MINBLOCKS_1L) * (smemBytes + 1024);
+			const long long cap = (long long)dev->prop.sharedMemPerMultiprocessor;
+			carve = (int)std::min<long long>(100, (want * 100 + cap - 1) / std::max<long long>(cap, 1));
+		}
+		if ((rc = Occupancy(kernel, block, smemBytes, &bps, carve)) != LRB_OK) return rc;
 		if (bps < 1)
 			return Fail(LRB_ERR_INTERNAL, "traversal kernel does not fit on an SM with the requested smem_depth");
 		if (dev->blocksPerSM > 0) bps = std::min(bps, dev->blocksPerSM);
@@ -859,7 +885,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		// optional coherence pre-pass
 		// (measured on a 2 GB triangle soup: 614 -> 720 Mrays/s; on the L2-resident kitchen the sort costs what it gains)
 		const bool wantSort = dev->sortRays == 1 || (dev->sortRays == 2 && bigScene);
-		if (wantSort && !signal && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
+		if (wantSort && !signal && !a.perm && s->view.rootHasBox && n >= (uint32_t)dev->sortMinRays) {
 			if ((rc = SortRays(s, rays, n, stream, &a.perm)) != LRB_OK) return rc;
 		}
 		if (signal) {
@@ -1092,6 +1118,57 @@ int lrb_ipc_close_handle(lrb_device *dev, void *devptr) {
 	return LRB_OK;
 }
 
+}   // extern "C"
+
+// End of a gather's pushes on the copy stream.  Default: the queue waits for them (later work is ordered after
+// the gather).  Deferred (device option gather_defer = 1): the queue does NOT wait -- the next trace may start
+// while the tail of this gather's pushes is still on the wire; the pushes of call k are waited for at the start
+// of call k + 2 (the caller alternates two RayHit buffers), by lrb_gather_wait, or by lrb_sync.
+static int GatherBegin(lrb_device *dev) {
+	if (!dev->gatherDefer)
+		return LRB_OK;
+	const int slot = dev->gatherSeq & 1u;
+	if (dev->gatherPending[slot]) {
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, dev->gatherDone[slot], 0));
+		dev->gatherPending[slot] = false;
+	}
+	return LRB_OK;
+}
+
+static int GatherEnd(lrb_device *dev, cudaEvent_t fallback) {
+	if (!dev->gatherDefer) {
+		LRB_CUDA(cudaEventRecord(fallback, dev->copyOutStream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, fallback, 0));
+		return LRB_OK;
+	}
+	const int slot = dev->gatherSeq & 1u;
+	if (!dev->gatherDone[slot])
+		LRB_CUDA(cudaEventCreateWithFlags(&dev->gatherDone[slot], cudaEventDisableTiming));
+	LRB_CUDA(cudaEventRecord(dev->gatherDone[slot], dev->copyOutStream));
+	dev->gatherPending[slot] = true;
+	++dev->gatherSeq;
+	return LRB_OK;
+}
+
+extern "C" {
+
+int lrb_gather_wait(lrb_device *dev, void *cudaStream, int which) {
+	LRB_SETDEV(dev);
+	cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : dev->stream;
+	// which: 0 = the most recent lrb_trace_gather, 1 = the one before it, -1 = both (and forget them)
+	for (int back = 0; back < 2; ++back) {
+		if (which >= 0 && which != back)
+			continue;
+		const int slot = (dev->gatherSeq + 1u - (unsigned)back) & 1u;      // seq was incremented after the record
+		if (dev->gatherDone[slot] && dev->gatherPending[slot]) {
+			LRB_CUDA(cudaStreamWaitEvent(st, dev->gatherDone[slot], 0));
+			if (which < 0 && st == dev->stream)
+				dev->gatherPending[slot] = false;
+		}
+	}
+	return LRB_OK;
+}
+
 int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, void *dst, uint32_t nChunks) {
 	if (!s)
 		return Fail(LRB_ERR_INVALID, "null scene");
@@ -1120,6 +1197,8 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 			LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 			dev->events.push_back(e);
 		}
+		if ((rc = GatherBegin(dev)) != LRB_OK)
+			return rc;
 		// the copy stream starts after everything queued so far (previous readers of dst / hits)
 		LRB_CUDA(cudaEventRecord(dev->events[0], dev->stream));
 		LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, dev->events[0], 0));
@@ -1138,9 +1217,7 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 			LRB_CUDA(cudaMemcpyAsync((lrb_rayhit *)dst + first, (lrb_rayhit *)hits + first, (size_t)cnt * sizeof(lrb_rayhit),
 					cudaMemcpyDefault, dev->copyOutStream));
 		}
-		LRB_CUDA(cudaEventRecord(dev->events[1], dev->copyOutStream));
-		LRB_CUDA(cudaStreamWaitEvent(dev->stream, dev->events[1], 0));
-		return LRB_OK;
+		return GatherEnd(dev, dev->events[1]);
 	}
 	if (nChunks > 1024) nChunks = 1024;
 	// chunk boundaries on multiples of 4 rays keep every RayHit range 16-byte aligned (4 x 20 B)

@@ -23,12 +23,18 @@
 namespace lrb {
 
 static const int kTraceBlock = 128;     // threads per block of every trace kernel
+// "auto" compaction threshold (measured crossover on kitchen bounce-2, profiles/r02_masked_batches.json: the list pays
+// for its three passes once about half of the lanes are dead)
+static const uint32_t kCompactAutoNum = 6, kCompactAutoDen = 10;
 // Resident blocks per SM the persistent kernels are compiled for (register budget = 65 536 / (128 x blocks)).
+// Measured on B200 (profiles/r02_*): one-level 8 -> 10 blocks (64 -> 48 registers, 88 bytes of spill stores in cold
+// paths) 3 108 -> 3 197 Mrays/s on kitchen bounce-2; two-level 6 -> 8 blocks (80 -> 64 registers) 1 555 -> 1 752
+// Mrays/s on lightinstances bounce-1.
 #ifndef LRB_MINBLOCKS_1L
-#define LRB_MINBLOCKS_1L 8
+#define LRB_MINBLOCKS_1L 10
 #endif
 #ifndef LRB_MINBLOCKS_2L
-#define LRB_MINBLOCKS_2L 6
+#define LRB_MINBLOCKS_2L 8
 #endif
 
 // ---- stacks ---------------------------------------------------------------------------------
@@ -145,6 +151,8 @@ struct TraceArgs {
 	                            // live rays left by the compaction kernels), or NULL
 	const uint32_t *rayCountDev;    // optional: number of entries of perm to process, read on the device (compaction
 	                            // leaves it there; no host round trip between the compaction and the trace)
+	uint32_t permAuto;          // compaction in "auto" mode: the list is only used (and was only written) when fewer than
+	                            // kCompactAutoNum / kCompactAutoDen of the rays are live; otherwise masked rays are skipped here
 	uint32_t *spillNode;        // global stack spill, [spillDepth][totalThreads]
 	float *spillT;
 	uint32_t smemDepth;         // stack entries held in shared memory per thread
@@ -294,7 +302,15 @@ __device__ __forceinline__ void DetectorLoop(const TraceArgs &a, const uint32_t 
 template <bool TWO_LEVEL, bool SPILL, bool SIGNAL, bool PREFETCH = false, bool ANYHIT = false>
 __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LRB_MINBLOCKS_1L) TracePersistent(const TraceArgs a) {
 	extern __shared__ uint32_t smem[];
-	const uint32_t rayCount = a.rayCountDev ? __ldg(a.rayCountDev) : a.rayCount;
+	uint32_t rayCount = a.rayCount;
+	const uint32_t *perm = a.perm;
+	if (a.rayCountDev) {
+		const uint32_t live = __ldg(a.rayCountDev);
+		if (a.permAuto && (unsigned long long)live * kCompactAutoDen > (unsigned long long)a.rayCount * kCompactAutoNum)
+			perm = nullptr;         // mostly live: index order, masked rays skipped below
+		else
+			rayCount = live;
+	}
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t warpId = (blockIdx.x * kTraceBlock + threadIdx.x) >> 5;
 	if (SIGNAL && warpId == 0) {
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 			if (state == kIdle) {
 				const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
 				if (slot < rayCount) {
-					const uint32_t idx = a.perm ? __ldg(a.perm + slot) : slot;
+					const uint32_t idx = perm ? __ldg(perm + slot) : slot;
 					lrb_ray r;
 					LoadRay(a.rays, idx, r);
 					// masked rays are skipped and their RayHit is left untouched (bvh.cl:242-244)
@@ -474,9 +490,17 @@ __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 	local.rays = local.wideNodes = local.triangles = local.instances = local.motionSamples = local.maxStack = 0;
 	unsigned long long nRays = 0;
 
-	const uint32_t rayCount = a.rayCountDev ? __ldg(a.rayCountDev) : a.rayCount;
+	uint32_t rayCount = a.rayCount;
+	const uint32_t *perm = a.perm;
+	if (a.rayCountDev) {
+		const uint32_t live = __ldg(a.rayCountDev);
+		if (a.permAuto && (unsigned long long)live * kCompactAutoDen > (unsigned long long)a.rayCount * kCompactAutoNum)
+			perm = nullptr;
+		else
+			rayCount = live;
+	}
 	for (uint32_t slot = gtid; slot < rayCount; slot += totalThreads) {
-		const uint32_t i = a.perm ? __ldg(a.perm + slot) : slot;
+		const uint32_t i = perm ? __ldg(perm + slot) : slot;
 		lrb_ray r;
 		LoadRay(a.rays, i, r);
 		if (r.flags & LRB_RAY_FLAGS_MASKED) {

@@ -455,11 +455,13 @@ template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
 	uint32_t cur = s.cur;
 	bool alive = true;
-	// single exit: lanes that finish and lanes that found work leave the loop together
-	for (;;) {
-		if (cur == kNullIndex) {
+	// On entry s.cur is kNullIndex (pop), or -- two-level -- an instance reference, which is returned as it is.
+	// Single exit: lanes that finish and lanes that found work leave the loop together.
+	if (!TWO_LEVEL || !IsInstanceRef(cur)) {
+		for (;;) {
 			if (stk.empty()) {
 				alive = false;
+				cur = kNullIndex;
 				break;
 			}
 			float t0;
@@ -467,29 +469,23 @@ LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, S
 			// entry distance recorded at push time; a closer hit found since then culls the entry
 			// (same effect as running the box test now: t0 > min(maxt, tFar)).  The sentinel is
 			// pushed with -inf and never culled.
-			if (t0 > s.maxt) {
-				cur = kNullIndex;
+			if (t0 > s.maxt)
 				continue;
+			if (cur < kTagInstance)
+				break;                  // a wide node or a triangle: the common case
+			if (TWO_LEVEL) {
+				if (cur == kStackSentinel) {
+					// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), its 1/d from the stash
+					s.ox = worldRay.o[0]; s.oy = worldRay.o[1]; s.oz = worldRay.o[2];
+					s.dx = worldRay.d[0]; s.dy = worldRay.d[1]; s.dz = worldRay.d[2];
+					stk.loadInv(s.ix, s.iy, s.iz);
+					s.inInstance = false;
+					continue;
+				}
+				if (cur != kNullIndex)
+					break;              // an instance reference: the caller runs EnterInstance
 			}
-		}
-		if (!TWO_LEVEL || cur < kTagInstance) {
-			if (!TWO_LEVEL && cur == kNullIndex)
-				continue;       // the reference of an empty slot (NaN / inf rays only)
-			break;
-		}
-		if (TWO_LEVEL) {
-			if (cur == kStackSentinel) {
-				// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), its 1/d from the stash
-				s.ox = worldRay.o[0]; s.oy = worldRay.o[1]; s.oz = worldRay.o[2];
-				s.dx = worldRay.d[0]; s.dy = worldRay.d[1]; s.dz = worldRay.d[2];
-				stk.loadInv(s.ix, s.iy, s.iz);
-				s.inInstance = false;
-				cur = kNullIndex;
-				continue;
-			}
-			if (cur == kNullIndex)
-				continue;           // the reference of an empty slot (NaN / inf rays only)
-			break;                  // an instance reference: the caller runs EnterInstance
+			// kNullIndex: the reference of an empty slot (NaN / inf rays only) -- pop on
 		}
 	}
 	s.cur = cur;

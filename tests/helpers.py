@@ -415,7 +415,8 @@ def check_anyhit(got, closest, rays, desc=None, what=""):
     (checked with the reference's own arithmetic when `desc` is a one-level scene), never closer than the closest hit."""
     miss_g, miss_c = got["meshIndex"] == NULL, closest["meshIndex"] == NULL
     assert (miss_g == miss_c).all(), "%s: any-hit hit/miss differs from closest-hit on %d rays" % (what, int((miss_g != miss_c).sum()))
-    assert got[miss_g].tobytes() == closest[miss_c].tobytes(), "%s: miss payload" % what
+    # miss payload: t = ray.maxt, meshIndex = NULL (b1 / b2 / triangleIndex of a miss are unspecified in the reference, SURVEY 8a a2)
+    assert (got["t"][miss_g].view(np.uint32) == closest["t"][miss_c].view(np.uint32)).all(), "%s: miss payload" % what
     h = ~miss_g
     assert (got["t"][h] >= closest["t"][h]).all(), "%s: any-hit closer than the closest hit" % what
     if desc is not None and h.any():

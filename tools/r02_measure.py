@@ -238,7 +238,7 @@ def section_masked():
         flags.copy_((u < frac).to(torch.int32))
         row = {"scene": "kitchen", "rays": "bounce-2", "n": n, "masked_fraction": frac}
         ref = None
-        for label, opt in (("skip_in_kernel", 0), ("compacted", 1)):
+        for label, opt in (("skip_in_kernel", 0), ("compacted", 1), ("auto", 2)):
             sess.set_option("compact", opt)
             hits.zero_()
             med, best = time_trace(sess, rays, hits, ARGS.reps)
@@ -247,7 +247,7 @@ def section_masked():
             if ref is None:
                 ref = hits.clone()
             else:
-                row["identical"] = bool(torch.equal(ref, hits))
+                row["identical"] = row.get("identical", True) and bool(torch.equal(ref, hits))
         sess.set_option("compact", 0)
         emit(row)
     flags.zero_()
