@@ -283,6 +283,19 @@ LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_
  * A completion signal for the gathering rank belongs behind this wait. */
 LRB_API int lrb_gather_wait(lrb_device *dev, void *cuda_stream, int which);
 
+/* ---- multi-GPU: film merge over NVLink -------------------------------------------------------- */
+/* The sum of per-GPU film planes that replaces the host-side merge of per-device films
+ * (PathOCLRenderEngine::MergeThreadFilms -> Film::AddFilm, src/slg/engines/pathocl/pathocl.cpp:184-201,
+ * src/slg/film/film.cpp:707-760):  dst[i] = (((0 + tile_0[i]) + tile_1[i]) + ...) for i in [first, first + count),
+ * binary32 adds in tile (= device) order, bit for bit what the reference's loop computes.  tiles_dev is a HOST
+ * array of n_tiles (<= 16) DEVICE pointers to float planes of identical layout -- this GPU's own film and the
+ * other ranks' films opened with lrb_ipc_open_handle -- and dst_dev the merged film (local or peer-mapped).
+ * Every rank calls this for its own slice of the film: peer loads over NVLink pull that slice of every film,
+ * the sums go straight into the merged film on the gathering GPU.  Asynchronous on the device's queue; the
+ * caller orders it after every rank finished writing its film and signals completion afterwards. */
+LRB_API int lrb_film_reduce(lrb_device *dev, const float *const *tiles_dev, uint32_t n_tiles, float *dst_dev,
+		uint64_t first, uint64_t count);
+
 /* ---- diagnostics ----------------------------------------------------------------------- */
 LRB_API const char *lrb_last_error_string(void);
 LRB_API int lrb_get_counters(lrb_device *dev, lrb_counters *out);

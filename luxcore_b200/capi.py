@@ -33,7 +33,7 @@ EXPORTS = [
     "lrb_trace_anyhit", "lrb_compact_rays", "lrb_trace_indexed", "lrb_advance_rays", "lrb_trace_passthrough",
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
-    "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait",
+    "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait", "lrb_film_reduce",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
             "lrb_ipc_close_handle": (i32, [vp, vp]),
             "lrb_trace_gather": (i32, [vp, vp, vp, u32, vp, u32]),
             "lrb_gather_wait": (i32, [vp, vp, i32]),
+            "lrb_film_reduce": (i32, [vp, C.POINTER(vp), u32, vp, u64, u64]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -236,6 +237,11 @@ class Device:
     def gather_wait(self, cuda_stream_handle=0, which=-1):
         """Deferred gathers (option gather_defer): make a stream wait for the pushes of the last (0) / previous (1) / both (-1) calls."""
         _check(lib().lrb_gather_wait(self.h, C.c_void_p(cuda_stream_handle or 0), which))
+
+    def film_reduce(self, tile_devptrs, dst_devptr, first, count):
+        """dst[first:first+count] = sum of the tiles' float planes in list order (Film::AddFilm order), asynchronous."""
+        arr = (C.c_void_p * len(tile_devptrs))(*[C.c_void_p(p) for p in tile_devptrs])
+        _check(lib().lrb_film_reduce(self.h, arr, len(tile_devptrs), C.c_void_p(dst_devptr), first, count))
 
     # ---- multi-GPU gather buffer sharing ----
     def ipc_get_handle(self, devptr):

@@ -168,6 +168,45 @@ __global__ void __launch_bounds__(256) CompactScatterKernel(const lrb_ray *__res
 	}
 }
 
+// ---- film merge over NVLink peer memory ------------------------------------------------------
+
+// Sum of per-GPU film planes in device order, the arithmetic of the reference's merge of per-device films
+// (PathOCLRenderEngine::MergeThreadFilms, src/slg/engines/pathocl/pathocl.cpp:184-201: film->Clear(), then
+// Film::AddFilm of every device's film in device order; AddFilm adds pixel by pixel, channel by channel,
+// src/slg/film/film.cpp:707-760):   dst[i] = (((0 + t_0[i]) + t_1[i]) + ...) + t_{n-1}[i]   in binary32.
+// The tile pointers may be local or peer-mapped (CUDA IPC over NVLink), and so may dst: every rank runs this
+// kernel over ITS slice of the film, pulling that slice of every other rank's planes with peer loads and
+// storing the sums into the merged film on the gathering GPU -- a reduce-scatter and the gather of its result
+// in one kernel per rank, no NCCL, no staging copy; the summation order does not depend on the rank count's
+// schedule, so the result is the reference's bit for bit.
+static const int kMaxFilmTiles = 16;
+struct FilmTiles { const float *tile[kMaxFilmTiles]; };
+
+__global__ void __launch_bounds__(256) FilmReduceKernel(const FilmTiles t, const int nTiles, float *__restrict__ dst,
+		const unsigned long long first, const unsigned long long count, const int vec4) {
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (vec4) {
+		// first and count are multiples of four floats and every pointer is 16-byte aligned
+		const unsigned long long n4 = count >> 2, f4 = first >> 2;
+		for (; i < n4; i += stride) {
+			float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+			for (int r = 0; r < nTiles; ++r) {
+				const float4 v = reinterpret_cast<const float4 *>(t.tile[r])[f4 + i];
+				acc.x = LRB_ADD(acc.x, v.x); acc.y = LRB_ADD(acc.y, v.y); acc.z = LRB_ADD(acc.z, v.z); acc.w = LRB_ADD(acc.w, v.w);
+			}
+			reinterpret_cast<float4 *>(dst)[f4 + i] = acc;
+		}
+	} else {
+		for (; i < count; i += stride) {
+			float acc = 0.f;
+			for (int r = 0; r < nTiles; ++r)
+				acc = LRB_ADD(acc, t.tile[r][first + i]);
+			dst[first + i] = acc;
+		}
+	}
+}
+
 }   // namespace lrb
 
 #endif

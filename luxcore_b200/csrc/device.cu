@@ -1065,6 +1065,29 @@ int lrb_trace_passthrough(lrb_scene *s, void *rays, void *hits, uint32_t n, cons
 	return LRB_OK;
 }
 
+int lrb_film_reduce(lrb_device *dev, const float *const *tilesDev, uint32_t nTiles, float *dstDev, uint64_t first, uint64_t count) {
+	LRB_SETDEV(dev);
+	if (count == 0)
+		return LRB_OK;
+	if (!tilesDev || !dstDev || nTiles == 0 || nTiles > (uint32_t)kMaxFilmTiles)
+		return Fail(LRB_ERR_INVALID, "film reduce: 1..16 tile pointers and a destination are required");
+	FilmTiles t;
+	memset(&t, 0, sizeof(t));
+	bool aligned = ((reinterpret_cast<uintptr_t>(dstDev) & 15u) == 0) && (first % 4 == 0) && (count % 4 == 0);
+	for (uint32_t r = 0; r < nTiles; ++r) {
+		if (!tilesDev[r])
+			return Fail(LRB_ERR_INVALID, "film reduce: null tile pointer");
+		t.tile[r] = tilesDev[r];
+		aligned = aligned && (reinterpret_cast<uintptr_t>(tilesDev[r]) & 15u) == 0;
+	}
+	const uint64_t items = aligned ? count / 4 : count;
+	const int grid = (int)std::min<uint64_t>((items + 255) / 256, (uint64_t)dev->prop.multiProcessorCount * 8);
+	FilmReduceKernel<<<grid, 256, 0, dev->stream>>>(t, (int)nTiles, dstDev, first, count, aligned ? 1 : 0);
+	LRB_CUDA(cudaGetLastError());
+	dev->counters.kernel_launches += 1;
+	return LRB_OK;
+}
+
 int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {
 	if (!s || !out)
 		return Fail(LRB_ERR_INVALID, "null argument");

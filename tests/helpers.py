@@ -427,3 +427,50 @@ def check_anyhit(got, closest, rays, desc=None, what=""):
         assert (t.view(np.uint32) == got["t"][h].view(np.uint32)).all() and (b1.view(np.uint32) == got["b1"][h].view(np.uint32)).all() \
             and (b2.view(np.uint32) == got["b2"][h].view(np.uint32)).all(), "%s: any-hit t / b1 / b2 not bit-exact" % what
     return {"rays": int(got.shape[0]), "hits": int(h.sum()), "same_as_closest": int((got[h] == closest[h]).sum())}
+
+
+def in_plane_rays(desc, n, seed):
+    """Adversarial batch for the one known parity residual (DESIGN.md "Parity"): rays lying IN THE PLANE of a scene
+    triangle, starting outside it, running along in-plane directions (a third of them exactly along an edge).  For a
+    triangle in general position Triangle::Intersect then divides rounding noise by rounding noise and the reference can
+    report a hit the ray misses by far -- whenever it gets to test the triangle."""
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rng = np.random.default_rng(seed)
+    tri = rng.integers(0, p0.shape[0], n)
+    P0, E1, E2 = p0[tri].astype(np.float64), e1[tri].astype(np.float64), e2[tri].astype(np.float64)
+    a, b = rng.uniform(-1.5, 2.5, n), rng.uniform(-1.5, 2.5, n)
+    inside = (a >= -0.05) & (b >= -0.05) & (a + b <= 1.05)
+    a[inside] += 1.5
+    o = P0 + a[:, None] * E1 + b[:, None] * E2
+    d = rng.standard_normal(n)[:, None] * E1 + rng.standard_normal(n)[:, None] * E2
+    mode = rng.integers(0, 3, n)
+    d[mode == 1] = E1[mode == 1]
+    d[mode == 2] = E2[mode == 2]
+    d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-30
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    rays["o"] = o.astype(np.float32)
+    rays["d"] = d.astype(np.float32)
+    rays["mint"] = 1e-5
+    rays["maxt"] = np.inf
+    return rays
+
+
+def index_differences(got, ref):
+    hit = ref["meshIndex"] != NULL
+    return int(((got["meshIndex"] != ref["meshIndex"]) | (hit & (got["triangleIndex"] != ref["triangleIndex"]))).sum())
+
+
+def coplanar_with_reported(desc, rays, rec):
+    """True where the ray lies in the plane of the triangle `rec` names (float64 geometry)."""
+    p0, e1, e2, offs = S.world_triangles(desc)
+    ok = rec["meshIndex"] != NULL
+    flat = np.where(ok, offs[np.minimum(rec["meshIndex"], len(offs) - 1).astype(np.int64)] + rec["triangleIndex"].astype(np.int64), 0)
+    n = np.cross(e1[flat].astype(np.float64), e2[flat].astype(np.float64))
+    n /= np.linalg.norm(n, axis=1, keepdims=True) + 1e-300
+    d = rays["d"].astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True) + 1e-300
+    lo, hi = desc.bbox()
+    scale = float(np.linalg.norm(hi - lo))
+    sin_to_plane = np.abs((n * d).sum(1))
+    dist = np.abs((n * (rays["o"].astype(np.float64) - p0[flat])).sum(1))
+    return ok & (sin_to_plane < 1e-5) & (dist < 1e-5 * scale)

@@ -274,3 +274,31 @@ def test_scheduling_model_is_consistent_with_the_per_ray_emulation():
         assert hits.tobytes() == ref.tobytes()
         assert c["rays"] == st["rays"] and c["node_lanes"] == st["wide_nodes"] and c["tri_lanes"] == st["triangles"]
         assert c["node_phases"] * 32 >= c["node_lanes"] and c["tri_phases"] * 32 >= c["tri_lanes"]
+
+
+@pytest.mark.parametrize("name,n", [("cornell", 400000), ("kitchen", 400000), ("bigmonkey", 200000)])
+def test_in_plane_rays_bound_the_known_residual(name, n):
+    """DESIGN.md "Parity", known residual -- BUILT.  Rays lying in the plane of a triangle in general position make
+    Triangle::Intersect (triangle.h:55-89) divide rounding noise by rounding noise: its t / b1 / b2 are arbitrary, it
+    "hits" triangles the ray misses by far, and which of those artefacts survives depends on the order in which the
+    reference's fixed depth-first walk meets them.  A traversal in another order (ours: near to far, triangles culled
+    by their own boxes) cannot reproduce that order dependence.  This test bounds the class: on a batch made ONLY of such
+    rays fewer than 1 in 1 000 answers differ, and every differing ray is coplanar with the triangle one of the two
+    sides names (i.e. belongs to the artefact class, not to ordinary geometry)."""
+    desc = S.load_fixture(name)
+    osc = H.oracle_scene(desc)
+    bvh = O.BVH(osc, tree_type=4)
+    verts, offs = H.flattened_from_oracle(desc, osc)
+    emu = H.Emu.bvh(bvh.nodes(), verts, offs)
+    rays = H.in_plane_rays(desc, n, seed=1)
+    ref = bvh.intersect(rays)
+    got = emu.trace(rays)
+    hit = ref["meshIndex"] != H.NULL
+    diff = (got["meshIndex"] != ref["meshIndex"]) | (hit & (got["triangleIndex"] != ref["triangleIndex"]))
+    print("%s: %d of %d in-plane rays answer differently" % (name, int(diff.sum()), n))
+    assert diff.sum() <= n * 1e-3       # observed: 0.8e-5 (kitchen), 3.5e-5 (cornell), 5.9e-4 (bigmonkey: every triangle in general position)
+    artefact = H.coplanar_with_reported(desc, rays, ref) | H.coplanar_with_reported(desc, rays, got)
+    assert artefact[diff].all()
+    # everywhere else the records are the reference's bit for bit
+    same = ~diff & hit
+    assert (got["t"][same].view(np.uint32) == ref["t"][same].view(np.uint32)).all()

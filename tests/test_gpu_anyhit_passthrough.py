@@ -132,6 +132,8 @@ def test_advance_rays_follows_the_reference_rule(dev):
     for i in np.flatnonzero(pass_mesh):
         words[i >> 5] |= np.uint32(1 << (i & 31))
     cont_flags = (rng.random(m) < 0.05).astype(np.uint8)
+    cont_flags[tight] = 1; cont_flags[huge] = 1            # the adversarial records do continue ...
+    rays["flags"][tight] = 0; rays["flags"][huge] = 0      # ... and are live
 
     d_rays, d_hits, d_words, d_flags = DevBuf(dev, rays), DevBuf(dev, hits), DevBuf(dev, words), DevBuf(dev, cont_flags)
     n_cont = scene.advance_rays(d_rays.p, d_hits.p, m, d_words.p, words.shape[0], d_flags.p)
@@ -295,3 +297,29 @@ def test_host_layer_shadow_rays_and_pass_through(dev):
     H.check_anyhit(got, orc.intersect(rays), rays, desc, what="host layer shadow rays")
     assert sess.total_rays() == n
     sess.stop(); sess.close()
+
+
+@pytest.mark.parametrize("n_floats,n_tiles", [(4 * 512 * 512, 8), (4 * 333 * 77 + 3, 5), (17, 16), (4 * 1024, 1)])
+def test_film_reduce_is_the_reference_sum(dev, n_floats, n_tiles):
+    """lrb_film_reduce == Film::AddFilm applied film by film in device order (film.cpp:707-760): binary32 adds in tile
+    order, bit for bit; here every "rank" is a buffer of the one GPU and the slices are summed by separate launches."""
+    from luxcore_b200 import shard
+    rng = np.random.default_rng(n_floats)
+    tiles = [(rng.standard_normal(n_floats).astype(np.float32) * np.float32(10.0 ** rng.integers(-4, 5))) for _ in range(n_tiles)]
+    tiles[0][:7] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 3e38][:min(7, n_floats)]
+    bufs = [DevBuf(dev, t) for t in tiles]
+    dst = DevBuf(dev, np.full(n_floats + 4, 7.0, dtype=np.float32))
+    world = 3
+    for r in range(world):
+        first, count = shard.film_slice(n_floats, world, r)
+        dev.film_reduce([b.p for b in bufs], dst.p, first, count)
+    dev.sync()
+    got = dst.read(np.float32, n_floats + 4)
+    want = np.zeros(n_floats, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        for t in tiles:
+            want = (want + t).astype(np.float32)
+    assert got[:n_floats].tobytes() == want.tobytes()
+    assert (got[n_floats:] == 7.0).all()
+    for b in bufs + [dst]:
+        b.free()

@@ -103,3 +103,68 @@ def test_instances_grazing_rays(dev, which):
     assert rep["hits"] > 0.3 * rep["n"]
     assert rep["bit_exact_hits"] == rep["hits"]
     scene.free()
+
+
+def _reference_mbvh(desc):
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref (the reference compiled from /root/reference) is not present on this machine")
+    return refapi.MBVH(H.reference_scene(desc))
+
+
+def test_full_lightinstances_against_the_reference_library(dev):
+    """BASELINE.json configs[2] at full size -- 4 502 objects, 4 500 instances -- against the REFERENCE's own
+    MBVHAccel::Intersect (oracle/_ref), not the oracle port: bit for bit (camera, uniform and bounce-like surface rays)."""
+    desc = S.load_fixture("lightinstances")
+    assert len(desc.meshes) == 4502
+    osc = H.oracle_scene(desc)
+    mb = O.MBVH(osc)
+    scene = _upload(dev, desc, mb)
+    assert scene.info().n_instances == 4502
+    ref_accel = _reference_mbvh(desc)
+    p0, e1, e2, _ = S.world_triangles(desc)
+    rays = np.concatenate([_rays(desc, 400000, 91), R.to_numpy_rays(R.surface_rays(p0, e1, e2, 200000, seed=93, axis_fraction=0.2))])
+    ref = ref_accel.intersect(rays)
+    got = scene.trace_host(rays)
+    rep = H.compare_hits_tie_aware(got, ref, rays, osc, what="full lightinstances vs reference library", two_level=True)
+    assert rep["hits"] > 0.2 * rep["n"]
+    assert rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
+
+
+@pytest.mark.parametrize("which", ["zoo-inst", "bigmonkey-instances"])
+def test_instances_against_the_reference_library(dev, which):
+    desc = Z.instances_scene() if which == "zoo-inst" else S.load_fixture(which)
+    osc = H.oracle_scene(desc)
+    scene = _upload(dev, desc, O.MBVH(osc))
+    ref_accel = _reference_mbvh(desc)
+    rays = _rays(desc, 300000, 95)
+    rep = H.compare_hits(scene.trace_host(rays), ref_accel.intersect(rays), rays, what=which + " vs reference library")
+    assert rep["hits"] > 0.1 * rep["n"] and rep["bit_exact_hits"] == rep["hits"]
+    scene.free()
+
+
+@pytest.mark.parametrize("which,n", [("zoo-motion", 300000), ("bigmonkey-motion", 300000)])
+def test_motion_against_the_reference_library(dev, which, n):
+    """Rotating (zoo-motion: Slerp) and translating (bigmonkey-motion) motion blur against the REFERENCE's own
+    MotionSystem::Sample + MBVHAccel::Intersect.  The reference's Slerp calls the host libm's sinf / acosf; the device
+    evaluates them in double and rounds once, which reproduces glibc in all but a small fraction of the calls -- the
+    observed fraction of hits that are not bit-identical is printed and bounded, none may be off by more than 1e-3."""
+    desc = Z.motion_scene() if which == "zoo-motion" else S.load_fixture(which)
+    osc = H.oracle_scene(desc)
+    scene = _upload(dev, desc, O.MBVH(osc))
+    ref_accel = _reference_mbvh(desc)
+    rays = _rays(desc, n, 97, time_range=(-0.05, 1.05))
+    ref = ref_accel.intersect(rays)
+    got = scene.trace_host(rays)
+    _, second = osc.brute(rays, two_level=True, want_second=True)
+    rep = H.compare_hits(got, ref, rays, second_t=second, rel_tol=1e-5, what=which + " vs reference library", libm_outlier_frac=1e-4)
+    frac_inexact = 1.0 - rep["bit_exact_hits"] / max(1, rep["hits"])
+    print("%s: %d hits, %.4f %% not bit-identical to the reference library, %d beyond 1e-5 (libm outliers), %d tie-exempt"
+          % (which, rep["hits"], 100.0 * frac_inexact, rep["libm_outliers"], rep["tie_exempt"]))
+    assert rep["hits"] > 0.1 * rep["n"]
+    assert rep["tie_exempt"] <= 1e-4 * rep["n"]
+    assert frac_inexact <= 0.005
+    if which == "bigmonkey-motion":
+        assert rep["libm_outliers"] == 0       # translation only: no trigonometry involved
+    scene.free()
