@@ -855,7 +855,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	if (dev->persistent && !stats) {
 		const int block = kTraceBlock;
 		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
-		const int smemBytes = depth * block * 8 + (two ? 3 * block * 4 : 0);     // stack columns (+ the world ray's 1/d, SmemStack::stashInv)
+		const int smemBytes = depth * block * 8 + (two ? 9 * block * 4 : 0);     // stack columns (+ the world ray, SmemStack::stashRay)
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
 		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);

@@ -91,12 +91,16 @@ template <bool SPILL> struct SmemStack {
 	}
 	__device__ __forceinline__ bool empty() const { return top == base; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)((top - base) / (2 * kTraceBlock) + over); }
-	// two-level kernels: three more words per thread behind the stack columns (the launch sizes shared memory for them)
-	__device__ __forceinline__ void stashInv(float x, float y, float z) {
-		limit[0] = __float_as_uint(x); limit[kTraceBlock] = __float_as_uint(y); limit[2 * kTraceBlock] = __float_as_uint(z);
+	// two-level kernels: nine more words per thread behind the stack columns (the launch sizes shared memory for them)
+	__device__ __forceinline__ void stashRay(float ox, float oy, float oz, float dx, float dy, float dz, float ix, float iy, float iz) {
+		limit[0] = __float_as_uint(ox); limit[kTraceBlock] = __float_as_uint(oy); limit[2 * kTraceBlock] = __float_as_uint(oz);
+		limit[3 * kTraceBlock] = __float_as_uint(dx); limit[4 * kTraceBlock] = __float_as_uint(dy); limit[5 * kTraceBlock] = __float_as_uint(dz);
+		limit[6 * kTraceBlock] = __float_as_uint(ix); limit[7 * kTraceBlock] = __float_as_uint(iy); limit[8 * kTraceBlock] = __float_as_uint(iz);
 	}
-	__device__ __forceinline__ void loadInv(float &x, float &y, float &z) const {
-		x = __uint_as_float(limit[0]); y = __uint_as_float(limit[kTraceBlock]); z = __uint_as_float(limit[2 * kTraceBlock]);
+	__device__ __forceinline__ void loadRay(float &ox, float &oy, float &oz, float &dx, float &dy, float &dz, float &ix, float &iy, float &iz) const {
+		ox = __uint_as_float(limit[0]); oy = __uint_as_float(limit[kTraceBlock]); oz = __uint_as_float(limit[2 * kTraceBlock]);
+		dx = __uint_as_float(limit[3 * kTraceBlock]); dy = __uint_as_float(limit[4 * kTraceBlock]); dz = __uint_as_float(limit[5 * kTraceBlock]);
+		ix = __uint_as_float(limit[6 * kTraceBlock]); iy = __uint_as_float(limit[7 * kTraceBlock]); iz = __uint_as_float(limit[8 * kTraceBlock]);
 	}
 };
 
@@ -136,9 +140,13 @@ template <int CAP> struct LocalStack {
 	}
 	__device__ __forceinline__ bool empty() const { return sp == 0; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
-	float inv[3];
-	__device__ __forceinline__ void stashInv(float x, float y, float z) { inv[0] = x; inv[1] = y; inv[2] = z; }
-	__device__ __forceinline__ void loadInv(float &x, float &y, float &z) const { x = inv[0]; y = inv[1]; z = inv[2]; }
+	float w[9];
+	__device__ __forceinline__ void stashRay(float ox, float oy, float oz, float dx, float dy, float dz, float ix, float iy, float iz) {
+		w[0] = ox; w[1] = oy; w[2] = oz; w[3] = dx; w[4] = dy; w[5] = dz; w[6] = ix; w[7] = iy; w[8] = iz;
+	}
+	__device__ __forceinline__ void loadRay(float &ox, float &oy, float &oz, float &dx, float &dy, float &dz, float &ix, float &iy, float &iz) const {
+		ox = w[0]; oy = w[1]; oz = w[2]; dx = w[3]; dy = w[4]; dz = w[5]; ix = w[6]; iy = w[7]; iz = w[8];
+	}
 };
 
 struct TraceArgs {
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 		int nLive;
 		do {
 			if (state == kActive && NeedsResolve<TWO_LEVEL>(s.cur)) {
-				if (!Resolve<TWO_LEVEL, false>(a.sc, a.rays[rayIdx], s, stk, nullptr))
+				if (!Resolve<TWO_LEVEL, false>(a.sc, s, stk, nullptr))
 					state = kUnsaved;
 			}
 			__syncwarp();
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 				nInst = __popc(__ballot_sync(0xffffffffu, work == kWorkInstance));
 				if (VoteEnterInstances(nInst, nNode, nTri, a.instBias, a.triBias)) {
 					if (work == kWorkInstance) {
-						EnterInstance<false>(a.sc, a.rays[rayIdx], s, stk, nullptr);
+						EnterInstance<false>(a.sc, s, stk, nullptr);
 						work = WorkOf<TWO_LEVEL>(s.cur);
 					}
 					__syncwarp();
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 		RayState s;
 		stk.sp = 0;
 		if (InitRay(a.sc, r, s)) {
-			while (Step<TWO_LEVEL, STATS>(a.sc, a.rays[i], s, stk, &local)) {
+			while (Step<TWO_LEVEL, STATS>(a.sc, s, stk, &local)) {
 				if (ANYHIT && s.hitMesh != kNullIndex)
 					break;
 			}

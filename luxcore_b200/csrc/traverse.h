@@ -418,7 +418,7 @@ LRB_HD bool VoteEnterInstances(const int nInst, const int nNode, const int nTri,
 // and this is its one expensive step (64-B matrix fetch, ~40 flops, three IEEE reciprocals); here all
 // lanes of a warp that enter an instance in the same iteration do it in the same instructions.
 template <bool STATS, class STACK>
-LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD void EnterInstance(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	const char *ip = reinterpret_cast<const char *>(&sc.insts[s.cur & kRefIndexMask]);
 	const uint4 ir = LRB_LDGU4(ip);
 	const uint4 ir2 = LRB_LDGU4(ip + 16);
@@ -427,15 +427,13 @@ LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState
 		s.cur = kNullIndex;     // empty leaf tree
 		return;
 	}
-	// s holds the world ray here (instances do not nest): keep its 1/d for the way back (Resolve), which would
-	// otherwise recompute three IEEE reciprocals inside its divergent pop loop
-	stk.stashInv(s.ix, s.iy, s.iz);
+	// s holds the world ray here (instances do not nest): keep it, with its 1/d, for the way back (Resolve), which
+	// would otherwise reload it from the ray buffer and recompute three IEEE reciprocals inside its divergent pop loop
+	stk.stashRay(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, s.ix, s.iy, s.iz);
 	if (ir.y != kNullIndex) {
-		TransformRay(s, sc.minv + 16 * (size_t)ir.y, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+		TransformRay(s, sc.minv + 16 * (size_t)ir.y, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz);
 	} else if (ir.z != kNullIndex) {
-		const Ray6 r = MotionRay(sc.motionFirst, sc.motionLast, sc.interps, ir.z, s.time, worldRay.o[0], worldRay.o[1], worldRay.o[2],
-				worldRay.d[0], worldRay.d[1], worldRay.d[2]);
+		const Ray6 r = MotionRay(sc.motionFirst, sc.motionLast, sc.interps, ir.z, s.time, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz);
 		if (STATS) stats->motionSamples++;
 		SetRay(s, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
 	}
@@ -450,9 +448,9 @@ LRB_HD void EnterInstance(const SceneView &sc, const lrb_ray &worldRay, RayState
 // to do or the popped entry lies behind the best hit, and leaves leaf trees (sentinel).  An instance
 // reference is returned as it is (EnterInstance follows).  Returns false when the ray is finished.
 // STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n) and a
-// three-float side slot stashInv(ix, iy, iz) / loadInv(ix&, iy&, iz&) (the world ray's 1/d while inside an instance).
+// nine-float side slot stashRay(o, d, 1/d) / loadRay(...) (the world ray while the traversal is inside an instance).
 template <bool TWO_LEVEL, bool STATS, class STACK>
-LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD bool Resolve(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	uint32_t cur = s.cur;
 	bool alive = true;
 	// On entry s.cur is kNullIndex (pop), or -- two-level -- an instance reference, which is returned as it is.
@@ -475,10 +473,8 @@ LRB_HD bool Resolve(const SceneView &sc, const lrb_ray &worldRay, RayState &s, S
 				break;                  // a wide node or a triangle: the common case
 			if (TWO_LEVEL) {
 				if (cur == kStackSentinel) {
-					// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), its 1/d from the stash
-					s.ox = worldRay.o[0]; s.oy = worldRay.o[1]; s.oz = worldRay.o[2];
-					s.dx = worldRay.d[0]; s.dy = worldRay.d[1]; s.dz = worldRay.d[2];
-					stk.loadInv(s.ix, s.iy, s.iz);
+					// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), from the stash
+					stk.loadRay(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, s.ix, s.iy, s.iz);
 					s.inInstance = false;
 					continue;
 				}
@@ -654,13 +650,13 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 // One unit of work for one ray: Resolve, then a node visit or a triangle test (static kernel, host
 // emulation).  Returns false when the ray is finished.
 template <bool TWO_LEVEL, bool STATS, class STACK>
-LRB_HD bool Step(const SceneView &sc, const lrb_ray &worldRay, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD bool Step(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	if (NeedsResolve<TWO_LEVEL>(s.cur)) {
-		if (!Resolve<TWO_LEVEL, STATS>(sc, worldRay, s, stk, stats))
+		if (!Resolve<TWO_LEVEL, STATS>(sc, s, stk, stats))
 			return false;
 	}
 	if (TWO_LEVEL && IsInstanceRef(s.cur)) {
-		EnterInstance<STATS>(sc, worldRay, s, stk, stats);
+		EnterInstance<STATS>(sc, s, stk, stats);
 		if (s.cur == kNullIndex)
 			return true;        // empty leaf tree: pop on at the next step
 	}

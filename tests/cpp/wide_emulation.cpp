@@ -27,9 +27,13 @@ struct HostStack {
 	void pop(uint32_t &a, float &b) { a = n.back(); b = t.back(); n.pop_back(); t.pop_back(); }
 	bool empty() const { return n.empty(); }
 	unsigned long long depth() const { return n.size(); }
-	float inv[3] = { 0.f, 0.f, 0.f };
-	void stashInv(float x, float y, float z) { inv[0] = x; inv[1] = y; inv[2] = z; }
-	void loadInv(float &x, float &y, float &z) const { x = inv[0]; y = inv[1]; z = inv[2]; }
+	float w[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+	void stashRay(float ox, float oy, float oz, float dx, float dy, float dz, float ix, float iy, float iz) {
+		w[0] = ox; w[1] = oy; w[2] = oz; w[3] = dx; w[4] = dy; w[5] = dz; w[6] = ix; w[7] = iy; w[8] = iz;
+	}
+	void loadRay(float &ox, float &oy, float &oz, float &dx, float &dy, float &dz, float &ix, float &iy, float &iz) const {
+		ox = w[0]; oy = w[1]; oz = w[2]; dx = w[3]; dy = w[4]; dz = w[5]; ix = w[6]; iy = w[7]; iz = w[8];
+	}
 };
 
 static std::string g_err;
@@ -61,7 +65,7 @@ template <bool TWO> static void Run(const WideScene &w, const lrb_ray *rays, lrb
 		RayState s;
 		stk.n.clear(); stk.t.clear();
 		if (InitRay(v, rays[i], s)) {
-			while (Step<TWO, true>(v, rays[i], s, stk, &st)) { }
+			while (Step<TWO, true>(v, s, stk, &st)) { }
 		}
 		WriteHit(s, rays[i].maxt, &hits[i]);
 	}
@@ -154,7 +158,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					if (L.state == 1 && NeedsResolve<TWO>(L.s.cur)) {
 						const size_t before = L.stk.n.size();
 						const bool wasInside = L.s.inInstance;
-						if (!Resolve<TWO, false>(v, rays[L.rayIdx], L.s, L.stk, nullptr))
+						if (!Resolve<TWO, false>(v, L.s, L.stk, nullptr))
 							L.state = 2;
 						if (TWO && wasInside && !L.s.inInstance) { ++leaveLanes; anyLeave = true; }
 						// pops performed (an entry into an instance pushes the sentinel: count at least one trip)
@@ -182,7 +186,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 						for (int l = 0; l < 32; ++l) {
 							SimLane &L = W.lane[l];
 							if (work[l] == kWorkInstance) {
-								EnterInstance<false>(v, rays[L.rayIdx], L.s, L.stk, nullptr);
+								EnterInstance<false>(v, L.s, L.stk, nullptr);
 								work[l] = WorkOf<TWO>(L.s.cur);
 								++instLanes;
 								maxInst = 1;

@@ -460,8 +460,10 @@ def index_differences(got, ref):
     return int(((got["meshIndex"] != ref["meshIndex"]) | (hit & (got["triangleIndex"] != ref["triangleIndex"]))).sum())
 
 
-def coplanar_with_reported(desc, rays, rec):
-    """True where the ray lies in the plane of the triangle `rec` names (float64 geometry)."""
+def coplanar_with_reported(desc, rays, rec, tol=1e-3):
+    """True where the ray lies in the plane of the triangle `rec` names, to within `tol` radians and `tol` x scene size
+    (float64 geometry).  1e-3: on the kitchen's needle triangles (0.3 long, 2e-3 wide) a ray 3e-4 rad off the plane still
+    gets a t from Triangle::Intersect that is 3 % off its float64 value (observed: round-2 GPU run, seed 2)."""
     p0, e1, e2, offs = S.world_triangles(desc)
     ok = rec["meshIndex"] != NULL
     flat = np.where(ok, offs[np.minimum(rec["meshIndex"], len(offs) - 1).astype(np.int64)] + rec["triangleIndex"].astype(np.int64), 0)
@@ -473,4 +475,4 @@ def coplanar_with_reported(desc, rays, rec):
     scale = float(np.linalg.norm(hi - lo))
     sin_to_plane = np.abs((n * d).sum(1))
     dist = np.abs((n * (rays["o"].astype(np.float64) - p0[flat])).sum(1))
-    return ok & (sin_to_plane < 1e-5) & (dist < 1e-5 * scale)
+    return ok & (sin_to_plane < tol) & (dist < tol * scale)

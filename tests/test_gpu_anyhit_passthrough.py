@@ -319,7 +319,10 @@ def test_film_reduce_is_the_reference_sum(dev, n_floats, n_tiles):
     with np.errstate(all="ignore"):
         for t in tiles:
             want = (want + t).astype(np.float32)
-    assert got[:n_floats].tobytes() == want.tobytes()
+    # NaN payloads are exempt: the device's add returns the canonical 0x7fffffff, SSE addss propagates the operand's
+    nan = np.isnan(want)
+    assert (np.isnan(got[:n_floats]) == nan).all()
+    assert got[:n_floats][~nan].tobytes() == want[~nan].tobytes()
     assert (got[n_floats:] == 7.0).all()
     for b in bufs + [dst]:
         b.free()
