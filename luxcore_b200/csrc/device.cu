@@ -92,7 +92,7 @@ struct lrb_scene {
 	WideScene host;                 // kept for MBVH (Update); cleared for single-level scenes
 	WideNode *dNodes;
 	TriRecord *dTris;
-	TriGate *dGates;
+	TriIds *dIds;
 	InstRecord *dInsts;
 	float *dMinv;
 	uint32_t *dMotionFirst, *dMotionLast;
@@ -496,7 +496,7 @@ static void FillView(lrb_scene *s) {
 	SceneView &v = s->view;
 	v.nodes = s->dNodes;
 	v.tris = s->dTris;
-	v.gates = s->dGates;
+	v.ids = s->dIds;
 	v.insts = s->dInsts;
 	v.minv = s->dMinv;
 	v.motionFirst = s->dMotionFirst;
@@ -517,7 +517,7 @@ static int UploadScene(lrb_scene *s) {
 	int rc;
 	if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.tris, &s->dTris, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
-	if ((rc = UploadArray(dev, s->host.gates, &s->dGates, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = UploadArray(dev, s->host.ids, &s->dIds, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.insts, &s->dInsts, &s->capInsts, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.minv, &s->dMinv, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.motionFirst, &s->dMotionFirst, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
@@ -542,7 +542,7 @@ static int UploadScene(lrb_scene *s) {
 static lrb_scene *NewScene(lrb_device *dev) {
 	lrb_scene *s = new lrb_scene();
 	s->dev = dev;
-	s->dNodes = nullptr; s->dTris = nullptr; s->dGates = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
+	s->dNodes = nullptr; s->dTris = nullptr; s->dIds = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
 	s->dMotionFirst = s->dMotionLast = nullptr; s->dInterps = nullptr;
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
@@ -561,7 +561,7 @@ int lrb_scene_free(lrb_scene *s) {
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
 	cudaStreamSynchronize(dev->stream);
-	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dGates); cudaFree(s->dInsts); cudaFree(s->dMinv);
+	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dIds); cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
 	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dWatermark); cudaFree(s->dChunkFlag);
 	{
@@ -596,7 +596,7 @@ int lrb_bvh_upload(lrb_device *dev, const lrb_bvh_node *nodes, uint32_t nNodes, 
 	// single-level scenes never change: drop the host copy (the view / info keep the bookkeeping)
 	std::vector<WideNode>().swap(s->host.wide);
 	std::vector<TriRecord>().swap(s->host.tris);
-	std::vector<TriGate>().swap(s->host.gates);
+	std::vector<TriIds>().swap(s->host.ids);
 	*out = s;
 	return LRB_OK;
 }
@@ -623,7 +623,7 @@ int lrb_mbvh_upload(lrb_device *dev, const lrb_mbvh_desc *desc, lrb_scene **out)
 	}
 	// triangles are immutable under Update; the wide nodes / instances stay on the host
 	std::vector<TriRecord>().swap(s->host.tris);
-	std::vector<TriGate>().swap(s->host.gates);
+	std::vector<TriIds>().swap(s->host.ids);
 	s->host.tris.resize(0);
 	*out = s;
 	return LRB_OK;
@@ -855,7 +855,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	if (dev->persistent && !stats) {
 		const int block = kTraceBlock;
 		int depth = std::min<int>(dev->smemDepth, (int)std::max<uint32_t>(s->info.stack_need, 4u));
-		const int smemBytes = depth * block * 8 + (two ? 9 * block * 4 : 0);     // stack columns (+ the world ray, SmemStack::stashRay)
+		const int smemBytes = (depth + 1) * block * 8 + (two ? 9 * block * 4 : 0);     // stack columns incl. the bottom entry (+ the world ray, SmemStack::stashRay)
 		int bps = 0;
 		const bool spill = s->info.stack_need > (uint32_t)depth;
 		const size_t sceneBytes = (size_t)s->info.n_wide_nodes * sizeof(WideNode) + (size_t)s->info.n_triangles * sizeof(TriRecord);

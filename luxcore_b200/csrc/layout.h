@@ -25,8 +25,10 @@
 //     reference's passes, up to the rounding discussed in traverse.h; boxes only cull, they never
 //     decide a result).  One 64-B fetch replaces up to five dependent 32-B fetches of the reference
 //     walk, and every child (node or triangle) is ordered near-to-far and culled by entry distance.
-//   TriRecord (64 B, 64-B aligned = two 256-bit loads): the three vertices pre-gathered next to
-//     meshIndex / triangleIndex, one per reference triangle leaf.
+//   TriRecord (64 B, 64-B aligned = two 256-bit loads): the three vertices pre-gathered next to the
+//     reference's gate for the triangle (exact box of its parent node, see below), one per reference
+//     triangle leaf, stored in the order of the leaves in the reference array -- the record index IS the
+//     tie-break order; meshIndex / triangleIndex live in a side table (TriIds) read once per ray.
 //   InstRecord (32 B): one per MBVH root leaf (bvhLeaf payload, bvhbuild_types.cl:33-37).
 //
 // Reference leaves carry no box of their own in the array (bvhclassicbuild.cpp:196-214): the
@@ -34,10 +36,10 @@
 // tests that cannot succeed (a hit point lies on the triangle, i.e. >= 128 ulp / 1e-5 inside the
 // grown box), so results are unchanged; see DESIGN.md "leaf boxes".
 //
-// `order` fields record the position of the leaf in the reference's depth-first array.  The
-// reference keeps the FIRST hit in array order among hits with exactly equal t (strict `t <
+// The reference keeps the FIRST hit in array order among hits with exactly equal t (strict `t <
 // rayHit->t`, bvhaccel.cpp:233); a traversal in any other order reproduces that choice by
-// preferring the smaller order on an exact tie.
+// preferring, on an exact tie, the leaf that comes first in the reference's depth-first array:
+// triangle records are stored in that order (per tree), instances carry an `order` field.
 #ifndef LRB_LAYOUT_H
 #define LRB_LAYOUT_H
 
@@ -53,6 +55,7 @@ static const uint32_t kTagTri = 0x40000000u;        // kTagTri | TriRecord index
 static const uint32_t kTagInstance = 0x80000000u;   // kTagInstance | InstRecord index
 static const uint32_t kRefIndexMask = 0x3fffffffu;
 static const uint32_t kStackSentinel = 0xfffffffeu; // pop => leave the current instance
+static const uint32_t kStackBottom = 0xfffffffdu;   // pop => the stack is empty (permanent entry under a shared-memory column)
 static const uint32_t kMaxRefIndex = 0x3ffffff0u;   // node / triangle / instance counts stay below this
 
 enum { kNodeEntry = 1 };    // WideNode::flags: one-child entry node carrying a tree's root box
@@ -68,23 +71,22 @@ struct __attribute__((aligned(64))) WideNode {
 };
 static const int kGridShift = 15;   // plane byte q sits in bits 8-15 of a float mantissa: 1 + q * 2^-15
 
-struct __attribute__((aligned(64))) TriRecord {
-	float p0[3], p1[3], p2[3];
-	uint32_t meshIndex, triangleIndex;
-	uint32_t order;         // index of the leaf in its reference BVHArrayNode array
-	uint32_t pad[4];        // 64 B: two 256-bit loads, never straddles a 128-B line
-};
-
 // The reference tests a leaf triangle exactly when the boxes of all its inner ancestors pass, and
 // its Triangle::Intersect can report a "hit" on a triangle the ray does not touch when the ray lies
 // in the triangle's plane (divisor = rounding noise).  The traversal here uses boxes that CONTAIN
-// the reference's, so it may reach such a triangle where the reference never does.  TriGate holds
+// the reference's, so it may reach such a triangle where the reference never does.  The gate is
 // the exact box of the triangle's parent node (the last, and tightest, of the reference's gates --
 // ancestor boxes are unions of their children's, so they pass whenever it does); a hit is accepted
-// only if the reference's own box arithmetic passes it.  Read once per ACCEPTED hit, not per test.
-struct __attribute__((aligned(32))) TriGate {
-	float lo[3], hi[3];
-	uint32_t pad[2];
+// only if the reference's own box arithmetic passes it.  It travels in the triangle's own record:
+// the test runs branch-free next to the triangle test, with no second, dependent fetch.
+struct __attribute__((aligned(64))) TriRecord {
+	float p0[3], p1[3], p2[3];
+	float gateLo[3], gateHi[3];
+	uint32_t order;         // index of the leaf in its reference BVHArrayNode array (layout checks; the kernels use the record index)
+};
+
+struct TriIds {
+	uint32_t meshIndex, triangleIndex;
 };
 
 struct __attribute__((aligned(16))) InstRecord {
@@ -114,7 +116,7 @@ enum {
 
 static_assert(sizeof(WideNode) == 64, "WideNode");
 static_assert(sizeof(TriRecord) == 64, "TriRecord");
-static_assert(sizeof(TriGate) == 32, "TriGate");
+static_assert(sizeof(TriIds) == 8, "TriIds");
 static_assert(sizeof(InstRecord) == 32, "InstRecord");
 static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
 
@@ -122,7 +124,7 @@ static_assert(sizeof(DevInterp) == 16 + 3 * 64 + 6 * 16, "DevInterp");
 struct SceneView {
 	const WideNode *nodes;
 	const TriRecord *tris;
-	const TriGate *gates;           // one per TriRecord
+	const TriIds *ids;              // one per TriRecord
 	const InstRecord *insts;
 	const float *minv;              // 16 floats per instance transform, row-major
 	const uint32_t *motionFirst;    // per motion system: first / last DevInterp index

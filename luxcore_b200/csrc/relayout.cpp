@@ -68,7 +68,7 @@ struct TreeInput {
 	const std::vector<DevInterp> *interps;
 };
 
-static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr) {
+static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr, TriIds *ids = nullptr) {
 	const lrb_bvh_node &nd = in.nodes[c];
 	const uint32_t mesh = nd.triangleLeaf.meshIndex;
 	if (mesh >= in.nMeshes)
@@ -85,10 +85,15 @@ static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr) {
 		tr->p1[k] = p[1][k];
 		tr->p2[k] = p[2][k];
 	}
-	tr->meshIndex = mesh;
-	tr->triangleIndex = nd.triangleLeaf.triangleIndex;
+	for (int k = 0; k < 3; ++k) {
+		tr->gateLo[k] = -std::numeric_limits<float>::infinity();
+		tr->gateHi[k] = std::numeric_limits<float>::infinity();
+	}
 	tr->order = c;
-	tr->pad[0] = tr->pad[1] = tr->pad[2] = tr->pad[3] = 0;
+	if (ids) {
+		ids->meshIndex = mesh;
+		ids->triangleIndex = nd.triangleLeaf.triangleIndex;
+	}
 }
 
 static void FillInst(const TreeInput &in, uint32_t c, InstRecord *ir) {
@@ -463,7 +468,8 @@ static double SlotSizeKey(const TreeInput &in, uint32_t c) {
 	return a == a ? a : std::numeric_limits<double>::infinity();     // NaN boxes last
 }
 
-// Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.
+// Adds reference child `c` (inner node, triangle leaf or MBVH root leaf) as the next slot of `b`.  wideOf[c] is the
+// wide-node index of an inner child and the (pre-assigned, reference-ordered) TriRecord index of a triangle leaf.
 static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, uint32_t c, const lrb_bvh_node *parent,
 		SlotBoxes *b, WideScene *out) {
 	const lrb_bvh_node &ch = in.nodes[c];
@@ -481,21 +487,21 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 		out->insts.push_back(ir);
 	} else {
 		TriRecord tr;
-		FillTri(in, c, &tr);
+		TriIds ids;
+		FillTri(in, c, &tr, &ids);
 		TriBuildBox(tr, b->lo[k], b->hi[k]);
 		SanitizeSlot(b, k);
-		b->child[k] = kTagTri | (uint32_t)out->tris.size();
-		out->tris.push_back(tr);
 		// the reference's gate for this triangle: its parent's exact box (none for a root that is a leaf)
-		TriGate g;
-		memset(&g, 0, sizeof(g));
 		for (int a = 0; a < 3; ++a) {
-			g.lo[a] = parent ? parent->bvhNode.bboxMin[a] : -kInfF;
-			g.hi[a] = parent ? parent->bvhNode.bboxMax[a] : kInfF;
-			if (g.lo[a] > g.hi[a])      // see SanitizeSlot: the reference's slab swap
-				std::swap(g.lo[a], g.hi[a]);
+			tr.gateLo[a] = parent ? parent->bvhNode.bboxMin[a] : -kInfF;
+			tr.gateHi[a] = parent ? parent->bvhNode.bboxMax[a] : kInfF;
+			if (tr.gateLo[a] > tr.gateHi[a])    // see SanitizeSlot: the reference's slab swap
+				std::swap(tr.gateLo[a], tr.gateHi[a]);
 		}
-		out->gates.push_back(g);
+		const uint32_t ti = wideOf[c];
+		b->child[k] = kTagTri | ti;
+		out->tris[ti] = tr;
+		out->ids[ti] = ids;
 	}
 }
 
@@ -516,6 +522,11 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	// The root itself is a leaf (one-triangle mesh / one-mesh dataset): wrap it in a node.
 	if (IsLeaf(nodes[0].nodeData)) {
 		SlotBoxes b;
+		if (!in.instLeaves) {
+			wideOf[0] = (uint32_t)out->tris.size();
+			out->tris.resize(out->tris.size() + 1);
+			out->ids.resize(out->tris.size());
+		}
 		AddSlot(in, wideOf, 0, nullptr, &b, out);
 		WideNode w;
 		QuantizeNode(b, kNullIndex, 0, &w);
@@ -528,9 +539,19 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 
 	// The reference tests the root's own box first (bvhaccel.cpp:245-255 with currentNode == 0);
 	// no parent holds that box, so a one-child entry node carries it.
-	// Pass 1: wide index of every inner reference node, in array order.
+	// Pass 1: wide index of every inner reference node, in array order; triangle leaves get their TriRecord index,
+	// also in array order (the record index is the reference's tie-break order, layout.h).
 	uint32_t nWide = 1;
 	uint64_t nLeafTotal = 0;
+	const size_t triStart = out->tris.size();
+	if (!in.instLeaves) {
+		uint64_t nTriLeaves = 0;
+		for (uint32_t i = 0; i < in.n; ++i)
+			if (IsLeaf(nodes[i].nodeData))
+				wideOf[i] = (uint32_t)(triStart + nTriLeaves++);
+		if (triStart + nTriLeaves >= kMaxRefIndex)
+			throw std::runtime_error("too many leaves");
+	}
 	for (uint32_t i = 0; i < in.n; ++i) {
 		if (IsLeaf(nodes[i].nodeData))
 			continue;
@@ -551,8 +572,8 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	if (in.instLeaves)
 		out->insts.reserve(out->insts.size() + nLeafTotal);
 	else {
-		out->tris.reserve(out->tris.size() + nLeafTotal);
-		out->gates.reserve(out->gates.size() + nLeafTotal);
+		out->tris.resize(triStart + nLeafTotal);
+		out->ids.resize(triStart + nLeafTotal);
 	}
 
 	{

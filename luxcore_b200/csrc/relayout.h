@@ -16,7 +16,7 @@ namespace lrb {
 struct WideScene {
 	std::vector<WideNode> wide;
 	std::vector<TriRecord> tris;
-	std::vector<TriGate> gates;
+	std::vector<TriIds> ids;
 	std::vector<InstRecord> insts;
 	std::vector<DevInterp> interps;
 	std::vector<uint32_t> motionFirst, motionLast;

@@ -40,31 +40,45 @@ static const uint32_t kCompactAutoNum = 6, kCompactAutoDen = 10;
 // ---- stacks ---------------------------------------------------------------------------------
 
 // Shared-memory column per thread + global spill (compiled out when the scene's worst-case stack
-// fits the shared depth, which the host knows at launch).  Entry i of thread t lives in words
-// [2 i * kTraceBlock + t] (reference) and [(2 i + 1) * kTraceBlock + t] (entry distance): both
-// stores of a push use one address register and every access is bank-conflict-free.
+// fits the shared depth, which the host knows at launch).  Entry i of thread t is the 8-byte word pair
+// [2 * (i * kTraceBlock + t)] = (reference, entry distance): one 64-bit store per push, one 64-bit load
+// per pop; a warp's 32 pairs are 256 contiguous bytes (two conflict-free wavefronts).
 template <bool SPILL> struct SmemStack {
-	uint32_t *base;         // &smem[threadIdx.x]
+	uint32_t *base;         // &smem[2 * threadIdx.x]
 	uint32_t *top;          // next free shared entry (== base + sp * 2 * kTraceBlock while sp <= depthSmem)
 	uint32_t *limit;        // base + depthSmem * 2 * kTraceBlock
-	uint32_t *gNode;        // &spillNodes[globalThread], stride = totalThreads (NULL when no spill is needed)
+	uint32_t *gNode;        // spill columns [spillDepth][totalThreads] (the kernel's arguments as they are: uniform)
 	float *gT;
-	uint32_t gStride;
+	uint32_t gStride;       // totalThreads
 	int over;               // SPILL: entries currently held in the global column
 
-	__device__ __forceinline__ void init(uint32_t *b, int depthSmem) { base = top = b; limit = b + depthSmem * (2 * kTraceBlock); over = 0; }
+	// Entry 0 of every column is the permanent bottom entry (kStackBottom, -inf): see Resolve.
+	__device__ __forceinline__ void init(uint32_t *smemBlock, int depthSmem) {
+		base = smemBlock + 2 * threadIdx.x;
+		st2(base, kStackBottom, -LRB_INF);
+		base += 2 * kTraceBlock;
+		top = base;
+		limit = base + depthSmem * (2 * kTraceBlock);
+		over = 0;
+	}
 	__device__ __forceinline__ void reset() { top = base; over = 0; }
+	__device__ __forceinline__ void keepBottom() { top += 2 * kTraceBlock; }
 	__device__ __forceinline__ bool room(int n) const { return !SPILL || top + n * (2 * kTraceBlock) <= limit; }
+	__device__ __forceinline__ static void st2(uint32_t *p, uint32_t n, float t) {
+		*reinterpret_cast<uint2 *>(p) = make_uint2(n, __float_as_uint(t));
+	}
+	__device__ __forceinline__ static void ld2(const uint32_t *p, uint32_t &n, float &t) {
+		const uint2 v = *reinterpret_cast<const uint2 *>(p);
+		n = v.x;
+		t = __uint_as_float(v.y);
+	}
 	__device__ __forceinline__ void pushFast(uint32_t n, float t) {
-		top[0] = n;
-		top[kTraceBlock] = __float_as_uint(t);
+		st2(top, n, t);
 		top += 2 * kTraceBlock;
 	}
 	__device__ __forceinline__ void pushFastIf(bool p, uint32_t n, float t) {
-		if (p) {
-			top[0] = n;
-			top[kTraceBlock] = __float_as_uint(t);
-		}
+		if (p)
+			st2(top, n, t);
 		top += p ? 2 * kTraceBlock : 0;
 	}
 	__device__ __forceinline__ void push(uint32_t n, float t) {
@@ -72,35 +86,62 @@ template <bool SPILL> struct SmemStack {
 			pushFast(n, t);
 			return;
 		}
-		const size_t o = (size_t)over * gStride;
+		const size_t o = spillSlot(over);
 		gNode[o] = n;
 		gT[o] = t;
 		++over;
 	}
+	// Slot of this thread's spilled entry `i`.  The address arithmetic must stay inside the (rare) branch that uses
+	// it: left alone, the compiler computes it speculatively in front of Resolve's loops, where every lane that pops
+	// pays ~20 instructions for it (round-2 SASS).  Nothing that depends on a volatile asm can move above it.
+	__device__ __forceinline__ size_t spillSlot(int i) const {
+		uint32_t z = 0;
+#if defined(__CUDA_ARCH__)
+		asm volatile("" : "+r"(z));
+#endif
+		return (size_t)i * gStride + (blockIdx.x * kTraceBlock + threadIdx.x + z);
+	}
 	__device__ __forceinline__ void pop(uint32_t &n, float &t) {
 		if (SPILL && over > 0) {
 			--over;
-			const size_t o = (size_t)over * gStride;
+			const size_t o = spillSlot(over);
 			n = gNode[o];
 			t = gT[o];
 			return;
 		}
 		top -= 2 * kTraceBlock;
-		n = top[0];
-		t = __uint_as_float(top[kTraceBlock]);
+		ld2(top, n, t);
 	}
+	__device__ __forceinline__ bool slow() const { return SPILL && over > 0; }
+	__device__ __forceinline__ void popFast(uint32_t &n, float &t) {
+		top -= 2 * kTraceBlock;
+		ld2(top, n, t);
+	}
+	// Speculative pop at the end of a phase (PopSpec): reads the top entry when `want` and the top lives in shared
+	// memory; nothing is removed until dropIf.
+	__device__ __forceinline__ bool peekIf(bool want, uint32_t &n, float &t) const {
+		const bool can = want && (!SPILL || over == 0);     // (an empty column shows its bottom entry)
+		if (can)
+			ld2(top - 2 * kTraceBlock, n, t);
+		return can;
+	}
+	__device__ __forceinline__ void dropIf(bool p) { top -= p ? 2 * kTraceBlock : 0; }
 	__device__ __forceinline__ bool empty() const { return top == base; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)((top - base) / (2 * kTraceBlock) + over); }
-	// two-level kernels: nine more words per thread behind the stack columns (the launch sizes shared memory for them)
+	// two-level kernels: nine more words per thread behind the stack columns (the launch sizes shared memory for
+	// them), word k of thread t at [(1 + depthSmem) * 2 * kTraceBlock + k * kTraceBlock + t]
+	__device__ __forceinline__ uint32_t *stash() const { return limit - threadIdx.x; }
 	__device__ __forceinline__ void stashRay(float ox, float oy, float oz, float dx, float dy, float dz, float ix, float iy, float iz) {
-		limit[0] = __float_as_uint(ox); limit[kTraceBlock] = __float_as_uint(oy); limit[2 * kTraceBlock] = __float_as_uint(oz);
-		limit[3 * kTraceBlock] = __float_as_uint(dx); limit[4 * kTraceBlock] = __float_as_uint(dy); limit[5 * kTraceBlock] = __float_as_uint(dz);
-		limit[6 * kTraceBlock] = __float_as_uint(ix); limit[7 * kTraceBlock] = __float_as_uint(iy); limit[8 * kTraceBlock] = __float_as_uint(iz);
+		uint32_t *w = stash();
+		w[0] = __float_as_uint(ox); w[kTraceBlock] = __float_as_uint(oy); w[2 * kTraceBlock] = __float_as_uint(oz);
+		w[3 * kTraceBlock] = __float_as_uint(dx); w[4 * kTraceBlock] = __float_as_uint(dy); w[5 * kTraceBlock] = __float_as_uint(dz);
+		w[6 * kTraceBlock] = __float_as_uint(ix); w[7 * kTraceBlock] = __float_as_uint(iy); w[8 * kTraceBlock] = __float_as_uint(iz);
 	}
 	__device__ __forceinline__ void loadRay(float &ox, float &oy, float &oz, float &dx, float &dy, float &dz, float &ix, float &iy, float &iz) const {
-		ox = __uint_as_float(limit[0]); oy = __uint_as_float(limit[kTraceBlock]); oz = __uint_as_float(limit[2 * kTraceBlock]);
-		dx = __uint_as_float(limit[3 * kTraceBlock]); dy = __uint_as_float(limit[4 * kTraceBlock]); dz = __uint_as_float(limit[5 * kTraceBlock]);
-		ix = __uint_as_float(limit[6 * kTraceBlock]); iy = __uint_as_float(limit[7 * kTraceBlock]); iz = __uint_as_float(limit[8 * kTraceBlock]);
+		const uint32_t *w = stash();
+		ox = __uint_as_float(w[0]); oy = __uint_as_float(w[kTraceBlock]); oz = __uint_as_float(w[2 * kTraceBlock]);
+		dx = __uint_as_float(w[3 * kTraceBlock]); dy = __uint_as_float(w[4 * kTraceBlock]); dz = __uint_as_float(w[5 * kTraceBlock]);
+		ix = __uint_as_float(w[6 * kTraceBlock]); iy = __uint_as_float(w[7 * kTraceBlock]); iz = __uint_as_float(w[8 * kTraceBlock]);
 	}
 };
 
@@ -138,6 +179,24 @@ template <int CAP> struct LocalStack {
 			t = gT[o];
 		}
 	}
+	__device__ __forceinline__ bool slow() const { return false; }
+	__device__ __forceinline__ void popFast(uint32_t &n, float &t) {
+		if (sp == 0) {
+			n = kStackBottom;
+			t = -LRB_INF;
+		} else
+			pop(n, t);
+	}
+	__device__ __forceinline__ void keepBottom() { }
+	__device__ __forceinline__ bool peekIf(bool want, uint32_t &n, float &t) const {
+		const bool can = want && sp > 0 && sp <= CAP;
+		if (can) {
+			n = node[sp - 1];
+			t = t0[sp - 1];
+		}
+		return can;
+	}
+	__device__ __forceinline__ void dropIf(bool p) { sp -= p ? 1 : 0; }
 	__device__ __forceinline__ bool empty() const { return sp == 0; }
 	__device__ __forceinline__ unsigned long long depth() const { return (unsigned long long)sp; }
 	float w[9];
@@ -232,7 +291,7 @@ __device__ __forceinline__ void StoreHitTo(lrb_rayhit *hits, uint32_t i, const l
 
 __device__ __forceinline__ void StoreHit(const TraceArgs &a, uint32_t i, const RayState &s, float rayMaxt) {
 	lrb_rayhit h;
-	WriteHit(s, rayMaxt, &h);
+	WriteHit(a.sc, s, rayMaxt, &h);
 	if (a.hits)
 		StoreHitTo(a.hits, i, h, (a.hitFlags & 1u) != 0);
 	if (a.hitsPeer)
@@ -309,7 +368,7 @@ __device__ __forceinline__ void DetectorLoop(const TraceArgs &a, const uint32_t 
 // reference's Intersect's): a ray is a hit exactly when at least one triangle passes the test and its gate.
 template <bool TWO_LEVEL, bool SPILL, bool SIGNAL, bool PREFETCH = false, bool ANYHIT = false>
 __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LRB_MINBLOCKS_1L) TracePersistent(const TraceArgs a) {
-	extern __shared__ uint32_t smem[];
+	extern __shared__ __align__(16) uint32_t smem[];
 	uint32_t rayCount = a.rayCount;
 	const uint32_t *perm = a.perm;
 	if (a.rayCountDev) {
@@ -329,9 +388,9 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 	const uint32_t gtid = blockIdx.x * kTraceBlock + threadIdx.x;
 
 	SmemStack<SPILL> stk;
-	stk.init(smem + threadIdx.x, (int)a.smemDepth);
-	stk.gNode = a.spillNode ? a.spillNode + gtid : nullptr;
-	stk.gT = a.spillT ? a.spillT + gtid : nullptr;
+	stk.init(smem, (int)a.smemDepth);
+	stk.gNode = a.spillNode;
+	stk.gT = a.spillT;
 	stk.gStride = totalThreads;
 
 	RayState s;
@@ -403,8 +462,11 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 		// node / four box tests / ordered push) or a triangle phase (one triangle per lane).  A lane
 		// holding a triangle reference waits for a triangle phase; batching the two kinds of work keeps
 		// lanes converged on incoherent rays instead of serialising them against each other.
-		// (Measured alternatives, both slower on incoherent rays: one converged pop attempt per
-		// iteration, and pops inside the phases -- lanes whose popped entry is culled then idle a phase.)
+		// (Round-2 ncu source view: Resolve's pop loop ran 2.5 trips per iteration at 3.8 of 32 lanes -- 22 % of the
+		// issue slots; it is now 5 instructions per culled entry, see Resolve.  Measured alternatives, all slower on
+		// incoherent rays: one converged pop attempt per iteration INSTEAD of the loop; pops only inside the phases --
+		// lanes whose popped entry is culled then idle a phase; and LRB_POPSPEC speculative attempts at the end of
+		// the phases in addition to the loop -- PopSpec, compiled out by default.)
 		const int floorLanes = exhausted ? 1 : (int)a.refillBelow;
 		int nLive;
 		do {
@@ -435,14 +497,17 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 			if (VoteTrianglePhase(nTri, nNode, a.triBias)) {
 				if (work == kWorkTri) {
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
-					if (ANYHIT && s.hitMesh != kNullIndex) {
+					if (ANYHIT && s.hitRef != kNullIndex) {
 						stk.reset();        // s.cur is already kNullIndex: the next Resolve finds the ray finished
 						s.inInstance = false;
 					}
+					PopSpec<TWO_LEVEL>(s, stk);
 				}
 			} else {
-				if (work == kWorkNode)
+				if (work == kWorkNode) {
 					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
+					PopSpec<TWO_LEVEL>(s, stk);
+				}
 			}
 			nLive = nTri + nNode + nInst;
 		} while (nLive >= floorLanes);
@@ -520,7 +585,7 @@ __global__ void __launch_bounds__(kTraceBlock) TraceStatic(const TraceArgs a) {
 		stk.sp = 0;
 		if (InitRay(a.sc, r, s)) {
 			while (Step<TWO_LEVEL, STATS>(a.sc, s, stk, &local)) {
-				if (ANYHIT && s.hitMesh != kNullIndex)
+				if (ANYHIT && s.hitRef != kNullIndex)
 					break;
 			}
 		}

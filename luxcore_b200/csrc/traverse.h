@@ -128,8 +128,9 @@ struct RayState {
 	float mint, maxt;       // maxt == best t so far (ray.maxt = rayHit->t in the reference)
 	float time;
 	float b1, b2;
-	uint32_t hitMesh, hitTri;
-	uint32_t bestInst, bestTri;     // reference array order of the current best hit
+	uint32_t hitRef;                // TriRecord index of the current best hit (== its reference array order), or kNullIndex
+	uint32_t hitMeshOffset;         // two-level: mesh offset of the instance the best hit lies in
+	uint32_t bestInst;              // two-level: reference array order of that instance
 	uint32_t curInstOrder, curMeshOffset;
 	// What to process next: a wide-node index, kTagTri | triangle, kTagInstance | instance,
 	// kStackSentinel, or kNullIndex when the stack must be popped (Resolve).
@@ -365,8 +366,9 @@ LRB_HD bool InitRay(const SceneView &sc, const lrb_ray &ray, RayState &s) {
 	s.maxt = ray.maxt;      // rayHit->t = ray->maxt
 	s.time = ray.time;
 	s.b1 = 0.f; s.b2 = 0.f;
-	s.hitMesh = kNullIndex; s.hitTri = kNullIndex;
-	s.bestInst = 0; s.bestTri = 0;
+	s.hitRef = kNullIndex;
+	s.hitMeshOffset = 0;
+	s.bestInst = 0;
 	s.curInstOrder = 0; s.curMeshOffset = 0;
 	s.inInstance = false;
 	if (!sc.nWide) {
@@ -444,62 +446,104 @@ LRB_HD void EnterInstance(const SceneView &sc, RayState &s, STACK &stk, TraceSta
 	s.cur = ir.x;
 }
 
+// A popped reference that is neither a wide node nor a triangle (cur >= kTagInstance; not culled).  Returns true when
+// the pop loop ends with it: an instance reference (the caller runs EnterInstance), or the bottom of the stack
+// (*bottom set: the ray is finished).  The sentinel takes the ray back to world space (mbvhaccel.cpp:271-283, from
+// the stash); it and the kNullIndex reference of an empty slot (only NaN / inf rays push those) are popped over.
+template <bool TWO_LEVEL, class STACK>
+LRB_HD bool RarePopped(RayState &s, STACK &stk, const uint32_t cur, bool *bottom) {
+	if (cur == kStackBottom) {
+		*bottom = true;
+		return true;
+	}
+	if (TWO_LEVEL) {
+		if (cur == kStackSentinel) {
+			stk.loadRay(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, s.ix, s.iy, s.iz);
+			s.inInstance = false;
+			return false;
+		}
+		return cur != kNullIndex;
+	}
+	return false;
+}
+
 // Turns s.cur into a wide-node, triangle or instance reference: pops the stack while there is nothing
 // to do or the popped entry lies behind the best hit, and leaves leaf trees (sentinel).  An instance
 // reference is returned as it is (EnterInstance follows).  Returns false when the ray is finished.
-// STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / empty() / depth() / room(n) and a
-// nine-float side slot stashRay(o, d, 1/d) / loadRay(...) (the world ray while the traversal is inside an instance).
+// An entry's distance was recorded at push time; a closer hit found since then culls the entry (same effect as
+// running the box test now: t0 > min(maxt, tFar)).  Sentinel and bottom carry -inf and are never culled.
+// STACK provides push(uint32_t ref, float t0) / pop(uint32_t&, float&) / depth() / room(n), a nine-float side slot
+// stashRay(o, d, 1/d) / loadRay(...) (the world ray while the traversal is inside an instance), and
+// slow() / popFast() / keepBottom(): while slow() the top entry lives in the global spill column and pop() must be
+// used; afterwards (pops never make a stack slow again) popFast() takes entries without looking at the spill and
+// returns (kStackBottom, -inf) from an empty stack -- the shared-memory columns keep that entry permanently
+// under the first real one, so the divergent loop below needs no emptiness test (it runs a different number of
+// trips on every lane and every instruction in it counts); keepBottom() undoes the pop of the bottom entry.
 template <bool TWO_LEVEL, bool STATS, class STACK>
 LRB_HD bool Resolve(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
 	uint32_t cur = s.cur;
-	bool alive = true;
+	bool bottom = false;
 	// On entry s.cur is kNullIndex (pop), or -- two-level -- an instance reference, which is returned as it is.
-	// Single exit: lanes that finish and lanes that found work leave the loop together.
+	// Single exit: lanes that finish and lanes that found work leave the loops together.
 	if (!TWO_LEVEL || !IsInstanceRef(cur)) {
-		for (;;) {
-			if (stk.empty()) {
-				alive = false;
-				cur = kNullIndex;
-				break;
-			}
+		bool found = false;
+		while (stk.slow()) {
 			float t0;
 			stk.pop(cur, t0);
-			// entry distance recorded at push time; a closer hit found since then culls the entry
-			// (same effect as running the box test now: t0 > min(maxt, tFar)).  The sentinel is
-			// pushed with -inf and never culled.
 			if (t0 > s.maxt)
 				continue;
-			if (cur < kTagInstance)
-				break;                  // a wide node or a triangle: the common case
-			if (TWO_LEVEL) {
-				if (cur == kStackSentinel) {
-					// leave the instance: back to the world-space ray (mbvhaccel.cpp:271-283), from the stash
-					stk.loadRay(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, s.ix, s.iy, s.iz);
-					s.inInstance = false;
-					continue;
-				}
-				if (cur != kNullIndex)
-					break;              // an instance reference: the caller runs EnterInstance
+			if (cur < kTagInstance || RarePopped<TWO_LEVEL>(s, stk, cur, &bottom)) {
+				found = true;
+				break;
 			}
-			// kNullIndex: the reference of an empty slot (NaN / inf rays only) -- pop on
+		}
+		if (!found) {
+			for (;;) {
+				float t0;
+				stk.popFast(cur, t0);
+				if (t0 > s.maxt)
+					continue;
+				if (cur < kTagInstance)
+					break;                  // a wide node or a triangle: the common case
+				if (RarePopped<TWO_LEVEL>(s, stk, cur, &bottom))
+					break;
+			}
+		}
+		if (bottom) {
+			stk.keepBottom();
+			cur = kNullIndex;
 		}
 	}
 	s.cur = cur;
-	return alive;
+	return !bottom;
 }
 
-// One pop attempt (warp-converged form of Resolve's inner loop for the persistent kernel): takes the
-// top entry; an entry behind the best hit leaves s.cur empty (the lane tries again at the next
-// attempt).  Returns false when the stack was empty, i.e. the ray is finished.
-template <class STACK>
-LRB_HD bool PopOnce(RayState &s, STACK &stk) {
-	if (stk.empty())
-		return false;
-	uint32_t c;
-	float t0;
-	stk.pop(c, t0);
-	s.cur = (t0 > s.maxt) ? kNullIndex : c;
-	return true;
+// Speculative pop at the end of a phase: a lane that is left with nothing to do (triangle tested; node without a
+// child on the ray) takes the top entry of its stack while the lanes of the phase are still converged.  An entry
+// behind the best hit is dropped and leaves s.cur empty; the sentinel, the bottom of the stack, kNullIndex
+// entries and spilled entries are left where they are: Resolve deals with all of those at the next iteration.  Purely a scheduling
+// device -- the entries come off the stack in the same order with the same culling rule as in Resolve.
+// STACK::peekIf(want, ref&, t0&) -> bool reads the top entry if there is one at hand; dropIf(bool) removes it.
+#ifndef LRB_POPSPEC
+#define LRB_POPSPEC 0       /* attempts per phase end; 0 = none (every pop happens in Resolve).  Measured on B200, kitchen
+                             * bounce-2 (gpurun_out/r02_measure_kitchen_c5_*): 0 -> 5.03 ms, 1 -> 5.08 ms, 2 -> 5.22 ms per 16 Mi rays:
+                             * what the attempts take out of Resolve's loop (65 -> 35 warp instructions per ray) they add to
+                             * the phases, where every lane of the phase pays for them. */
+#endif
+template <bool TWO_LEVEL, class STACK>
+LRB_HD void PopSpec(RayState &s, STACK &stk) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int attempt = 0; attempt < LRB_POPSPEC; ++attempt) {
+		uint32_t c = kNullIndex;
+		float t0 = 0.f;
+		const bool can = stk.peekIf(s.cur == kNullIndex, c, t0);
+		const bool take = can && c < kStackBottom;      // not the bottom, the sentinel or an empty slot's kNullIndex
+		stk.dropIf(take);
+		if (take)
+			s.cur = (t0 > s.maxt) ? kNullIndex : c;
+	}
 }
 
 // Tests the triangle s.cur refers to.
@@ -511,28 +555,28 @@ LRB_HD void TriStep(const SceneView &sc, RayState &s, TraceStats *stats) {
 	const uint32_t triIndex = s.cur & kRefIndexMask;
 	const char *tp = reinterpret_cast<const char *>(sc.tris + triIndex);
 	s.cur = kNullIndex;
-	const F8 a = Ld256(tp), b = Ld256(tp + 32);    // p0 p1 p2.xy | p2.z mesh tri order pad
+	const F8 a = Ld256(tp), b = Ld256(tp + 32);    // p0 p1 p2.xy | p2.z gateLo gateHi order
 	if (STATS) stats->triangles++;
 	float t, b1, b2;
 	const bool hit = TriangleTest(s, a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7], b.v[0], &t, &b1, &b2);
-	const uint32_t mesh = LRB_F2U(b.v[1]), tri = LRB_F2U(b.v[2]), order = LRB_F2U(b.v[3]);
 	const uint32_t instOrder = TWO_LEVEL ? s.curInstOrder : 0u;
 	const bool closer = t < s.maxt;
-	const bool tieWin = (t == s.maxt) & (s.hitMesh != kNullIndex) &
-			((instOrder < s.bestInst) | ((instOrder == s.bestInst) & (order < s.bestTri)));
-	if (hit & (closer | tieWin)) {
-		// the reference's gate (layout.h TriGate): its parent's exact box with the reference's own
-		// arithmetic.  A genuine hit always passes (the hit point is inside the triangle's grown box).
-		const F8 g = Ld256(sc.gates + triIndex);
-		const float ge = ChildEntry(s, s.ix < 0.f, s.iy < 0.f, s.iz < 0.f, g.v[0], g.v[1], g.v[2], g.v[3], g.v[4], g.v[5]);
-		if (!(ge < LRB_INF))
-			return;
+	// (records are stored in reference order: the record index is the tie-break order, layout.h)
+	const bool tieWin = (t == s.maxt) & (s.hitRef != kNullIndex) &
+			((instOrder < s.bestInst) | ((instOrder == s.bestInst) & (triIndex < s.hitRef)));
+	// the reference's gate (layout.h): the exact box of the triangle's parent with the reference's own
+	// arithmetic, against the ray as it is BEFORE this hit shortens it.  A genuine hit always passes (the
+	// hit point is inside the triangle's grown box).  Evaluated for every tested triangle, next to the
+	// triangle test: no second fetch and no divergent side path for the accepted hits.
+	const float ge = ChildEntry(s, s.ix < 0.f, s.iy < 0.f, s.iz < 0.f, b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6]);
+	if (hit & (closer | tieWin) & (ge < LRB_INF)) {
 		s.maxt = t;
 		s.b1 = b1; s.b2 = b2;
-		s.hitMesh = TWO_LEVEL ? (mesh + s.curMeshOffset) : mesh;
-		s.hitTri = tri;
-		s.bestInst = instOrder;
-		s.bestTri = order;
+		s.hitRef = triIndex;
+		if (TWO_LEVEL) {
+			s.hitMeshOffset = s.curMeshOffset;
+			s.bestInst = instOrder;
+		}
 	}
 }
 
@@ -669,8 +713,8 @@ LRB_HD bool Step(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats
 
 // Final RayHit.  Miss payload: t = ray.maxt, meshIndex = triangleIndex = NULL_INDEX (bvh.cl:219-223);
 // b1/b2 are written as 0 (the reference leaves them unspecified).
-LRB_HD void WriteHit(const RayState &s, float rayMaxt, lrb_rayhit *hit) {
-	if (s.hitMesh == kNullIndex) {
+LRB_HD void WriteHit(const SceneView &sc, const RayState &s, float rayMaxt, lrb_rayhit *hit) {
+	if (s.hitRef == kNullIndex) {
 		hit->t = rayMaxt;
 		hit->b1 = 0.f; hit->b2 = 0.f;
 		hit->meshIndex = kNullIndex;
@@ -678,8 +722,9 @@ LRB_HD void WriteHit(const RayState &s, float rayMaxt, lrb_rayhit *hit) {
 	} else {
 		hit->t = s.maxt;
 		hit->b1 = s.b1; hit->b2 = s.b2;
-		hit->meshIndex = s.hitMesh;
-		hit->triangleIndex = s.hitTri;
+		const TriIds id = sc.ids[s.hitRef];     // (two-level: mesh index relative to the instance's leaf tree, which holds one mesh)
+		hit->meshIndex = id.meshIndex + s.hitMeshOffset;
+		hit->triangleIndex = id.triangleIndex;
 	}
 }
 

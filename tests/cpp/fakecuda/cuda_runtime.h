@@ -19,6 +19,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__
+#define __align__(n) __attribute__((aligned(n)))
 #define __restrict__ __restrict
 
 struct float4 { float x, y, z, w; };

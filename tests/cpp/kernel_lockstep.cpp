@@ -77,7 +77,7 @@ void __syncwarp() {
 #include "trace_kernels.cuh"
 
 namespace lrb {
-uint32_t smem[kTraceBlock * (2 * 64 + 9)];        // `extern __shared__ uint32_t smem[]` of the kernels: one block at a time
+__attribute__((aligned(16))) uint32_t smem[kTraceBlock * (2 * 65 + 9)];        // `extern __shared__ uint32_t smem[]` of the kernels: one block at a time
 }
 
 using namespace lrb;

@@ -25,6 +25,18 @@ struct HostStack {
 	void pushFast(uint32_t a, float b) { push(a, b); }
 	void pushFastIf(bool p, uint32_t a, float b) { if (p) push(a, b); }
 	void pop(uint32_t &a, float &b) { a = n.back(); b = t.back(); n.pop_back(); t.pop_back(); }
+	bool slow() const { return false; }
+	void popFast(uint32_t &a, float &b) {
+		if (n.empty()) { a = kStackBottom; b = -LRB_INF; }
+		else pop(a, b);
+	}
+	void keepBottom() { }
+	bool peekIf(bool want, uint32_t &a, float &b) const {
+		if (!want || n.empty()) return false;
+		a = n.back(); b = t.back();
+		return true;
+	}
+	void dropIf(bool p) { if (p) { n.pop_back(); t.pop_back(); } }
 	bool empty() const { return n.empty(); }
 	unsigned long long depth() const { return n.size(); }
 	float w[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
@@ -43,7 +55,7 @@ static SceneView View(const WideScene &w) {
 	memset(&v, 0, sizeof(v));
 	v.nodes = w.wide.data();
 	v.tris = w.tris.data();
-	v.gates = w.gates.data();
+	v.ids = w.ids.data();
 	v.insts = w.insts.data();
 	v.minv = w.minv.data();
 	v.motionFirst = w.motionFirst.data();
@@ -67,7 +79,7 @@ template <bool TWO> static void Run(const WideScene &w, const lrb_ray *rays, lrb
 		if (InitRay(v, rays[i], s)) {
 			while (Step<TWO, true>(v, s, stk, &st)) { }
 		}
-		WriteHit(s, rays[i].maxt, &hits[i]);
+		WriteHit(v, s, rays[i].maxt, &hits[i]);
 	}
 	if (stats6) {
 		stats6[0] = st.rays; stats6[1] = st.wideNodes; stats6[2] = st.triangles;
@@ -95,8 +107,14 @@ struct SimWarp {
 
 template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n,
 		uint32_t nWarps, uint32_t refillBelow, uint32_t triBias, unsigned long long *out16) {
-	const uint32_t instBias = triBias >> 16;      // packed by the Python wrapper: low 16 bits tri_bias, high 16 bits inst_bias
+	const uint32_t instBias = (triBias >> 16) & 0x7fffu;      // packed by the Python wrapper: low 16 bits tri_bias, bits 16-30 inst_bias,
+	const bool specPop = !(triBias >> 31);                    // bit 31: WITHOUT the speculative pop at the end of the phases
 	triBias &= 0xffffu;
+	// experimental policy (refillBelow bits 8-15 = triMin > 0): every iteration runs the node phase for all lanes that hold a
+	// node and THEN the triangle phase for all lanes that hold a triangle (including those that just got one), the latter
+	// only when at least triMin lanes are ready or no node phase ran
+	const uint32_t triMin = (refillBelow >> 8) & 0xffu;
+	refillBelow &= 0xffu;
 	const SceneView v = View(w);
 	std::vector<SimWarp> warps(nWarps);
 	uint32_t counter = 0;
@@ -114,7 +132,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 			for (int l = 0; l < 32; ++l) {
 				SimLane &L = W.lane[l];
 				if (L.state == 2) {
-					WriteHit(L.s, rays[L.rayIdx].maxt, &hits[L.rayIdx]);
+					WriteHit(v, L.s, rays[L.rayIdx].maxt, &hits[L.rayIdx]);
 					L.state = 0;
 					anyStore = true;
 				}
@@ -137,7 +155,7 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					++traced;
 					L.stk.n.clear(); L.stk.t.clear();
 					if (InitRay(v, rays[slot], L.s)) L.state = 1;
-					else WriteHit(L.s, rays[slot].maxt, &hits[slot]);
+					else WriteHit(v, L.s, rays[slot].maxt, &hits[slot]);
 				}
 				if (base + (uint32_t)nIdle >= n) W.exhausted = true;
 			}
@@ -198,6 +216,41 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					}
 				}
 				instTrips += maxInst;
+				if (triMin) {
+					bool ranNode = false;
+					if (nNode) {
+						ranNode = true;
+						++nodePhases;
+						nodeLanes += (unsigned long long)nNode;
+						for (int l = 0; l < 32; ++l) {
+							SimLane &L = W.lane[l];
+							if (work[l] == kWorkNode) {
+								NodeStep<TWO, false>(v, L.s, L.stk, nullptr);
+								work[l] = (L.s.cur != kNullIndex && L.s.cur < kTagInstance && (L.s.cur & kTagTri)) ? kWorkTri : kWorkNone;
+							}
+						}
+					}
+					int nT = 0;
+					for (int l = 0; l < 32; ++l) nT += work[l] == kWorkTri;
+					if (nT && ((uint32_t)nT >= triMin || !ranNode)) {
+						++triPhases;
+						triLanes += (unsigned long long)nT;
+						int accepted = 0;
+						for (int l = 0; l < 32; ++l) {
+							SimLane &L = W.lane[l];
+							if (work[l] == kWorkTri) {
+								const float before = L.s.maxt;
+								const uint32_t bi = L.s.bestInst, hm = L.s.hitRef;
+								TriStep<TWO, false>(v, L.s, nullptr);
+								if (L.s.maxt != before || L.s.bestInst != bi || L.s.hitRef != hm) ++accepted;
+							}
+						}
+						if (accepted) { ++gatePhases; gateLanes += (unsigned long long)accepted; }
+					}
+					// live lanes for the loop condition
+					nTri = 0; nNode = 0;
+					for (int l = 0; l < 32; ++l) nNode += W.lane[l].state == 1;
+				} else
 				if (VoteTrianglePhase(nTri, nNode, triBias)) {
 					if (nTri) {
 						++triPhases;
@@ -208,9 +261,10 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 							SimLane &L = W.lane[l];
 							if (work[l] == kWorkTri) {
 								const float before = L.s.maxt;
-								const uint32_t bt = L.s.bestTri, bi = L.s.bestInst, hm = L.s.hitMesh;
+								const uint32_t bi = L.s.bestInst, hm = L.s.hitRef;
 								TriStep<TWO, false>(v, L.s, nullptr);
-								if (L.s.maxt != before || L.s.bestTri != bt || L.s.bestInst != bi || L.s.hitMesh != hm) ++accepted;
+								if (L.s.maxt != before || L.s.bestInst != bi || L.s.hitRef != hm) ++accepted;
+								if (specPop) PopSpec<TWO>(L.s, L.stk);
 							}
 						}
 						if (accepted) { ++gatePhases; gateLanes += (unsigned long long)accepted; }
@@ -227,8 +281,10 @@ template <bool TWO> static void WarpSim(const WideScene &w, const lrb_ray *rays,
 					idlePhaseLanes += (unsigned long long)nTri;
 					for (int l = 0; l < 32; ++l) {
 						SimLane &L = W.lane[l];
-						if (work[l] == kWorkNode)
+						if (work[l] == kWorkNode) {
 							NodeStep<TWO, false>(v, L.s, L.stk, nullptr);
+							if (specPop) PopSpec<TWO>(L.s, L.stk);
+						}
 					}
 				}
 				nLive = nTri + nNode + nInst;
@@ -299,9 +355,9 @@ void emu_copy_tris(void *wp, void *dst) {
 	const WideScene *w = (const WideScene *)wp;
 	memcpy(dst, w->tris.data(), w->tris.size() * sizeof(TriRecord));
 }
-void emu_copy_gates(void *wp, void *dst) {
+void emu_copy_ids(void *wp, void *dst) {
 	const WideScene *w = (const WideScene *)wp;
-	memcpy(dst, w->gates.data(), w->gates.size() * sizeof(TriGate));
+	memcpy(dst, w->ids.data(), w->ids.size() * sizeof(TriIds));
 }
 
 void emu_trace(void *wp, const lrb_ray *rays, lrb_rayhit *hits, uint32_t n, unsigned long long *stats6) {

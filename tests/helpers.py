@@ -200,7 +200,7 @@ class Emu:
             L.emu_free.argtypes = [C.c_void_p]
             L.emu_info.argtypes = [C.c_void_p, C.c_void_p]
             L.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
-            for f in (L.emu_copy_nodes, L.emu_copy_tris, L.emu_copy_gates):
+            for f in (L.emu_copy_nodes, L.emu_copy_tris, L.emu_copy_ids):
                 f.argtypes = [C.c_void_p, C.c_void_p]
             L.emu_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
             L.emu_scene_view_size.restype = C.c_uint32
@@ -248,23 +248,22 @@ class Emu:
 
     WIDE_DTYPE = np.dtype([("org", "<f4", 3), ("exps", "<u4"), ("child", "<u4", 4), ("qlo", "<u4", 3), ("qhi", "<u4", 3),
                            ("next", "<u4"), ("flags", "<u4")])
-    TRI_DTYPE = np.dtype([("p0", "<f4", 3), ("p1", "<f4", 3), ("p2", "<f4", 3), ("meshIndex", "<u4"), ("triangleIndex", "<u4"),
-                          ("order", "<u4"), ("pad", "<u4", 4)])
-    GATE_DTYPE = np.dtype([("lo", "<f4", 3), ("hi", "<f4", 3), ("pad", "<u4", 2)])
+    TRI_DTYPE = np.dtype([("p0", "<f4", 3), ("p1", "<f4", 3), ("p2", "<f4", 3), ("gateLo", "<f4", 3), ("gateHi", "<f4", 3), ("order", "<u4")])
+    IDS_DTYPE = np.dtype([("meshIndex", "<u4"), ("triangleIndex", "<u4")])
 
     def arrays(self):
-        """The re-laid-out arrays exactly as they would be uploaded: (wide nodes, triangle records, gates)."""
-        assert self.WIDE_DTYPE.itemsize == 64 and self.TRI_DTYPE.itemsize == 64 and self.GATE_DTYPE.itemsize == 32
+        """The re-laid-out arrays exactly as they would be uploaded: (wide nodes, triangle records, triangle ids)."""
+        assert self.WIDE_DTYPE.itemsize == 64 and self.TRI_DTYPE.itemsize == 64 and self.IDS_DTYPE.itemsize == 8
         i = self.info()
         wide = np.zeros(i["wide"], dtype=self.WIDE_DTYPE)
         tris = np.zeros(i["tris"], dtype=self.TRI_DTYPE)
-        gates = np.zeros(i["tris"], dtype=self.GATE_DTYPE)
+        ids = np.zeros(i["tris"], dtype=self.IDS_DTYPE)
         if i["wide"]:
             self.lib().emu_copy_nodes(self.h, wide.ctypes.data)
         if i["tris"]:
             self.lib().emu_copy_tris(self.h, tris.ctypes.data)
-            self.lib().emu_copy_gates(self.h, gates.ctypes.data)
-        return wide, tris, gates
+            self.lib().emu_copy_ids(self.h, ids.ctypes.data)
+        return wide, tris, ids
 
     def trace(self, rays, want_stats=False):
         rays = np.ascontiguousarray(rays)
@@ -345,9 +344,11 @@ WARP_SIM_FIELDS = ["rays", "outer_iters", "inner_iters", "node_phases", "tri_pha
                    "pop_lanes", "gate_phases", "gate_lanes", "store_phases", "refills", "waiting_lanes", "slow_push_phases", "slow_push_lanes", "instance_trips", "instance_lanes", "leave_trips", "leave_lanes"]
 
 
-def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8):
-    """Scheduling model of TracePersistent (tests/cpp/wide_emulation.cpp WarpSim): -> (hits, counts)."""
-    tri_bias = (tri_bias & 0xFFFF) | (inst_bias << 16)
+def warp_sim(emu, rays, n_warps=64, refill_below=24, tri_bias=8, inst_bias=8, spec_pop=True, tri_min=0):
+    """Scheduling model of TracePersistent (tests/cpp/wide_emulation.cpp WarpSim): -> (hits, counts).
+    spec_pop=False: the loop without the speculative pop at the end of the phases (the round-1 kernel)."""
+    tri_bias = (tri_bias & 0xFFFF) | ((inst_bias & 0x7FFF) << 16) | (0 if spec_pop else 1 << 31)
+    refill_below = (refill_below & 0xFF) | ((tri_min & 0xFF) << 8)       # experimental "both phases per iteration" policy
     rays = np.ascontiguousarray(rays)
     hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
     out = np.zeros(20, dtype=np.uint64)

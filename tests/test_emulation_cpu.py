@@ -76,13 +76,17 @@ def test_quantized_nodes_contain_the_reference_boxes(name, tree_type):
     nodes = bvh.nodes()
     verts, offs = H.flattened_from_oracle(desc, osc)
     emu = H.Emu.bvh(nodes, verts, offs)
-    wide, tris, gates = emu.arrays()
+    wide, tris, ids = emu.arrays()
     raw = nodes.view(np.uint8).reshape(len(nodes), 32)
     ref_box = raw[:, :24].copy().view(np.float32).reshape(-1, 6).astype(np.float64)
     nd = nodes["nodeData"]
     is_leaf = (nd >> 31) == 1
     assert len(tris) == int(is_leaf.sum())
-    assert sorted(tris["order"].tolist()) == np.nonzero(is_leaf)[0].tolist()
+    # triangle records are stored in the order of the leaves in the reference array (the record index is the tie-break order)
+    assert tris["order"].tolist() == np.nonzero(is_leaf)[0].tolist()
+    leaf_raw = raw[tris["order"]]
+    assert np.array_equal(ids["meshIndex"], leaf_raw[:, 12:16].copy().view(np.uint32).ravel())
+    assert np.array_equal(ids["triangleIndex"], leaf_raw[:, 16:20].copy().view(np.uint32).ravel())
 
     # parent of every reference node (depth-first array, skip index = end of the subtree)
     parent = np.full(len(nodes), -1, dtype=np.int64)
@@ -97,7 +101,7 @@ def test_quantized_nodes_contain_the_reference_boxes(name, tree_type):
     # gates: exact box of the parent
     par = parent[tris["order"]]
     assert (par >= 0).all()
-    assert np.array_equal(gates["lo"].astype(np.float64), ref_box[par, :3]) and np.array_equal(gates["hi"].astype(np.float64), ref_box[par, 3:])
+    assert np.array_equal(tris["gateLo"].astype(np.float64), ref_box[par, :3]) and np.array_equal(tris["gateHi"].astype(np.float64), ref_box[par, 3:])
 
     org = wide["org"].astype(np.float64)
     eb = np.stack([(wide["exps"] >> (8 * a)) & 0xFF for a in range(3)], axis=1).astype(np.int64)

@@ -114,9 +114,11 @@ def main():
     verts, offs = H.flattened_from_oracle(desc, osc)
     emu = H.Emu.bvh(nodes, verts, offs)
     ref, st = emu.trace(rays, want_stats=True)
-    hits, c = H.warp_sim(emu, rays, n_warps=256, refill_below=refill, tri_bias=bias)
+    spec = os.environ.get("LRB_MODEL_SPEC_POP", "1") != "0"
+    hits, c = H.warp_sim(emu, rays, n_warps=256, refill_below=refill, tri_bias=bias, spec_pop=spec, tri_min=int(os.environ.get("LRB_MODEL_TRI_MIN", "0")))
     assert hits.tobytes() == ref.tobytes(), "scheduling model and per-ray emulation disagree"
     instr, lanes = model(c)
+    print("speculative pop in the phases:", spec, {k: round(v / c["rays"], 3) for k, v in c.items()})
     r = c["rays"]
     print("scene %s: ref nodes %d wide %d | per ray: nodes %.2f tris %.2f | node phases %.2f (%.1f lanes) tri phases %.2f (%.1f lanes) "
           "pop trips %.2f inner %.2f" % (scene, nodes.shape[0], emu.info()["wide"], st["wide_nodes"] / r, st["triangles"] / r,
