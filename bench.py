@@ -323,7 +323,7 @@ def main():
     #   nccl : trace, then torch.distributed gather (the baseline way)
     dev_view = capi.Device.borrow(sess.native_device())
     gather_mode = args.gather if world > 1 else "none"
-    pipeline = gather_mode == "p2p" and args.chunks == 0 and not args.no_pipeline
+    pipeline = gather_mode == "p2p" and not args.no_pipeline
     n_buf = 2 if pipeline else 1
     gbuf_local, gbuf_peer, my_dst, glist = [], [], [], None
     hits_buf = [hits] + ([torch.empty((n, 20), dtype=torch.uint8, device=device)] if pipeline else [])

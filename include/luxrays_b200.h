@@ -283,6 +283,22 @@ LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_
  * A completion signal for the gathering rank belongs behind this wait. */
 LRB_API int lrb_gather_wait(lrb_device *dev, void *cuda_stream, int which);
 
+/* ---- BVH construction on the device ------------------------------------------------------------- */
+/* Replaces BuildEmbreeBVHMorton (src/luxrays/core/bvh/bvhembreebuild.cpp:218-336 with rtcBVHBuilderMorton,
+ * declared in include/luxrays/core/bvh/bvhbuild.h:68-69): a linear BVH (63-bit Morton codes, radix sort, Karras
+ * radix tree, k-ary collapse by depth) built on the GPU from the n_leaves leaf boxes the accelerators hand their
+ * builders (BVHAccel::Init bvhaccel.cpp:100-135, MBVHAccel root tree mbvhaccel.cpp:132-200): leaf_boxes = 6
+ * floats per leaf (min xyz, max xyz), HOST memory.  out_nodes (HOST, capacity >= 2 * n_leaves - 1) receives the
+ * depth-first skip-list array of bvhclassicbuild.cpp:181-220 with at most tree_type (2 / 4 / 8) children per node;
+ * a leaf node carries the INDEX of its input leaf in triangleLeaf.v[0] (== bvhLeaf.leafIndex) and zeros elsewhere:
+ * the caller, which owns the mesh / instance tables, writes the leaf payload in.  Synchronous. */
+typedef struct {
+	double h2d_ms, sort_ms, tree_ms, emit_ms, d2h_ms;   /* CUDA-event times of the stages */
+	uint32_t kernels;                                   /* own kernels launched (CUB's passes not counted) */
+} lrb_build_timings;
+LRB_API int lrb_build_lbvh(lrb_device *dev, const float *leaf_boxes, uint32_t n_leaves, uint32_t tree_type,
+		lrb_bvh_node *out_nodes, uint32_t out_capacity, uint32_t *n_nodes, lrb_build_timings *timings);
+
 /* ---- multi-GPU: film merge over NVLink -------------------------------------------------------- */
 /* The sum of per-GPU film planes that replaces the host-side merge of per-device films
  * (PathOCLRenderEngine::MergeThreadFilms -> Film::AddFilm, src/slg/engines/pathocl/pathocl.cpp:184-201,

@@ -34,6 +34,7 @@ EXPORTS = [
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
     "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait", "lrb_film_reduce",
+    "lrb_build_lbvh",
 ]
 
 
@@ -65,6 +66,11 @@ class Counters(C.Structure):
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("wide_nodes", C.c_uint64), ("triangles", C.c_uint64),
                 ("instances", C.c_uint64), ("motion_samples", C.c_uint64), ("max_stack", C.c_uint64)]
+
+
+class BuildTimings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("sort_ms", C.c_double), ("tree_ms", C.c_double), ("emit_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("kernels", C.c_uint32)]
 
 
 class LrbError(RuntimeError):
@@ -124,6 +130,7 @@ def lib():
             "lrb_trace_gather": (i32, [vp, vp, vp, u32, vp, u32]),
             "lrb_gather_wait": (i32, [vp, vp, i32]),
             "lrb_film_reduce": (i32, [vp, C.POINTER(vp), u32, vp, u64, u64]),
+            "lrb_build_lbvh": (i32, [vp, vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(BuildTimings)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -256,6 +263,21 @@ class Device:
 
     def ipc_close_handle(self, devptr):
         _check(lib().lrb_ipc_close_handle(self.h, C.c_void_p(devptr)))
+
+    # ---- BVH construction on the device ----
+    def build_lbvh(self, leaf_boxes, tree_type=4, node_dtype=None):
+        """GPU linear-BVH builder (lrb_build_lbvh): leaf_boxes [n, 6] float32 (min xyz, max xyz) -> (BVHArrayNode array
+        as a [n_nodes] array of 32-byte records, BuildTimings).  Leaf records carry the input index of their leaf in
+        their first word; the caller writes the leaf payload in."""
+        boxes = np.ascontiguousarray(leaf_boxes, dtype=np.float32).reshape(-1, 6)
+        n = boxes.shape[0]
+        dt = node_dtype or np.dtype([("w", "<u4", 6), ("nodeData", "<u4"), ("pad0", "<i4")])
+        assert dt.itemsize == 32
+        out = np.zeros(max(1, 2 * n), dtype=dt)
+        total = C.c_uint32()
+        tm = BuildTimings()
+        _check(lib().lrb_build_lbvh(self.h, _ptr(boxes), n, tree_type, _ptr(out), out.shape[0], C.byref(total), C.byref(tm)))
+        return out[:total.value].copy(), tm
 
     # ---- scenes ----
     def upload_bvh(self, nodes, verts, mesh_vertex_offsets):

@@ -24,6 +24,7 @@
 #include "relayout.h"
 #include "trace_kernels.cuh"
 #include "batch_kernels.cuh"
+#include "build_kernels.cuh"
 
 using namespace lrb;
 
@@ -1088,6 +1089,112 @@ int lrb_film_reduce(lrb_device *dev, const float *const *tilesDev, uint32_t nTil
 	return LRB_OK;
 }
 
+// ---- BVH construction on the device (build_kernels.cuh) ---------------------------------------------------
+
+int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, lrb_bvh_node *outNodes,
+		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
+	if (!leafBoxes || !outNodes || !nNodes)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	if (treeType != 2 && treeType != 4 && treeType != 8)
+		return Fail(LRB_ERR_INVALID, "tree type must be 2, 4 or 8 (bvhaccel.cpp:51)");
+	if (nLeaves == 0 || nLeaves >= 0x3fffffffu)
+		return Fail(LRB_ERR_INVALID, "leaf count out of range");
+	LRB_SETDEV(dev);
+	*nNodes = 0;
+	if (timings) memset(timings, 0, sizeof(*timings));
+	if (nLeaves == 1) {
+		// the tree is its only leaf (bvhclassicbuild.cpp: a leaf list of one)
+		if (outCapacity < 1)
+			return Fail(LRB_ERR_INVALID, "output array too small");
+		memset(outNodes, 0, sizeof(*outNodes));
+		outNodes[0].triangleLeaf.v[0] = 0;
+		outNodes[0].nodeData = 1u | 0x80000000u;
+		*nNodes = 1;
+		return LRB_OK;
+	}
+	const uint32_t levelStep = treeType == 2 ? 1u : (treeType == 4 ? 2u : 3u);
+	const int n = (int)nLeaves, nInner = n - 1;
+	cudaStream_t st = dev->stream;
+	cudaEvent_t ev[6];
+	for (int i = 0; i < 6; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
+	BuildEvents evGuard = { ev, 6 };
+
+	DevBuf dBoxes, dBounds, dKeys[2], dVals[2], dTemp, dLeft, dRight, dParI, dParL, dDepth, dBox, dSize, dArrived, dOut;
+	LRB_CUDA(cudaMalloc(&dBoxes.p, (size_t)n * 24));
+	LRB_CUDA(cudaMalloc(&dBounds.p, 32));
+	for (int k = 0; k < 2; ++k) {
+		LRB_CUDA(cudaMalloc(&dKeys[k].p, (size_t)n * 8));
+		LRB_CUDA(cudaMalloc(&dVals[k].p, (size_t)n * 4));
+	}
+	LRB_CUDA(cudaMalloc(&dLeft.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dRight.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dParI.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dParL.p, (size_t)n * 4));
+	LRB_CUDA(cudaMalloc(&dDepth.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dBox.p, (size_t)nInner * 24));
+	LRB_CUDA(cudaMalloc(&dSize.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dArrived.p, (size_t)nInner * 4));
+
+	LRB_CUDA(cudaEventRecord(ev[0], st));
+	LRB_CUDA(cudaMemcpyAsync(dBoxes.p, leafBoxes, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+	dev->counters.h2d_bytes += (uint64_t)n * 24;
+	LRB_CUDA(cudaEventRecord(ev[1], st));
+
+	// 1 + 2: centroid bounds, Morton codes, sort
+	const uint32_t initBounds[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+	LRB_CUDA(cudaMemcpyAsync(dBounds.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
+	const int blocks = (n + 255) / 256;
+	CentroidBoundsKernel<<<std::min(blocks, dev->prop.multiProcessorCount * 8), 256, 0, st>>>(dBoxes.as<float>(), nLeaves, dBounds.as<uint32_t>());
+	MortonKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), nLeaves, dBounds.as<uint32_t>(), dKeys[0].as<uint64_t>(), dVals[0].as<uint32_t>());
+	cub::DoubleBuffer<uint64_t> keys(dKeys[0].as<uint64_t>(), dKeys[1].as<uint64_t>());
+	cub::DoubleBuffer<uint32_t> vals(dVals[0].as<uint32_t>(), dVals[1].as<uint32_t>());
+	size_t tempBytes = 0;
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, vals, n, 0, 63, st));
+	LRB_CUDA(cudaMalloc(&dTemp.p, std::max<size_t>(tempBytes, 16)));
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(dTemp.p, tempBytes, keys, vals, n, 0, 63, st));
+	LRB_CUDA(cudaEventRecord(ev[2], st));
+
+	// 3 - 5: radix tree, depths, boxes + subtree sizes
+	const int iblocks = (nInner + 255) / 256;
+	RadixTreeKernel<<<iblocks, 256, 0, st>>>(keys.Current(), n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dParL.as<uint32_t>());
+	DepthKernel<<<iblocks, 256, 0, st>>>(dParI.as<uint32_t>(), nInner, dDepth.as<uint32_t>());
+	LRB_CUDA(cudaMemsetAsync(dArrived.p, 0, (size_t)nInner * 4, st));
+	BottomUpKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), vals.Current(), n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(),
+			dParL.as<uint32_t>(), dDepth.as<uint32_t>(), levelStep, dBox.as<float>(), dSize.as<uint32_t>(), dArrived.as<uint32_t>());
+	LRB_CUDA(cudaEventRecord(ev[3], st));
+	uint32_t total = 0;
+	LRB_CUDA(cudaMemcpyAsync(&total, dSize.p, 4, cudaMemcpyDeviceToHost, st));      // size of the root's subtree = nodes in the array
+	LRB_CUDA(cudaStreamSynchronize(st));
+	if (total < nLeaves + 1 || total > 2u * nLeaves - 1u)
+		return Fail(LRB_ERR_INTERNAL, "device builder: inconsistent tree size");
+	if (total > outCapacity)
+		return Fail(LRB_ERR_INVALID, "output array too small (2 * leaves - 1 nodes always suffice)");
+
+	// 6 + 7: array indices and emission
+	LRB_CUDA(cudaMalloc(&dOut.p, (size_t)total * sizeof(lrb_bvh_node)));
+	EmitInnerKernel<<<iblocks, 256, 0, st>>>(nInner, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dDepth.as<uint32_t>(),
+			dSize.as<uint32_t>(), dBox.as<float>(), levelStep, dOut.as<lrb_bvh_node>());
+	EmitLeafKernel<<<blocks, 256, 0, st>>>(n, vals.Current(), dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dParL.as<uint32_t>(),
+			dDepth.as<uint32_t>(), dSize.as<uint32_t>(), levelStep, dOut.as<lrb_bvh_node>());
+	LRB_CUDA(cudaEventRecord(ev[4], st));
+	LRB_CUDA(cudaMemcpyAsync(outNodes, dOut.p, (size_t)total * sizeof(lrb_bvh_node), cudaMemcpyDeviceToHost, st));
+	dev->counters.d2h_bytes += (uint64_t)total * sizeof(lrb_bvh_node);
+	LRB_CUDA(cudaEventRecord(ev[5], st));
+	LRB_CUDA(cudaStreamSynchronize(st));
+	LRB_CUDA(cudaGetLastError());
+	*nNodes = total;
+	if (timings) {
+		float ms;
+		cudaEventElapsedTime(&ms, ev[0], ev[1]); timings->h2d_ms = ms;
+		cudaEventElapsedTime(&ms, ev[1], ev[2]); timings->sort_ms = ms;
+		cudaEventElapsedTime(&ms, ev[2], ev[3]); timings->tree_ms = ms;
+		cudaEventElapsedTime(&ms, ev[3], ev[4]); timings->emit_ms = ms;
+		cudaEventElapsedTime(&ms, ev[4], ev[5]); timings->d2h_ms = ms;
+		timings->kernels = 8;
+	}
+	return LRB_OK;
+}
+
 int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {
 	if (!s || !out)
 		return Fail(LRB_ERR_INVALID, "null argument");
@@ -1251,6 +1358,12 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 		LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		dev->events.push_back(e);
 	}
+	if (push) {
+		// (deferred gathers: the pushes of the call before the previous one must have left this RayHit buffer)
+		const int rc = GatherBegin(dev);
+		if (rc != LRB_OK)
+			return rc;
+	}
 	uint32_t c = 0;
 	for (uint32_t first = 0; first < n; first += per, ++c) {
 		const uint32_t cnt = std::min(per, n - first);
@@ -1266,11 +1379,8 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 			LRB_CUDA(cudaMemcpyAsync((lrb_rayhit *)dst + first, h, (size_t)cnt * sizeof(lrb_rayhit), cudaMemcpyDefault, dev->copyOutStream));
 		}
 	}
-	if (push) {
-		cudaEvent_t done = dev->events[2 * (size_t)nChunks + 1];
-		LRB_CUDA(cudaEventRecord(done, dev->copyOutStream));
-		LRB_CUDA(cudaStreamWaitEvent(dev->stream, done, 0));
-	}
+	if (push)
+		return GatherEnd(dev, dev->events[2 * (size_t)nChunks + 1]);
 	return LRB_OK;
 }
 

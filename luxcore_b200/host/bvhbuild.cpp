@@ -6,8 +6,8 @@
 //                              during the recursion instead of building a pointer tree and
 //                              flattening it; partitions, split values and box unions are the same
 //                              operations in the same order, so the array is bit-identical.
-//   BuildEmbreeBVHBinnedSAH /
-//   BuildEmbreeBVHMorton     : the reference delegates these to Intel Embree 3.12.2 (not part of
+//   BuildEmbreeBVHMorton     : GPU linear-BVH builder behind the C ABI (lrb_build_lbvh), see below.
+//   BuildEmbreeBVHBinnedSAH  : the reference delegates these to Intel Embree 3.12.2 (not part of
 //                              /root/reference).  Replaced by a from-scratch binned-SAH k-ary
 //                              builder (16 bins, 3 axes, largest-area child split first, one
 //                              primitive per leaf, at most treeType children per node), multi-
@@ -20,9 +20,13 @@
 #include <cstring>
 #include <limits>
 #include <future>
+#include <mutex>
+#include <stdexcept>
+#include <string>
 #include <thread>
 
 #include "luxrays/core/bvh/bvhbuild.h"
+#include "luxrays_b200.h"
 
 namespace luxrays {
 
@@ -709,9 +713,78 @@ Node *BuildEmbreeBVHBinnedSAH(const BVHParams &params, u_int *nNodes, const std:
 	return ToArray(out, nNodes);
 }
 
+// EMBREE_MORTON (bvhembreebuild.cpp:218-336 with rtcBVHBuilderMorton): the fast builder.  Here: a linear BVH built ON
+// THE GPU by the C ABI's lrb_build_lbvh (luxcore_b200/csrc/build_kernels.cuh) from the leaf boxes; this function
+// only gathers the boxes and writes the leaf payload (vertex indices / instance records, which live in host
+// tables) into the array the device returns.  The device is the process-wide builder device (LRB_BUILDER_DEVICE,
+// default CUDA ordinal 0), opened on first use.  Without any CUDA device the host SAH builder answers instead
+// (stated on stderr): tree topology never changes a closest hit.
+static lrb_device *BuilderDevice() {
+	static std::mutex mtx;
+	static lrb_device *dev = nullptr;
+	static bool tried = false;
+	std::lock_guard<std::mutex> lock(mtx);
+	if (!tried) {
+		tried = true;
+		int count = 0;
+		if (lrb_device_count(&count) == LRB_OK && count > 0) {
+			const char *env = getenv("LRB_BUILDER_DEVICE");
+			if (lrb_device_create(env ? atoi(env) : 0, &dev) != LRB_OK)
+				dev = nullptr;
+		}
+	}
+	return dev;
+}
+
 Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
-	// quality/speed trade-off of the Morton builder is not reproduced; same SAH builder
-	return BuildEmbreeBVHBinnedSAH(params, nNodes, meshes, leafList);
+	lrb_device *dev = leafList.empty() ? nullptr : BuilderDevice();
+	if (!dev) {
+		if (!leafList.empty())
+			fprintf(stderr, "luxrays_b200: EMBREE_MORTON: no CUDA device for the GPU builder, using the host SAH builder\n");
+		return BuildEmbreeBVHBinnedSAH(params, nNodes, meshes, leafList);
+	}
+	const size_t n = leafList.size();
+	std::vector<float> boxes(6 * n);
+	for (size_t i = 0; i < n; ++i) {
+		const BBox &b = leafList[i]->bbox;
+		float *o = &boxes[6 * i];
+		o[0] = b.pMin.x; o[1] = b.pMin.y; o[2] = b.pMin.z;
+		o[3] = b.pMax.x; o[4] = b.pMax.y; o[5] = b.pMax.z;
+	}
+	const size_t cap = 2 * n;
+	Node *arr = new Node[cap];
+	uint32_t total = 0;
+	lrb_build_timings tm;
+	static_assert(sizeof(Node) == sizeof(lrb_bvh_node), "BVHArrayNode layout");
+	if (lrb_build_lbvh(dev, boxes.data(), (uint32_t)n, params.treeType, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, &tm) != LRB_OK) {
+		delete[] arr;
+		throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+	}
+	// leaf payload (the device wrote the input index of every leaf into the first word)
+	for (uint32_t i = 0; i < total; ++i) {
+		Node &an = arr[i];
+		if (!(an.nodeData & 0x80000000u))
+			continue;
+		const BVHTreeNode *leaf = leafList[an.triangleLeaf.v[0]];
+		const u_int nodeData = an.nodeData;
+		memset(&an, 0, sizeof(an));
+		if (meshes) {
+			const Triangle &tri = (*meshes)[leaf->triangleLeaf.meshIndex]->GetTriangles()[leaf->triangleLeaf.triangleIndex];
+			an.triangleLeaf.v[0] = tri.v[0];
+			an.triangleLeaf.v[1] = tri.v[1];
+			an.triangleLeaf.v[2] = tri.v[2];
+			an.triangleLeaf.meshIndex = leaf->triangleLeaf.meshIndex;
+			an.triangleLeaf.triangleIndex = leaf->triangleLeaf.triangleIndex;
+		} else {
+			an.bvhLeaf.leafIndex = leaf->bvhLeaf.leafIndex;
+			an.bvhLeaf.transformIndex = leaf->bvhLeaf.transformIndex;
+			an.bvhLeaf.motionIndex = leaf->bvhLeaf.motionIndex;
+			an.bvhLeaf.meshOffsetIndex = leaf->bvhLeaf.meshOffsetIndex;
+		}
+		an.nodeData = nodeData;
+	}
+	*nNodes = total;
+	return arr;
 }
 
 }   // namespace luxrays

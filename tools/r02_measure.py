@@ -213,6 +213,8 @@ def section_soup(n_tris):
          ("sorted 7 bits, refill 16", {"sort_rays": 1, "sort_bits": 7, "refill_below": 16}),
          ("sorted 7 bits, carveout 25", {"sort_rays": 1, "sort_bits": 7, "carveout": 25}),
          ("sorted 7 bits, simple kernel", {"sort_rays": 1, "sort_bits": 7, "kernel": "simple"})]
+    if ARGS.quick:
+        v = [("sorted 5 bits (what sort_rays = auto picks for a scene larger than L2)", {"sort_rays": 1, "sort_bits": 5})]
     sweep(sess, "soup:%d" % n_tris, "uniform", rays, v, orc, sample=20000)
     # probes for the roofline denominators, same process / same clocks
     dv = capi.Device.borrow(sess.native_device())
