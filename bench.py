@@ -239,7 +239,8 @@ def main():
     ap.add_argument("--builder", default="EMBREE_BINNED_SAH")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "direct", "none"])
-    ap.add_argument("--chunks", type=int, default=0, help="0 = fused in-kernel push; >= 1 = launches per batch for the copy-engine push")
+    ap.add_argument("--chunks", type=int, default=1, help="p2p gather: >= 1 = launches per batch, each followed by a copy-engine push of its RayHit "
+                    "slice (default 1: plain kernel + one push, measured fastest); 0 = ONE kernel that signals finished chunks to the copy stream")
     ap.add_argument("--no-pipeline", action="store_true", help="p2p gather: every step waits for its own pushes and completion signal "
                     "(default: the tail of step k's pushes and its signal overlap the trace of step k + 1; two RayHit buffers)")
     ap.add_argument("--timeline", action="store_true", help="N > 1: CUDA-event breakdown of un-pipelined steps per rank (kernel / tail of the pushes / signal)")
@@ -613,9 +614,12 @@ def main():
                 roof = {"bound": "hbm", "achieved": round(hbm_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(hbm_gbs / peak, 4), "traffic": dram,
                         "peak_source": peak_src,
                         "note": "scene (%.1f GB on the device) does not fit L2; achieved = ncu-measured DRAM bytes of one launch / live kernel time. "
-                                "ncu: L2 hit rate %.0f %%, issue slots %.0f %% busy, top stall long_scoreboard %.1f warps per issue: the walk is bound by the "
-                                "latency of dependent node fetches, not by HBM bandwidth" % (
+                                "ncu: L2 hit rate %.0f %%, issue slots %.0f %% busy (%.0f warp instructions per ray at %.1f of 32 lanes), top stall "
+                                "long_scoreboard %.1f warps per issue: the walk sits between the SMs' issue bound and the latency of dependent node "
+                                "fetches; HBM bandwidth itself is not the limit (more resident warps spill registers and run slower, an L2 prefetch of the "
+                                "pushed children costs more traffic than it hides: both measured, DESIGN.md)" % (
                                     info.device_bytes / 1e9, cap.get("lts_hit_rate_pct") or 0, cap.get("issue_active_pct") or 0,
+                                    cap.get("warp_instructions_per_ray") or 0, cap.get("threads_per_instruction") or 0,
                                     (cap.get("top_stalls_warps_per_issue") or {}).get("long_scoreboard", 0))}
             roof["memory"] = memory
             roof["traffic_source"] = cap.get("source")

@@ -36,6 +36,9 @@ static const uint32_t kCompactAutoNum = 6, kCompactAutoDen = 10;
 #ifndef LRB_MINBLOCKS_2L
 #define LRB_MINBLOCKS_2L 8
 #endif
+#ifndef LRB_BOTH_PHASES
+#define LRB_BOTH_PHASES 0
+#endif
 
 // ---- stacks ---------------------------------------------------------------------------------
 
@@ -494,6 +497,31 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 					nInst = 0;
 				}
 			}
+#if LRB_BOTH_PHASES
+			// Experimental schedule (-DLRB_BOTH_PHASES=<triMin>): every iteration runs the node phase for the lanes that
+			// hold a node and THEN the triangle phase for the lanes that hold a triangle -- those that waited and those
+			// whose nearest child just turned out to be one -- when at least triMin of them are ready or no node phase
+			// ran.  One Resolve / vote / loop overhead per pair of phases instead of per phase.
+			if (nNode) {
+				if (work == kWorkNode) {
+					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
+					work = (s.cur < kTagInstance && (s.cur & kTagTri)) ? kWorkTri : kWorkNone;
+				}
+				__syncwarp();
+				nTri = __popc(__ballot_sync(0xffffffffu, work == kWorkTri));
+			}
+			if (nTri && (nTri >= LRB_BOTH_PHASES || !nNode)) {
+				if (work == kWorkTri) {
+					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
+					if (ANYHIT && s.hitRef != kNullIndex) {
+						stk.reset();
+						s.inInstance = false;
+					}
+				}
+			}
+			nLive = __popc(__ballot_sync(0xffffffffu, state == kActive));
+			continue;
+#endif
 			if (VoteTrianglePhase(nTri, nNode, a.triBias)) {
 				if (work == kWorkTri) {
 					TriStep<TWO_LEVEL, false>(a.sc, s, nullptr);
