@@ -351,6 +351,7 @@ def main():
 
     pending = []        # async completion signals of the pipelined gather
     step_no = [0]
+    probe = [None]      # when a list: (start, stop) CUDA events around every step's trace on the device queue
 
     def step():
         k = step_no[0]
@@ -363,8 +364,13 @@ def main():
         elif gather_mode == "p2p":
             import torch.distributed as dist
             b = k % n_buf
+            if probe[0] is not None:
+                probe[0].append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                probe[0][-1][0].record(stream)
             # rank 0 traces straight into its slice of the gather buffer (no copy at all)
             scene.trace_gather(rays.data_ptr(), my_dst[b] if rank == 0 else hits_buf[b].data_ptr(), n, my_dst[b], args.chunks)
+            if probe[0] is not None:
+                probe[0][-1][1].record(stream)
             if not pipeline:
                 dist.all_reduce(flag)           # 4-byte "batch complete" signal, ordered after the pushes
             else:
@@ -435,6 +441,24 @@ def main():
         b_.record()
     torch.cuda.synchronize()
     kern_ms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in kev]))
+
+    # ---- N > 1, pipelined gather: every rank's trace time inside the running pipeline (not part of the timed region): the
+    # kernel of step k + 1 shares the GPU with the push of step k -- and rank 0's with the slices arriving from every rank
+    pipe_kernel_ms = None
+    if world > 1 and pipeline:
+        import torch.distributed as dist
+        barrier()
+        probe[0] = []
+        for _ in range(10):
+            step()
+        drain()
+        torch.cuda.synchronize()
+        mine = float(np.median([a_.elapsed_time(b_) for a_, b_ in probe[0][2:]]))
+        probe[0] = None
+        allk = [None] * world
+        dist.all_gather_object(allk, mine)
+        pipe_kernel_ms = [round(x, 4) for x in allk]
+        barrier()
 
     # ---- N > 1: where a step's time goes (CUDA events, un-pipelined steps; not part of the timed region) ----
     timeline = None
@@ -567,6 +591,8 @@ def main():
         out["parity_check"] = parity
     if timeline:
         out["timeline"] = timeline
+    if pipe_kernel_ms:
+        out["gather"]["per_rank_trace_ms_in_pipeline"] = pipe_kernel_ms
 
     if rank == 0:
         peak, peak_src = read_peaks()

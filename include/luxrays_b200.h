@@ -162,12 +162,22 @@ LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
  * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2),
  * "compact" (0 = default: masked rays are skipped inside the kernel | 1 = lrb_trace compacts the live rays first |
  * 2 = counts them first and compacts when fewer than 60 % are live),
- * "carveout" (preferred shared-memory carve-out of the trace kernels in percent, -1 = driver default). */
+ * "carveout" (preferred shared-memory carve-out of the trace kernels in percent, -1 = driver default),
+ * "l2_persist" (L2 access-policy window over a one-level scene: 0 = default never | 1 always | 2 when it fits the set-aside),
+ * "pipeline" (1 = default: the h2d / trace / d2h sequence below is pipelined chunk by chunk | 0 = every call as it is). */
 LRB_API int lrb_device_set_option(lrb_device *dev, const char *key, const char *value);
 
 /* ---- memory + queue (cudadevice.cpp:407-540) ------------------------------------------- */
 LRB_API int lrb_alloc(lrb_device *dev, size_t bytes, void **devptr);
 LRB_API int lrb_free(lrb_device *dev, void *devptr);
+/* One in-order queue, as in the reference.  Behind that contract the reference-facing sequence
+ *     AllocBufferRW(&rays, hostRays) -> EnqueueTraceRayBuffer(rays, hits, n) -> EnqueueReadBuffer(hits, hostHits) -> FinishQueue
+ *   = lrb_h2d(rays_dev, ..., blocking = 0) -> lrb_trace(scene, rays_dev, hits_dev, n) -> lrb_d2h(hostHits, hits_dev, ...) -> lrb_sync
+ * is pipelined: a non-blocking upload of >= 32 MB travels in chunks of "host_chunk" rays on a copy stream, a trace
+ * whose ray buffer is exactly that upload follows it chunk by chunk, and a read of exactly that trace's RayHit buffer
+ * follows the trace chunk by chunk on a second copy stream (PCIe is full duplex).  Any other call first joins the
+ * queue with whatever is pending, so results and ordering are those of the plain sequence; as with the reference's
+ * cuMemcpyHtoDAsync (cudadevice.cpp:485) a pinned source must stay valid until the queue has been finished. */
 LRB_API int lrb_h2d(lrb_device *dev, void *dst_dev, const void *src_host, size_t bytes, int blocking);
 LRB_API int lrb_d2h(lrb_device *dev, void *dst_host, const void *src_dev, size_t bytes, int blocking);
 LRB_API int lrb_flush(lrb_device *dev);

@@ -73,6 +73,9 @@ struct lrb_device {
 	uint32_t *compactIdx, *compactBlocks, *compactTotal;    // scratch of the compaction kernels
 	size_t compactCap;
 	int carveout;                   // preferred shared-memory carve-out of the trace kernels in percent (-1 = driver default)
+	int l2Persist;                  // L2 persistence window over the scene's nodes + triangles: 0 never, 1 always (if it fits), 2 = when it fits the set-aside
+	const void *l2WindowBase;       // window currently set on the queue (stream attribute), or NULL
+	size_t l2WindowBytes;
 	int prefetch;                   // L2 prefetch of the children pushed on the stack: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
@@ -82,6 +85,22 @@ struct lrb_device {
 	void *sortTemp;
 	size_t sortCap, sortTempBytes;
 	int hostChunk;                  // rays per chunk in lrb_trace_host
+	// The reference-facing call sequence (AllocBufferRW(src) / EnqueueTraceRayBuffer / EnqueueReadBuffer / FinishQueue =
+	// lrb_h2d / lrb_trace / lrb_d2h / lrb_sync) pipelined behind its own interface: a large asynchronous upload is cut
+	// into chunks on the copy-in stream, a trace whose ray buffer is exactly that upload follows it chunk by chunk, a
+	// read of exactly that trace's RayHit buffer follows the trace chunk by chunk on the copy-out stream.  Anything
+	// else first joins the queue with what is pending (JoinPending), so the in-order semantics of the queue hold.
+	int pipeline;                   // option "pipeline": 1 (default) = as described, 0 = every call on the queue as it is
+	struct Pending {
+		const char *base;           // device range [base, base + bytes)
+		size_t bytes, chunkBytes;
+		std::vector<cudaEvent_t> ev;    // one per chunk (borrowed from pipeEvents)
+		bool active;
+	} pendUpload[2], pendTraced;
+	std::vector<cudaEvent_t> pipeEvents;
+	size_t pipeEventNext;
+	cudaEvent_t pipeJoin;
+	bool copyOutBusy;               // the copy-out stream holds chunked reads the queue has not joined yet
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
 	size_t stageRaysBytes, stageHitsBytes;
@@ -94,6 +113,8 @@ struct lrb_scene {
 	WideNode *dNodes;
 	TriRecord *dTris;
 	TriIds *dIds;
+	void *dSlab;                    // one-level scenes: nodes + triangle records + ids in ONE allocation (the L2 persistence window covers it)
+	size_t slabBytes;
 	InstRecord *dInsts;
 	float *dMinv;
 	uint32_t *dMotionFirst, *dMotionLast;
@@ -123,6 +144,70 @@ static int SetDev(lrb_device *dev) {
 		const int rc_ = SetDev(dev);            \
 		if (rc_ != LRB_OK) return rc_;          \
 	} while (0)
+
+// ---- the plugin sequence, pipelined (see lrb_device::pipeline) ----------------------------------------------
+
+static const size_t kPipeMinBytes = 32u << 20;     // smaller transfers are not worth cutting up
+
+static int PipeEvent(lrb_device *dev, cudaEvent_t *out) {
+	if (dev->pipeEvents.size() < 1024) {
+		cudaEvent_t e;
+		LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		dev->pipeEvents.push_back(e);
+		*out = e;
+		return LRB_OK;
+	}
+	*out = dev->pipeEvents[dev->pipeEventNext++ % dev->pipeEvents.size()];     // (an event that old has long been consumed)
+	return LRB_OK;
+}
+
+// Everything the side streams still hold becomes part of the device's in-order queue.
+static int JoinPending(lrb_device *dev) {
+	for (int k = 0; k < 2; ++k) {
+		lrb_device::Pending &u = dev->pendUpload[k];
+		if (u.active && !u.ev.empty())
+			LRB_CUDA(cudaStreamWaitEvent(dev->stream, u.ev.back(), 0));
+		u.active = false;
+	}
+	dev->pendTraced.active = false;     // its chunk events were recorded on the queue itself: nothing to wait for
+	if (dev->copyOutBusy) {
+		if (!dev->pipeJoin)
+			LRB_CUDA(cudaEventCreateWithFlags(&dev->pipeJoin, cudaEventDisableTiming));
+		LRB_CUDA(cudaEventRecord(dev->pipeJoin, dev->copyOutStream));
+		LRB_CUDA(cudaStreamWaitEvent(dev->stream, dev->pipeJoin, 0));
+		dev->copyOutBusy = false;
+	}
+	return LRB_OK;
+}
+
+// Asynchronous upload in chunks on the copy-in stream, remembered as pending.
+static int PipelinedUpload(lrb_device *dev, void *dst, const void *src, size_t bytes) {
+	int slot = dev->pendUpload[0].active ? 1 : 0;
+	if (dev->pendUpload[slot].active) {
+		const int rc = JoinPending(dev);
+		if (rc != LRB_OK) return rc;
+		slot = 0;
+	}
+	lrb_device::Pending &u = dev->pendUpload[slot];
+	// the copy-in stream starts behind everything queued so far (earlier users of dst)
+	cudaEvent_t start;
+	int rc = PipeEvent(dev, &start);
+	if (rc != LRB_OK) return rc;
+	LRB_CUDA(cudaEventRecord(start, dev->stream));
+	LRB_CUDA(cudaStreamWaitEvent(dev->copyInStream, start, 0));
+	const size_t chunk = (size_t)dev->hostChunk * sizeof(lrb_ray);     // a whole number of rays AND of RayHits (48 = lcm-friendly: 12 x 4)
+	u.base = (const char *)dst; u.bytes = bytes; u.chunkBytes = chunk; u.ev.clear();
+	for (size_t off = 0; off < bytes; off += chunk) {
+		const size_t cnt = std::min(chunk, bytes - off);
+		LRB_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, cnt, cudaMemcpyHostToDevice, dev->copyInStream));
+		cudaEvent_t e;
+		if ((rc = PipeEvent(dev, &e)) != LRB_OK) return rc;
+		LRB_CUDA(cudaEventRecord(e, dev->copyInStream));
+		u.ev.push_back(e);
+	}
+	u.active = true;
+	return LRB_OK;
+}
 
 extern "C" {
 
@@ -180,6 +265,9 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortRays = 2;
 	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
 	dev->carveout = -1;
+	dev->l2Persist = 0;     // measured on B200 (profiles/r02_measure_ingest_c10.json): no gain alone, no protection against concurrent traffic
+	dev->l2WindowBase = nullptr;
+	dev->l2WindowBytes = 0;
 	dev->compact = 0;
 	dev->compactIdx = dev->compactBlocks = dev->compactTotal = nullptr;
 	dev->compactCap = 0;
@@ -196,6 +284,11 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortTemp = nullptr;
 	dev->sortCap = dev->sortTempBytes = 0;
 	dev->hostChunk = 1 << 20;
+	dev->pipeline = 1;
+	dev->pendUpload[0].active = dev->pendUpload[1].active = dev->pendTraced.active = false;
+	dev->pipeEventNext = 0;
+	dev->pipeJoin = nullptr;
+	dev->copyOutBusy = false;
 	*out = dev;
 	return LRB_OK;
 }
@@ -204,8 +297,12 @@ int lrb_device_destroy(lrb_device *dev) {
 	if (!dev)
 		return LRB_OK;
 	LRB_SETDEV(dev);
+	cudaStreamSynchronize(dev->copyInStream);
+	cudaStreamSynchronize(dev->copyOutStream);
 	cudaStreamSynchronize(dev->stream);
 	for (size_t i = 0; i < dev->events.size(); ++i) cudaEventDestroy(dev->events[i]);
+	for (size_t i = 0; i < dev->pipeEvents.size(); ++i) cudaEventDestroy(dev->pipeEvents[i]);
+	if (dev->pipeJoin) cudaEventDestroy(dev->pipeJoin);
 	for (int i = 0; i < 2; ++i) if (dev->gatherDone[i]) cudaEventDestroy(dev->gatherDone[i]);
 	if (dev->stageRays) cudaFree(dev->stageRays);
 	if (dev->stageHits) cudaFree(dev->stageHits);
@@ -236,7 +333,13 @@ int lrb_device_get_props(lrb_device *dev, lrb_device_props *out) {
 int lrb_device_set_stream(lrb_device *dev, void *s) {
 	if (!dev)
 		return Fail(LRB_ERR_INVALID, "null device");
+	{
+		const int rcJoin = JoinPending(dev);    // what the side streams hold joins the queue that is being left
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	dev->stream = s ? (cudaStream_t)s : dev->ownStream;
+	dev->l2WindowBase = nullptr;        // the access-policy window is an attribute of the queue: set again at the next launch
+	dev->l2WindowBytes = 0;
 	return LRB_OK;
 }
 
@@ -286,6 +389,12 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "compact") {
 		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "compact must be 0 (masked rays are skipped inside the trace kernel), 1 (compacted before it) or 2 (counted; compacted when fewer than 60 % are live)");
 		dev->compact = iv;
+	} else if (k == "pipeline") {
+		if (iv < 0 || iv > 1) return Fail(LRB_ERR_INVALID, "pipeline must be 0 or 1");
+		dev->pipeline = iv;
+	} else if (k == "l2_persist") {
+		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "l2_persist must be 0 (never), 1 (always, clipped to the set-aside) or 2 (scenes that fit the set-aside)");
+		dev->l2Persist = iv;
 	} else if (k == "carveout") {
 		if (iv < -1 || iv > 100) return Fail(LRB_ERR_INVALID, "carveout must be -1 (default) or 0..100 percent of shared memory");
 		dev->carveout = iv;
@@ -337,6 +446,10 @@ int lrb_free(lrb_device *dev, void *devptr) {
 		dev->counters.device_bytes_in_use -= std::min<uint64_t>(dev->counters.device_bytes_in_use, it->second);
 		dev->allocs.erase(it);
 	}
+	{
+		const int rc = JoinPending(dev);    // (cudaFree synchronises the device; the bookkeeping must not outlive the buffer)
+		if (rc != LRB_OK) return rc;
+	}
 	LRB_CUDA(cudaFree(devptr));
 	return LRB_OK;
 }
@@ -347,10 +460,14 @@ int lrb_h2d(lrb_device *dev, void *dst, const void *src, size_t bytes, int block
 		return LRB_OK;
 	if (!dst || !src)
 		return Fail(LRB_ERR_INVALID, "null pointer in h2d");
+	dev->counters.h2d_bytes += bytes;
+	if (dev->pipeline && !blocking && bytes >= kPipeMinBytes)
+		return PipelinedUpload(dev, dst, src, bytes);
+	int rc = JoinPending(dev);
+	if (rc != LRB_OK) return rc;
 	LRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream));
 	if (blocking)
 		LRB_CUDA(cudaStreamSynchronize(dev->stream));
-	dev->counters.h2d_bytes += bytes;
 	return LRB_OK;
 }
 
@@ -360,10 +477,30 @@ int lrb_d2h(lrb_device *dev, void *dst, const void *src, size_t bytes, int block
 		return LRB_OK;
 	if (!dst || !src)
 		return Fail(LRB_ERR_INVALID, "null pointer in d2h");
+	dev->counters.d2h_bytes += bytes;
+	lrb_device::Pending &t = dev->pendTraced;
+	if (t.active && (const char *)src == t.base && bytes == t.bytes) {
+		// the RayHit buffer of the chunked trace: every chunk leaves as soon as it has been traced
+		size_t c = 0;
+		for (size_t off = 0; off < bytes; off += t.chunkBytes, ++c) {
+			const size_t cnt = std::min(t.chunkBytes, bytes - off);
+			LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, t.ev[c], 0));
+			LRB_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, cnt, cudaMemcpyDeviceToHost, dev->copyOutStream));
+		}
+		t.active = false;
+		dev->copyOutBusy = true;
+		if (blocking) {
+			const int rc = JoinPending(dev);
+			if (rc != LRB_OK) return rc;
+			LRB_CUDA(cudaStreamSynchronize(dev->stream));
+		}
+		return LRB_OK;
+	}
+	const int rc = JoinPending(dev);
+	if (rc != LRB_OK) return rc;
 	LRB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
 	if (blocking)
 		LRB_CUDA(cudaStreamSynchronize(dev->stream));
-	dev->counters.d2h_bytes += bytes;
 	return LRB_OK;
 }
 
@@ -378,6 +515,10 @@ int lrb_flush(lrb_device *dev) {
 
 int lrb_sync(lrb_device *dev) {
 	LRB_SETDEV(dev);
+	{
+		const int rc = JoinPending(dev);
+		if (rc != LRB_OK) return rc;
+	}
 	if (dev->gatherPending[0] || dev->gatherPending[1]) {      // deferred gather pushes (gather_defer)
 		LRB_CUDA(cudaStreamSynchronize(dev->copyOutStream));
 		dev->gatherPending[0] = dev->gatherPending[1] = false;
@@ -440,6 +581,10 @@ int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double 
 	if (!gbps || bytes < 4096 || iters < 1)
 		return Fail(LRB_ERR_INVALID, "bad argument");
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	void *buf = nullptr;
 	unsigned *sink = nullptr;
 	LRB_CUDA(cudaMalloc(&buf, bytes));
@@ -469,6 +614,49 @@ int lrb_measure_read_bandwidth(lrb_device *dev, size_t bytes, int iters, double 
 // ---- scenes -----------------------------------------------------------------------------------
 
 }   // extern "C"
+
+// L2 persistence (the reference only asks for CU_FUNC_CACHE_PREFER_L1, cudadevice.cpp:162).
+// A scene that is L2-resident competes for L2 with what streams through it: the 48-B rays and 20-B RayHits of its own
+// batch and, on the gathering GPU of a multi-GPU run, the other ranks' RayHit slices arriving over NVLink.  An access-
+// policy window on the queue marks the scene's slab "persisting" for the kernels launched there; the set-aside is sized
+// once per device.  Clipped to the device's limits; a no-op for scenes that do not fit.
+static int ClearL2Window(lrb_device *dev) {
+	if (!dev->l2WindowBase)
+		return LRB_OK;
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof(attr));
+	attr.accessPolicyWindow.num_bytes = 0;
+	LRB_CUDA(cudaStreamSetAttribute(dev->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+	dev->l2WindowBase = nullptr;
+	dev->l2WindowBytes = 0;
+	return LRB_OK;
+}
+
+static int SetL2Window(lrb_device *dev, const void *base, size_t bytes) {
+	const size_t maxPersist = (size_t)dev->prop.persistingL2CacheMaxSize, maxWindow = (size_t)dev->prop.accessPolicyMaxWindowSize;
+	const bool fits = base && bytes && maxPersist && bytes <= maxPersist && bytes <= maxWindow;
+	const bool want = dev->l2Persist == 1 ? (base && bytes && maxPersist && maxWindow) : (dev->l2Persist == 2 && fits);
+	if (!want)
+		return ClearL2Window(dev);
+	if (dev->l2WindowBase == base && dev->l2WindowBytes == bytes)
+		return LRB_OK;
+	size_t limit = 0;
+	LRB_CUDA(cudaDeviceGetLimit(&limit, cudaLimitPersistingL2CacheSize));
+	const size_t need = std::min(bytes, maxPersist);
+	if (limit < need)
+		LRB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need));
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof(attr));
+	attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+	attr.accessPolicyWindow.num_bytes = std::min(bytes, maxWindow);
+	attr.accessPolicyWindow.hitRatio = fits ? 1.f : (float)((double)maxPersist / (double)bytes);
+	attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	LRB_CUDA(cudaStreamSetAttribute(dev->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+	dev->l2WindowBase = base;
+	dev->l2WindowBytes = bytes;
+	return LRB_OK;
+}
 
 template <class T> static int UploadArray(lrb_device *dev, const std::vector<T> &src, T **dst, size_t *cap, uint64_t *bytes) {
 	const size_t n = src.size();
@@ -516,9 +704,31 @@ static int UploadScene(lrb_scene *s) {
 	lrb_device *dev = s->dev;
 	uint64_t bytes = 0;
 	int rc;
-	if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
-	if ((rc = UploadArray(dev, s->host.tris, &s->dTris, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
-	if ((rc = UploadArray(dev, s->host.ids, &s->dIds, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	if ((rc = JoinPending(dev)) != LRB_OK) return rc;
+	if (!s->host.twoLevel && !s->dNodes && !s->host.wide.empty()) {
+		// one-level scenes never change: nodes, triangle records and ids share ONE allocation, so that a single
+		// L2 access-policy window (SetL2Window) can keep all of it resident
+		const size_t nb = (s->host.wide.size() * sizeof(WideNode) + 255) & ~(size_t)255;
+		const size_t tb = (s->host.tris.size() * sizeof(TriRecord) + 255) & ~(size_t)255;
+		const size_t ib = (s->host.ids.size() * sizeof(TriIds) + 255) & ~(size_t)255;
+		LRB_CUDA(cudaMalloc(&s->dSlab, nb + tb + ib));
+		s->slabBytes = nb + tb + ib;
+		bytes += s->slabBytes;
+		s->dNodes = reinterpret_cast<WideNode *>(s->dSlab);
+		s->dTris = reinterpret_cast<TriRecord *>((char *)s->dSlab + nb);
+		s->dIds = reinterpret_cast<TriIds *>((char *)s->dSlab + nb + tb);
+		s->capNodes = s->host.wide.size();
+		LRB_CUDA(cudaMemcpyAsync(s->dNodes, s->host.wide.data(), s->host.wide.size() * sizeof(WideNode), cudaMemcpyHostToDevice, dev->stream));
+		if (!s->host.tris.empty()) {
+			LRB_CUDA(cudaMemcpyAsync(s->dTris, s->host.tris.data(), s->host.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice, dev->stream));
+			LRB_CUDA(cudaMemcpyAsync(s->dIds, s->host.ids.data(), s->host.ids.size() * sizeof(TriIds), cudaMemcpyHostToDevice, dev->stream));
+		}
+		dev->counters.h2d_bytes += s->slabBytes;
+	} else {
+		if ((rc = UploadArray(dev, s->host.wide, &s->dNodes, &s->capNodes, &bytes)) != LRB_OK) return rc;
+		if ((rc = UploadArray(dev, s->host.tris, &s->dTris, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+		if ((rc = UploadArray(dev, s->host.ids, &s->dIds, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
+	}
 	if ((rc = UploadArray(dev, s->host.insts, &s->dInsts, &s->capInsts, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.minv, &s->dMinv, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
 	if ((rc = UploadArray(dev, s->host.motionFirst, &s->dMotionFirst, (size_t *)nullptr, &bytes)) != LRB_OK) return rc;
@@ -544,6 +754,7 @@ static lrb_scene *NewScene(lrb_device *dev) {
 	lrb_scene *s = new lrb_scene();
 	s->dev = dev;
 	s->dNodes = nullptr; s->dTris = nullptr; s->dIds = nullptr; s->dInsts = nullptr; s->dMinv = nullptr;
+	s->dSlab = nullptr; s->slabBytes = 0;
 	s->dMotionFirst = s->dMotionLast = nullptr; s->dInterps = nullptr;
 	s->capNodes = s->capInsts = 0;
 	s->dCounter = nullptr; s->dSpillNode = nullptr; s->dSpillT = nullptr; s->spillEntries = 0;
@@ -562,7 +773,14 @@ int lrb_scene_free(lrb_scene *s) {
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
 	cudaStreamSynchronize(dev->stream);
-	cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dIds); cudaFree(s->dInsts); cudaFree(s->dMinv);
+	if (s->dSlab) {
+		if (dev->l2WindowBase == s->dSlab)
+			ClearL2Window(dev);
+		cudaFree(s->dSlab);
+	} else {
+		cudaFree(s->dNodes); cudaFree(s->dTris); cudaFree(s->dIds);
+	}
+	cudaFree(s->dInsts); cudaFree(s->dMinv);
 	cudaFree(s->dMotionFirst); cudaFree(s->dMotionLast); cudaFree(s->dInterps);
 	cudaFree(s->dCounter); cudaFree(s->dSpillNode); cudaFree(s->dSpillT); cudaFree(s->dStats); cudaFree(s->dWatermark); cudaFree(s->dChunkFlag);
 	{
@@ -826,6 +1044,10 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		return Fail(LRB_ERR_INVALID, "null ray/hit buffer");
 	if ((reinterpret_cast<uintptr_t>(rays) & 15u) != 0)
 		return Fail(LRB_ERR_INVALID, "ray buffer must be 16-byte aligned");
+	{
+		const int rcJoin = JoinPending(dev);    // chunked uploads / reads of the pipelined plugin sequence (no-op when there are none)
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 
 	TraceArgs a;
 	memset(&a, 0, sizeof(a));
@@ -883,6 +1105,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 		a.spillNode = s->dSpillNode;
 		a.spillT = s->dSpillT;
 		LRB_CUDA(cudaMemsetAsync(s->dCounter, 0, 2 * sizeof(uint32_t), stream));
+		if (stream == dev->stream && (rc = SetL2Window(dev, s->dSlab, s->slabBytes)) != LRB_OK) return rc;
 		// optional coherence pre-pass
 		// (measured on a 2 GB triangle soup: 614 -> 720 Mrays/s; on the L2-resident kitchen the sort costs what it gains)
 		const bool wantSort = dev->sortRays == 1 || (dev->sortRays == 2 && bigScene);
@@ -958,7 +1181,43 @@ int lrb_trace(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
 	if (!s)
 		return Fail(LRB_ERR_INVALID, "null scene");
 	LRB_SETDEV(s->dev);
-	return LaunchTrace(s, rays, hits, n, false, s->dev->stream);
+	lrb_device *dev = s->dev;
+	for (int k = 0; k < 2; ++k) {
+		lrb_device::Pending &u = dev->pendUpload[k];
+		if (!u.active || (const char *)rays != u.base || (size_t)n * sizeof(lrb_ray) != u.bytes || !hits || n == 0)
+			continue;
+		// the ray buffer is arriving in chunks: trace every chunk as it lands.  Any other pending upload (a pre-loaded
+		// RayHit buffer) must be complete before the first chunk writes.
+		lrb_device::Pending &o = dev->pendUpload[1 - k];
+		if (o.active && !o.ev.empty())
+			LRB_CUDA(cudaStreamWaitEvent(dev->stream, o.ev.back(), 0));
+		o.active = false;
+		const uint32_t chunkRays = (uint32_t)(u.chunkBytes / sizeof(lrb_ray));
+		const std::vector<cudaEvent_t> landed = u.ev;
+		u.active = false;       // (the launches below join whatever else is pending; the queue follows this upload chunk by chunk)
+		std::vector<cudaEvent_t> traced;
+		size_t c = 0;
+		for (uint32_t first = 0; first < n; first += chunkRays, ++c) {
+			const uint32_t cnt = std::min(chunkRays, n - first);
+			LRB_CUDA(cudaStreamWaitEvent(dev->stream, landed[c], 0));
+			int rc = LaunchTrace(s, (const lrb_ray *)rays + first, (lrb_rayhit *)hits + first, cnt, false, dev->stream);
+			if (rc != LRB_OK) {
+				for (size_t r = c + 1; r < landed.size(); ++r)      // the rest of the upload still belongs in front of what follows
+					cudaStreamWaitEvent(dev->stream, landed[r], 0);
+				return rc;
+			}
+			cudaEvent_t e;
+			if ((rc = PipeEvent(dev, &e)) != LRB_OK) return rc;
+			LRB_CUDA(cudaEventRecord(e, dev->stream));
+			traced.push_back(e);
+		}
+		lrb_device::Pending &t = dev->pendTraced;
+		t.base = (const char *)hits; t.bytes = (size_t)n * sizeof(lrb_rayhit); t.chunkBytes = (size_t)chunkRays * sizeof(lrb_rayhit);
+		t.ev.swap(traced);
+		t.active = true;
+		return LRB_OK;
+	}
+	return LaunchTrace(s, rays, hits, n, false, dev->stream);
 }
 
 int lrb_trace_anyhit(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
@@ -974,6 +1233,10 @@ int lrb_compact_rays(lrb_device *dev, const void *rays, uint32_t n, const uint32
 	if (!liveIdxDev || !liveCountDev)
 		return Fail(LRB_ERR_INVALID, "null out pointer");
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	*liveIdxDev = nullptr; *liveCountDev = nullptr;
 	if (liveCountHost) *liveCountHost = 0;
 	if (n == 0)
@@ -1015,6 +1278,10 @@ int lrb_advance_rays(lrb_scene *s, void *rays, void *hits, uint32_t n, const uin
 		return LRB_OK;
 	if (!rays || !hits)
 		return Fail(LRB_ERR_INVALID, "null ray/hit buffer");
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	uint32_t *cnt = s->dCounter + 8;        // a word of the scene's counter block the trace kernels do not use
 	LRB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), dev->stream));
 	AdvanceRaysKernel<<<(n + 255) / 256, 256, 0, dev->stream>>>((lrb_ray *)rays, (lrb_rayhit *)hits, n, passMeshBitsDev, nPassWords,
@@ -1068,6 +1335,10 @@ int lrb_trace_passthrough(lrb_scene *s, void *rays, void *hits, uint32_t n, cons
 
 int lrb_film_reduce(lrb_device *dev, const float *const *tilesDev, uint32_t nTiles, float *dstDev, uint64_t first, uint64_t count) {
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	if (count == 0)
 		return LRB_OK;
 	if (!tilesDev || !dstDev || nTiles == 0 || nTiles > (uint32_t)kMaxFilmTiles)
@@ -1100,6 +1371,10 @@ int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, ui
 	if (nLeaves == 0 || nLeaves >= 0x3fffffffu)
 		return Fail(LRB_ERR_INVALID, "leaf count out of range");
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	*nNodes = 0;
 	if (timings) memset(timings, 0, sizeof(*timings));
 	if (nLeaves == 1) {
@@ -1304,6 +1579,10 @@ int lrb_trace_gather(lrb_scene *s, const void *rays, void *hits, uint32_t n, voi
 		return Fail(LRB_ERR_INVALID, "null scene");
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	if (n == 0)
 		return LRB_OK;
 	if (!rays || !dst || (!hits && nChunks != 0))
@@ -1391,6 +1670,10 @@ int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t
 		return Fail(LRB_ERR_INVALID, "null scene");
 	lrb_device *dev = s->dev;
 	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
 	if (n == 0)
 		return LRB_OK;
 	if (!rays || !hits)

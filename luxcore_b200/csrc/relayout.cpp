@@ -11,7 +11,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <cstdlib>
+#include <exception>
 #include <stdexcept>
+#include <thread>
 
 namespace lrb {
 
@@ -594,41 +597,73 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		}
 	}
 
-	// Pass 2: fill, children in reference order.
-	std::vector<uint32_t> kids;
-	std::vector<std::pair<double, uint32_t> > keyed;
-	for (uint32_t i = 0; i < in.n; ++i) {
-		if (IsLeaf(nodes[i].nodeData))
-			continue;
-		kids.clear();
-		const uint32_t end = Skip(nodes[i].nodeData);
-		for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData))
-			kids.push_back(c);
-		// Slot order = ascending box size.  The kernel sorts the children of a node by entry distance with
-		// a network that keeps the slot order of equal keys, and for a ray that STARTS inside several child
-		// boxes (every bounce ray does, near the root) all those keys equal ray.mint: visiting the smaller
-		// box first finds a near hit sooner and culls more of the rest (kitchen, bounce-2 rays: 16.2 -> 15.6
-		// node visits and 5.4 -> 4.8 triangle tests per ray).  Order never changes a result.
-		if (kids.size() > 1) {
-			keyed.clear();
-			for (uint32_t c : kids)
-				keyed.push_back(std::make_pair(SlotSizeKey(in, c), c));
-			std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<double, uint32_t> &a, const std::pair<double, uint32_t> &b) { return a.first < b.first; });
-			for (size_t k = 0; k < kids.size(); ++k)
-				kids[k] = keyed[k].second;
+	// Pass 2: fill, children in reference order.  Every inner node writes its own wide node(s) and its own
+	// triangle records (indices fixed in pass 1), so ranges of the array are filled concurrently for big triangle
+	// trees (a 50 M-triangle soup: 74 M reference nodes); instance trees append to `insts` and stay serial.
+	auto fillRange = [&](const uint32_t i0, const uint32_t i1) {
+		std::vector<uint32_t> kids;
+		std::vector<std::pair<double, uint32_t> > keyed;
+		for (uint32_t i = i0; i < i1; ++i) {
+			if (IsLeaf(nodes[i].nodeData))
+				continue;
+			kids.clear();
+			const uint32_t end = Skip(nodes[i].nodeData);
+			for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData))
+				kids.push_back(c);
+			// Slot order = ascending box size.  The kernel sorts the children of a node by entry distance with
+			// a network that keeps the slot order of equal keys, and for a ray that STARTS inside several child
+			// boxes (every bounce ray does, near the root) all those keys equal ray.mint: visiting the smaller
+			// box first finds a near hit sooner and culls more of the rest (kitchen, bounce-2 rays: 16.2 -> 15.6
+			// node visits and 5.4 -> 4.8 triangle tests per ray).  Order never changes a result.
+			if (kids.size() > 1) {
+				keyed.clear();
+				for (uint32_t c : kids)
+					keyed.push_back(std::make_pair(SlotSizeKey(in, c), c));
+				std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<double, uint32_t> &a, const std::pair<double, uint32_t> &b) { return a.first < b.first; });
+				for (size_t k = 0; k < kids.size(); ++k)
+					kids[k] = keyed[k].second;
+			}
+			const uint32_t nW = std::max<uint32_t>(1u, ((uint32_t)kids.size() + kWideSlots - 1) / kWideSlots);
+			for (uint32_t j = 0; j < nW; ++j) {
+				const uint32_t first = j * kWideSlots;
+				const uint32_t cnt = std::min<uint32_t>(kWideSlots, (uint32_t)kids.size() - std::min<uint32_t>((uint32_t)kids.size(), first));
+				SlotBoxes b;
+				// the node's own box bounds every child; MBVH root leaves (no box of their own) take it whole
+				b.hasOwn = true;
+				for (int a = 0; a < 3; ++a) { b.ownLo[a] = nodes[i].bvhNode.bboxMin[a]; b.ownHi[a] = nodes[i].bvhNode.bboxMax[a]; }
+				for (uint32_t k = 0; k < cnt; ++k)
+					AddSlot(in, wideOf, kids[first + k], &nodes[i], &b, out);
+				QuantizeNode(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
+			}
 		}
-		const uint32_t nW = std::max<uint32_t>(1u, ((uint32_t)kids.size() + kWideSlots - 1) / kWideSlots);
-		for (uint32_t j = 0; j < nW; ++j) {
-			const uint32_t first = j * kWideSlots;
-			const uint32_t cnt = std::min<uint32_t>(kWideSlots, (uint32_t)kids.size() - std::min<uint32_t>((uint32_t)kids.size(), first));
-			SlotBoxes b;
-			// the node's own box bounds every child; MBVH root leaves (no box of their own) take it whole
-			b.hasOwn = true;
-			for (int a = 0; a < 3; ++a) { b.ownLo[a] = nodes[i].bvhNode.bboxMin[a]; b.ownHi[a] = nodes[i].bvhNode.bboxMax[a]; }
-			for (uint32_t k = 0; k < cnt; ++k)
-				AddSlot(in, wideOf, kids[first + k], &nodes[i], &b, out);
-			QuantizeNode(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
+	};
+	unsigned nThreads = 1;
+	if (!in.instLeaves && in.n >= 400000u) {
+		nThreads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+		if (const char *env = getenv("LRB_RELAYOUT_THREADS"))
+			nThreads = (unsigned)std::max(1, atoi(env));
+	}
+	if (nThreads <= 1)
+		fillRange(0, in.n);
+	else {
+		std::vector<std::thread> pool;
+		std::vector<std::exception_ptr> errors(nThreads);
+		const uint64_t per = ((uint64_t)in.n + nThreads - 1) / nThreads;
+		for (unsigned t = 0; t < nThreads; ++t) {
+			const uint32_t i0 = (uint32_t)std::min<uint64_t>(in.n, per * t), i1 = (uint32_t)std::min<uint64_t>(in.n, per * (t + 1));
+			pool.emplace_back([&, t, i0, i1]() {
+				try {
+					fillRange(i0, i1);
+				} catch (...) {
+					errors[t] = std::current_exception();
+				}
+			});
 		}
+		for (std::thread &th : pool)
+			th.join();
+		for (unsigned t = 0; t < nThreads; ++t)
+			if (errors[t])
+				std::rethrow_exception(errors[t]);
 	}
 
 	// Worst-case live stack entries.  Children always have larger wide indices than their parent

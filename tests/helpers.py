@@ -186,7 +186,7 @@ class Emu:
                    os.path.join(ROOT, "luxcore_b200", "csrc", "relayout.cpp")]
             deps = src + [os.path.join(ROOT, "luxcore_b200", "csrc", f) for f in ("traverse.h", "layout.h", "relayout.h")]
             if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse", "-msse2", "-mfma", "-ffp-contract=off"] + (["-DLRB_EXIT_ORDER=" + os.environ["LRB_EXIT_ORDER"]] if "LRB_EXIT_ORDER" in os.environ else []) + [
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-msse", "-msse2", "-mfma", "-ffp-contract=off"] + (["-DLRB_EXIT_ORDER=" + os.environ["LRB_EXIT_ORDER"]] if "LRB_EXIT_ORDER" in os.environ else []) + [
                                        "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "luxcore_b200", "csrc"),
                                        "-o", so] + src)
             L = C.CDLL(so)
