@@ -77,6 +77,7 @@ struct lrb_device {
 	const void *l2WindowBase;       // window currently set on the queue (stream attribute), or NULL
 	size_t l2WindowBytes;
 	int prefetch;                   // L2 prefetch of the children pushed on the stack: 0 never, 1 always, 2 when the scene does not fit L2
+	int prefetchMode;               // what the prefetching kernels fetch ahead: bit 0 pushed children -> L2, bit 1 nearest child -> L2, bit 2 nearest child -> L1
 	int sortRays;                   // order the rays of a batch for coherence before tracing them: 0 never, 1 always, 2 when the scene does not fit L2
 	int sortBitsPerAxis;            // origin-cell resolution of the sort key
 	int sortMinRays;                // batches smaller than this are traced in index order
@@ -265,6 +266,7 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortRays = 2;
 	dev->prefetch = 0;      // prepared, not yet measured on a GPU: off
 	dev->carveout = -1;
+	dev->prefetchMode = 1;
 	dev->l2Persist = 0;     // measured on B200 (profiles/r02_measure_ingest_c10.json): no gain alone, no protection against concurrent traffic
 	dev->l2WindowBase = nullptr;
 	dev->l2WindowBytes = 0;
@@ -401,6 +403,9 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "prefetch") {
 		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "prefetch must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
 		dev->prefetch = iv;
+	} else if (k == "prefetch_mode") {
+		if (iv < 1 || iv > 7) return Fail(LRB_ERR_INVALID, "prefetch_mode is a bit mask 1..7 (1 pushed children -> L2, 2 nearest child -> L2, 4 nearest child -> L1)");
+		dev->prefetchMode = iv;
 	} else if (k == "sort_rays") {
 		if (iv < 0 || iv > 2) return Fail(LRB_ERR_INVALID, "sort_rays must be 0 (never), 1 (always) or 2 (scenes larger than L2)");
 		dev->sortRays = iv;
@@ -1065,6 +1070,7 @@ static int LaunchTrace(lrb_scene *s, const void *rays, void *hits, uint32_t n, b
 	a.refillBelow = (uint32_t)dev->refillBelow;
 	a.triBias = (uint32_t)dev->triBias;
 	a.instBias = (uint32_t)dev->instBias;
+	a.prefetchMode = (uint32_t)dev->prefetchMode;
 	const bool two = s->view.twoLevel != 0;
 	const int sm = dev->prop.multiProcessorCount;
 	int rc;

@@ -229,6 +229,7 @@ struct TraceArgs {
 	uint32_t refillBelow;       // re-fill when fewer live lanes than this
 	uint32_t triBias;           // triangle phase runs when nTri * triBias >= nNode * 4 (4 = plain majority)
 	uint32_t instBias;          // two-level: instances are entered when nInst * instBias >= max(nNode * 4, nTri * triBias); 0 = at once
+	uint32_t prefetchMode;      // PREFETCH kernels: see NodeStep
 	TraceStats *stats;          // STATS kernels only
 	// Multi-GPU gather fused into the trace: when set, every RayHit record is ALSO stored here -- this
 	// rank's slice of the gather buffer on the destination GPU, peer-mapped over NVLink.  The five
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(kTraceBlock, TWO_LEVEL ? LRB_MINBLOCKS_2L : LR
 				}
 			} else {
 				if (work == kWorkNode) {
-					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr);
+					NodeStep<TWO_LEVEL, false, PREFETCH>(a.sc, s, stk, nullptr, a.prefetchMode);
 					PopSpec<TWO_LEVEL>(s, stk);
 				}
 			}

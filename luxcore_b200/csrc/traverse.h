@@ -100,8 +100,10 @@ __device__ __forceinline__ F8 Ld256(const void *p) {
 }
 // L2 prefetch of the record a child reference points at (scenes that do not fit L2; see NodeStep).
 __device__ __forceinline__ void PrefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void PrefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #else
 static inline void PrefetchL2(const void *) { }
+static inline void PrefetchL1(const void *) { }
 static inline F8 Ld256(const void *p) { F8 r; __builtin_memcpy(&r, p, 32); return r; }
 static inline uint32_t HostF2U(float x) { uint32_t u; __builtin_memcpy(&u, &x, 4); return u; }
 static inline float HostU2F(uint32_t u) { float x; __builtin_memcpy(&x, &u, 4); return x; }
@@ -612,8 +614,11 @@ LRB_HD float SlotEntry(const RayState &s, const uint32_t one, const uint32_t nqx
 // waits for): the records of the children that go on the stack are requested into L2 now; by the time
 // one of them is popped its fetch hits L2.  Entries that are culled before they are popped cost
 // bandwidth (plentiful: a latency-bound walk uses a small fraction of HBM), not time.
+// pfMode (PREFETCH kernels; device option prefetch_mode): bit 0 = the pushed children into L2, bit 1 = the NEAREST child
+// -- the record this lane fetches next, whatever happens, about a hundred issue slots from now -- into L2, bit 2 =
+// the nearest child into L1.
 template <bool TWO_LEVEL, bool STATS, bool PREFETCH = false, class STACK>
-LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats) {
+LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *stats, const uint32_t pfMode = 1u) {
 	// ---- fetch the 64-byte node with two 256-bit loads ----
 	const char *np = reinterpret_cast<const char *>(sc.nodes + s.cur);
 	if (STATS) stats->wideNodes++;
@@ -666,6 +671,14 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 	LRB_CSWAP(d1, c1, d2, c2)
 #undef LRB_CSWAP
 
+	if (PREFETCH && (pfMode & 6u)) {
+		if (d0 < kInf && c0 < kTagInstance) {
+			const char *p0 = ((c0 & kTagTri) ? reinterpret_cast<const char *>(sc.tris) : reinterpret_cast<const char *>(sc.nodes)) +
+					((size_t)(c0 & kRefIndexMask) << 6);
+			if (pfMode & 2u) PrefetchL2(p0);
+			if (pfMode & 4u) PrefetchL1(p0);
+		}
+	}
 	// push far-to-near, continue with the nearest.  A continuation node (reference nodes with more
 	// than four children) is always visited.
 	const bool h1 = d1 < kInf, h2 = d2 < kInf, h3 = d3 < kInf;
@@ -680,7 +693,7 @@ LRB_HD void NodeStep(const SceneView &sc, RayState &s, STACK &stk, TraceStats *s
 		if (h2) stk.push(c2, d2);
 		if (h1) stk.push(c1, d1);
 	}
-	if (PREFETCH) {
+	if (PREFETCH && (pfMode & 1u)) {
 		// wide nodes and triangle records are both 64 bytes: one address computation serves either
 		const char *nb = reinterpret_cast<const char *>(sc.nodes), *tb = reinterpret_cast<const char *>(sc.tris);
 		if (h1 && c1 < kTagInstance) PrefetchL2(((c1 & kTagTri) ? tb : nb) + ((size_t)(c1 & kRefIndexMask) << 6));

@@ -24,13 +24,14 @@ ap.add_argument("--no-parity", action="store_true")
 ap.add_argument("--quick", action="store_true", help="default options only (A/B of differently compiled libraries, LRB_LIB_DIR)")
 ap.add_argument("--opt", action="append", default=[], help="device option key=value applied to every variant")
 ap.add_argument("--tag", default="")
+ap.add_argument("--prefetch-modes", action="store_true", help="soup: sweep of what the prefetching kernel fetches ahead (device option prefetch_mode)")
 ARGS = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 rows = []
-DEFAULTS0 = {"smem_depth": 16, "refill_below": 24, "tri_bias": 8, "inst_bias": 8, "sort_rays": 2, "prefetch": 0,
+DEFAULTS0 = {"smem_depth": 16, "refill_below": 24, "tri_bias": 8, "inst_bias": 8, "sort_rays": 2, "prefetch": 0, "prefetch_mode": 1,
             "blocks_per_sm": 0, "carveout": -1, "sort_bits": 5, "kernel": "persistent"}
 DEFAULTS = dict(DEFAULTS0)
 for kv in ARGS.opt:
@@ -250,6 +251,11 @@ def section_soup(n_tris):
          ("sorted 7 bits, simple kernel", {"sort_rays": 1, "sort_bits": 7, "kernel": "simple"})]
     if ARGS.quick:
         v = [("sorted 5 bits (what sort_rays = auto picks for a scene larger than L2)", {"sort_rays": 1, "sort_bits": 5})]
+    if ARGS.prefetch_modes:
+        v = [("sorted 5 bits", {"sort_rays": 1, "sort_bits": 5})]
+        v += [("sorted 5 bits + prefetch mode %d" % m, {"sort_rays": 1, "sort_bits": 5, "prefetch": 1, "prefetch_mode": m}) for m in (2, 4, 6, 3, 1)]
+        v += [("index order + prefetch mode %d" % m, {"sort_rays": 0, "prefetch": 1, "prefetch_mode": m}) for m in (2, 4)]
+        v += [("sorted 5 bits again", {"sort_rays": 1, "sort_bits": 5})]
     sweep(sess, "soup:%d" % n_tris, "uniform", rays, v, orc, sample=20000)
     # probes for the roofline denominators, same process / same clocks
     dv = capi.Device.borrow(sess.native_device())
