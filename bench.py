@@ -243,6 +243,8 @@ def main():
                     "slice (default 1: plain kernel + one push, measured fastest); 0 = ONE kernel that signals finished chunks to the copy stream")
     ap.add_argument("--no-pipeline", action="store_true", help="p2p gather: every step waits for its own pushes and completion signal "
                     "(default: the tail of step k's pushes and its signal overlap the trace of step k + 1; two RayHit buffers)")
+    ap.add_argument("--completion", default="flag", choices=["flag", "nccl"], help="pipelined p2p gather: completion signal = a step counter written by the "
+                    "copy engine into rank 0's memory (default) or a 4-byte ncclAllReduce on a side stream")
     ap.add_argument("--timeline", action="store_true", help="N > 1: CUDA-event breakdown of un-pipelined steps per rank (kernel / tail of the pushes / signal)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -327,21 +329,29 @@ def main():
     pipeline = gather_mode == "p2p" and not args.no_pipeline
     n_buf = 2 if pipeline else 1
     gbuf_local, gbuf_peer, my_dst, glist = [], [], [], None
+    flags_local, flags_peer, my_flag = 0, 0, 0
     hits_buf = [hits] + ([torch.empty((n, 20), dtype=torch.uint8, device=device)] if pipeline else [])
     side = torch.cuda.Stream(device=device) if pipeline else None
     if gather_mode in ("p2p", "direct"):
         import torch.distributed as dist
         if rank == 0:
             gbuf_local = [dev_view.alloc(total_rays * 20) for _ in range(n_buf)]
-            handle = [[dev_view.ipc_get_handle(p) for p in gbuf_local]]
+            # one completion flag per rank (step counters), written by the ranks' copy engines, waited for on this GPU's queue
+            flags_local = dev_view.alloc(4 * world)
+            dev_view.h2d(flags_local, np.zeros(world, dtype=np.uint32), blocking=True)
+            handle = [[dev_view.ipc_get_handle(p) for p in gbuf_local + [flags_local]]]
         else:
             handle = [None]
         dist.broadcast_object_list(handle, src=0)
         if rank == 0:
             my_dst = list(gbuf_local)
+            my_flag = flags_local
         else:
-            gbuf_peer = [dev_view.ipc_open_handle(h) for h in handle[0]]
+            opened = [dev_view.ipc_open_handle(h) for h in handle[0]]
+            gbuf_peer = opened[:n_buf]
+            flags_peer = opened[n_buf]
             my_dst = [p + offsets[rank] * 20 for p in gbuf_peer]
+            my_flag = flags_peer + 4 * rank
         flag = torch.zeros(1, dtype=torch.int32, device=device)
         if pipeline:
             sess.set_option("gather_defer", 1)
@@ -373,6 +383,11 @@ def main():
                 probe[0][-1][1].record(stream)
             if not pipeline:
                 dist.all_reduce(flag)           # 4-byte "batch complete" signal, ordered after the pushes
+            elif args.completion == "flag":
+                # completion signal of step k: this rank's step counter, written into rank 0's flag word by the copy engine
+                # behind the push -- no kernel, no NCCL (an all-reduce kernel cannot run next to a persistent trace kernel
+                # that fills every SM: measured +0.25 ms per step at >= 4 GPUs)
+                dev_view.gather_signal(my_flag, step_no[0] & 0xFFFF)
             else:
                 # the signal of step k rides on a side stream behind this step's kernel and pushes; the queue goes on
                 done = torch.cuda.Event()
@@ -394,10 +409,15 @@ def main():
         """Everything the steps left in flight joins the queue (inside the timed region)."""
         if pipeline:
             dev_view.gather_wait(0, -1)
-            for w in pending:
-                w.wait()
-            del pending[:]
-            stream.wait_stream(side)
+            if args.completion == "flag":
+                if rank == 0:       # the gathered batch is complete when every rank's counter has reached this step
+                    for r in range(world):
+                        dev_view.wait_value(flags_local + 4 * r, step_no[0] & 0xFFFF)
+            else:
+                for w in pending:
+                    w.wait()
+                del pending[:]
+                stream.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -582,7 +602,8 @@ def main():
            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic rays (seeded, generated on the GPU) over " + ("a synthetic triangle soup" if is_soup(args.scene) else "the reference's %s scene geometry" % args.scene),
            "config": config, "gpu_launches": launches,
-           "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "pipelined": pipeline, "verified": gather_ok,
+           "gather": {"mode": gather_mode, "chunks": args.chunks if gather_mode == "p2p" else None, "pipelined": pipeline,
+                      "signal": (args.completion if pipeline else ("nccl" if gather_mode == "p2p" else None)), "verified": gather_ok,
                       "bytes_per_step_into_rank0": (total_rays - counts[0]) * 20 if world > 1 else 0},
            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 20,
                    "api": "lrb_trace_host (C ABI, pinned host buffers, chunked copy/trace overlap)",
@@ -680,10 +701,10 @@ def main():
         import torch.distributed as dist
         dist.barrier()
         torch.cuda.synchronize()
-        for p_ in gbuf_peer:
+        for p_ in gbuf_peer + ([flags_peer] if flags_peer else []):
             dev_view.ipc_close_handle(p_)
         dist.barrier()
-        for p_ in gbuf_local:
+        for p_ in gbuf_local + ([flags_local] if flags_local else []):
             dev_view.free(p_)
     sess.stop()
     sess.close()

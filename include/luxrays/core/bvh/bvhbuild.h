@@ -67,6 +67,9 @@ extern ocl::BVHArrayNode *BuildEmbreeBVHBinnedSAH(const BVHParams &params, u_int
 		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
 extern ocl::BVHArrayNode *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes,
 		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
+// extension: builder type "B200_PLOC" -- the GPU builder with a PLOC binary tree (luxcore_b200/csrc/build_kernels.cuh)
+extern ocl::BVHArrayNode *BuildB200BVHPloc(const BVHParams &params, u_int *nNodes,
+		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
 
 }   // namespace luxrays
 

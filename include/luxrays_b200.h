@@ -292,6 +292,14 @@ LRB_API int lrb_trace_gather(lrb_scene *scene, const void *rays_dev, void *hits_
  * device's queue) wait for the pushes of the most recent call (which = 0), the one before it (1) or both (-1).
  * A completion signal for the gathering rank belongs behind this wait. */
 LRB_API int lrb_gather_wait(lrb_device *dev, void *cuda_stream, int which);
+/* Completion signal without a kernel and without NCCL: lrb_gather_signal writes `value` (a 16-bit step counter) into the
+ * 32-bit flag word flag_dev -- normally a word of the gathering GPU's memory, peer-mapped like the gather buffer -- as
+ * a 4-byte copy-engine transfer ordered behind this rank's pushes and behind everything queued so far.  On the
+ * gathering GPU lrb_wait_value makes a stream (NULL = the device's queue) wait until that word is >= value
+ * (cuStreamWaitValue32): no SM is involved on either side, so the signal is not serialised against a persistent trace
+ * kernel that occupies every SM (which is what happens to a 4-byte ncclAllReduce: +0.25 ms per 5 ms step at >= 4 GPUs). */
+LRB_API int lrb_gather_signal(lrb_device *dev, void *flag_dev, uint32_t value);
+LRB_API int lrb_wait_value(lrb_device *dev, void *flag_dev, uint32_t value, void *cuda_stream);
 
 /* ---- BVH construction on the device ------------------------------------------------------------- */
 /* Replaces BuildEmbreeBVHMorton (src/luxrays/core/bvh/bvhembreebuild.cpp:218-336 with rtcBVHBuilderMorton,
@@ -307,6 +315,12 @@ typedef struct {
 	uint32_t kernels;                                   /* own kernels launched (CUB's passes not counted) */
 } lrb_build_timings;
 LRB_API int lrb_build_lbvh(lrb_device *dev, const float *leaf_boxes, uint32_t n_leaves, uint32_t tree_type,
+		lrb_bvh_node *out_nodes, uint32_t out_capacity, uint32_t *n_nodes, lrb_build_timings *timings);
+/* Same interface with a choice of binary tree under the k-ary collapse: quality 0 = the radix tree of lrb_build_lbvh
+ * (EMBREE_MORTON's trade-off: fastest build, dearest traversal), quality 1 = PLOC, parallel locally-ordered
+ * clustering (Meister & Bittner 2018) with search radius 16 -- the stand-in for BuildEmbreeBVHBinnedSAH
+ * (bvhembreebuild.cpp:218-336) when the tree is to be built on the GPU (host layer: builder type "B200_PLOC"). */
+LRB_API int lrb_build_bvh(lrb_device *dev, const float *leaf_boxes, uint32_t n_leaves, uint32_t tree_type, uint32_t quality,
 		lrb_bvh_node *out_nodes, uint32_t out_capacity, uint32_t *n_nodes, lrb_build_timings *timings);
 
 /* ---- multi-GPU: film merge over NVLink -------------------------------------------------------- */

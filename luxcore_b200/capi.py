@@ -34,7 +34,7 @@ EXPORTS = [
     "lrb_last_error_string", "lrb_get_counters", "lrb_reset_counters", "lrb_version_string",
     "lrb_measure_read_bandwidth",
     "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait", "lrb_film_reduce",
-    "lrb_build_lbvh",
+    "lrb_build_lbvh", "lrb_build_bvh", "lrb_gather_signal", "lrb_wait_value",
 ]
 
 
@@ -131,6 +131,9 @@ def lib():
             "lrb_gather_wait": (i32, [vp, vp, i32]),
             "lrb_film_reduce": (i32, [vp, C.POINTER(vp), u32, vp, u64, u64]),
             "lrb_build_lbvh": (i32, [vp, vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(BuildTimings)]),
+            "lrb_gather_signal": (i32, [vp, vp, u32]),
+            "lrb_wait_value": (i32, [vp, vp, u32, vp]),
+            "lrb_build_bvh": (i32, [vp, vp, u32, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(BuildTimings)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -245,6 +248,14 @@ class Device:
         """Deferred gathers (option gather_defer): make a stream wait for the pushes of the last (0) / previous (1) / both (-1) calls."""
         _check(lib().lrb_gather_wait(self.h, C.c_void_p(cuda_stream_handle or 0), which))
 
+    def gather_signal(self, flag_devptr, value):
+        """Write `value` into the 32-bit flag word (local or peer-mapped) behind this device's pushes: copy engine only."""
+        _check(lib().lrb_gather_signal(self.h, C.c_void_p(flag_devptr), value))
+
+    def wait_value(self, flag_devptr, value, cuda_stream_handle=0):
+        """Make a stream (0 = the device's queue) wait until the flag word (this device's memory) is >= value."""
+        _check(lib().lrb_wait_value(self.h, C.c_void_p(flag_devptr), value, C.c_void_p(cuda_stream_handle or 0)))
+
     def film_reduce(self, tile_devptrs, dst_devptr, first, count):
         """dst[first:first+count] = sum of the tiles' float planes in list order (Film::AddFilm order), asynchronous."""
         arr = (C.c_void_p * len(tile_devptrs))(*[C.c_void_p(p) for p in tile_devptrs])
@@ -265,10 +276,10 @@ class Device:
         _check(lib().lrb_ipc_close_handle(self.h, C.c_void_p(devptr)))
 
     # ---- BVH construction on the device ----
-    def build_lbvh(self, leaf_boxes, tree_type=4, node_dtype=None):
-        """GPU linear-BVH builder (lrb_build_lbvh): leaf_boxes [n, 6] float32 (min xyz, max xyz) -> (BVHArrayNode array
-        as a [n_nodes] array of 32-byte records, BuildTimings).  Leaf records carry the input index of their leaf in
-        their first word; the caller writes the leaf payload in."""
+    def build_lbvh(self, leaf_boxes, tree_type=4, node_dtype=None, quality=0):
+        """GPU BVH builder (lrb_build_bvh; quality 0 = radix tree = lrb_build_lbvh, 1 = PLOC): leaf_boxes [n, 6] float32
+        (min xyz, max xyz) -> (BVHArrayNode array as a [n_nodes] array of 32-byte records, BuildTimings).  Leaf records
+        carry the input index of their leaf in their first word; the caller writes the leaf payload in."""
         boxes = np.ascontiguousarray(leaf_boxes, dtype=np.float32).reshape(-1, 6)
         n = boxes.shape[0]
         dt = node_dtype or np.dtype([("w", "<u4", 6), ("nodeData", "<u4"), ("pad0", "<i4")])
@@ -276,7 +287,7 @@ class Device:
         out = np.zeros(max(1, 2 * n), dtype=dt)
         total = C.c_uint32()
         tm = BuildTimings()
-        _check(lib().lrb_build_lbvh(self.h, _ptr(boxes), n, tree_type, _ptr(out), out.shape[0], C.byref(total), C.byref(tm)))
+        _check(lib().lrb_build_bvh(self.h, _ptr(boxes), n, tree_type, quality, _ptr(out), out.shape[0], C.byref(total), C.byref(tm)))
         return out[:total.value].copy(), tm
 
     # ---- scenes ----

@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -102,6 +103,7 @@ struct lrb_device {
 	size_t pipeEventNext;
 	cudaEvent_t pipeJoin;
 	bool copyOutBusy;               // the copy-out stream holds chunked reads the queue has not joined yet
+	uint32_t *signalValues;         // lrb_gather_signal: table of step values in device memory
 	// staging for lrb_trace_host
 	void *stageRays, *stageHits;
 	size_t stageRaysBytes, stageHitsBytes;
@@ -177,6 +179,7 @@ static int JoinPending(lrb_device *dev) {
 		LRB_CUDA(cudaEventRecord(dev->pipeJoin, dev->copyOutStream));
 		LRB_CUDA(cudaStreamWaitEvent(dev->stream, dev->pipeJoin, 0));
 		dev->copyOutBusy = false;
+	dev->signalValues = nullptr;
 	}
 	return LRB_OK;
 }
@@ -305,6 +308,7 @@ int lrb_device_destroy(lrb_device *dev) {
 	for (size_t i = 0; i < dev->events.size(); ++i) cudaEventDestroy(dev->events[i]);
 	for (size_t i = 0; i < dev->pipeEvents.size(); ++i) cudaEventDestroy(dev->pipeEvents[i]);
 	if (dev->pipeJoin) cudaEventDestroy(dev->pipeJoin);
+	cudaFree(dev->signalValues);
 	for (int i = 0; i < 2; ++i) if (dev->gatherDone[i]) cudaEventDestroy(dev->gatherDone[i]);
 	if (dev->stageRays) cudaFree(dev->stageRays);
 	if (dev->stageHits) cudaFree(dev->stageHits);
@@ -1368,12 +1372,14 @@ int lrb_film_reduce(lrb_device *dev, const float *const *tilesDev, uint32_t nTil
 
 // ---- BVH construction on the device (build_kernels.cuh) ---------------------------------------------------
 
-int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, lrb_bvh_node *outNodes,
+int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, uint32_t quality, lrb_bvh_node *outNodes,
 		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
 	if (!leafBoxes || !outNodes || !nNodes)
 		return Fail(LRB_ERR_INVALID, "null argument");
 	if (treeType != 2 && treeType != 4 && treeType != 8)
 		return Fail(LRB_ERR_INVALID, "tree type must be 2, 4 or 8 (bvhaccel.cpp:51)");
+	if (quality > 1)
+		return Fail(LRB_ERR_INVALID, "builder quality must be 0 (radix tree) or 1 (PLOC)");
 	if (nLeaves == 0 || nLeaves >= 0x3fffffffu)
 		return Fail(LRB_ERR_INVALID, "leaf count out of range");
 	LRB_SETDEV(dev);
@@ -1393,28 +1399,28 @@ int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, ui
 		*nNodes = 1;
 		return LRB_OK;
 	}
-	const uint32_t levelStep = treeType == 2 ? 1u : (treeType == 4 ? 2u : 3u);
-	const int n = (int)nLeaves, nInner = n - 1;
+	const uint32_t n = nLeaves, nInner = n - 1, nAll = 2 * n - 1;
 	cudaStream_t st = dev->stream;
 	cudaEvent_t ev[6];
 	for (int i = 0; i < 6; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
 	BuildEvents evGuard = { ev, 6 };
+	uint32_t launches = 0;
 
-	DevBuf dBoxes, dBounds, dKeys[2], dVals[2], dTemp, dLeft, dRight, dParI, dParL, dDepth, dBox, dSize, dArrived, dOut;
+	DevBuf dBoxes, dBounds, dKeys[2], dVals[2], dTemp, dLeft, dRight, dParent, dNodeBox, dSize, dArrived, dKept, dOut, dCounters;
 	LRB_CUDA(cudaMalloc(&dBoxes.p, (size_t)n * 24));
 	LRB_CUDA(cudaMalloc(&dBounds.p, 32));
 	for (int k = 0; k < 2; ++k) {
 		LRB_CUDA(cudaMalloc(&dKeys[k].p, (size_t)n * 8));
 		LRB_CUDA(cudaMalloc(&dVals[k].p, (size_t)n * 4));
 	}
-	LRB_CUDA(cudaMalloc(&dLeft.p, (size_t)nInner * 4));
-	LRB_CUDA(cudaMalloc(&dRight.p, (size_t)nInner * 4));
-	LRB_CUDA(cudaMalloc(&dParI.p, (size_t)nInner * 4));
-	LRB_CUDA(cudaMalloc(&dParL.p, (size_t)n * 4));
-	LRB_CUDA(cudaMalloc(&dDepth.p, (size_t)nInner * 4));
-	LRB_CUDA(cudaMalloc(&dBox.p, (size_t)nInner * 24));
+	LRB_CUDA(cudaMalloc(&dLeft.p, (size_t)nAll * 4));
+	LRB_CUDA(cudaMalloc(&dRight.p, (size_t)nAll * 4));
+	LRB_CUDA(cudaMalloc(&dParent.p, (size_t)nAll * 4));
+	LRB_CUDA(cudaMalloc(&dNodeBox.p, (size_t)nAll * 24));
 	LRB_CUDA(cudaMalloc(&dSize.p, (size_t)nInner * 4));
 	LRB_CUDA(cudaMalloc(&dArrived.p, (size_t)nInner * 4));
+	LRB_CUDA(cudaMalloc(&dKept.p, (size_t)nInner));
+	LRB_CUDA(cudaMalloc(&dCounters.p, 64));
 
 	LRB_CUDA(cudaEventRecord(ev[0], st));
 	LRB_CUDA(cudaMemcpyAsync(dBoxes.p, leafBoxes, (size_t)n * 24, cudaMemcpyHostToDevice, st));
@@ -1424,39 +1430,112 @@ int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, ui
 	// 1 + 2: centroid bounds, Morton codes, sort
 	const uint32_t initBounds[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
 	LRB_CUDA(cudaMemcpyAsync(dBounds.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
-	const int blocks = (n + 255) / 256;
-	CentroidBoundsKernel<<<std::min(blocks, dev->prop.multiProcessorCount * 8), 256, 0, st>>>(dBoxes.as<float>(), nLeaves, dBounds.as<uint32_t>());
-	MortonKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), nLeaves, dBounds.as<uint32_t>(), dKeys[0].as<uint64_t>(), dVals[0].as<uint32_t>());
+	const int blocks = (int)((n + 255) / 256);
+	CentroidBoundsKernel<<<std::min(blocks, dev->prop.multiProcessorCount * 8), 256, 0, st>>>(dBoxes.as<float>(), n, dBounds.as<uint32_t>());
+	MortonKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), n, dBounds.as<uint32_t>(), dKeys[0].as<uint64_t>(), dVals[0].as<uint32_t>());
+	launches += 2;
 	cub::DoubleBuffer<uint64_t> keys(dKeys[0].as<uint64_t>(), dKeys[1].as<uint64_t>());
 	cub::DoubleBuffer<uint32_t> vals(dVals[0].as<uint32_t>(), dVals[1].as<uint32_t>());
-	size_t tempBytes = 0;
-	LRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, vals, n, 0, 63, st));
-	LRB_CUDA(cudaMalloc(&dTemp.p, std::max<size_t>(tempBytes, 16)));
-	LRB_CUDA(cub::DeviceRadixSort::SortPairs(dTemp.p, tempBytes, keys, vals, n, 0, 63, st));
+	size_t tempBytes = 0, selectBytes = 0;
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, vals, (int)n, 0, 63, st));
+	if (quality == 1)
+		LRB_CUDA(cub::DeviceSelect::Flagged(nullptr, selectBytes, (const uint32_t *)nullptr, (const uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, st));
+	LRB_CUDA(cudaMalloc(&dTemp.p, std::max<size_t>(std::max(tempBytes, selectBytes), 16)));
+	LRB_CUDA(cub::DeviceRadixSort::SortPairs(dTemp.p, tempBytes, keys, vals, (int)n, 0, 63, st));
+	GatherLeafBoxesKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), vals.Current(), n, dNodeBox.as<float>());
+	++launches;
 	LRB_CUDA(cudaEventRecord(ev[2], st));
 
-	// 3 - 5: radix tree, depths, boxes + subtree sizes
-	const int iblocks = (nInner + 255) / 256;
-	RadixTreeKernel<<<iblocks, 256, 0, st>>>(keys.Current(), n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dParL.as<uint32_t>());
-	DepthKernel<<<iblocks, 256, 0, st>>>(dParI.as<uint32_t>(), nInner, dDepth.as<uint32_t>());
-	LRB_CUDA(cudaMemsetAsync(dArrived.p, 0, (size_t)nInner * 4, st));
-	BottomUpKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), vals.Current(), n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(),
-			dParL.as<uint32_t>(), dDepth.as<uint32_t>(), levelStep, dBox.as<float>(), dSize.as<uint32_t>(), dArrived.as<uint32_t>());
+	// 3: the binary tree
+	uint32_t root = n;
+	uint32_t *dCount = dCounters.as<uint32_t>();        // [0] inner nodes created (PLOC) / next frontier size, [1] compaction result
+	if (quality == 0) {
+		RadixTreeKernel<<<(int)((nInner + 255) / 256), 256, 0, st>>>(keys.Current(), (int)n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>());
+		LRB_CUDA(cudaMemsetAsync(dArrived.p, 0, (size_t)nInner * 4, st));
+		BottomUpKernel<true, false><<<blocks, 256, 0, st>>>(n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>(), nullptr,
+				dNodeBox.as<float>(), nullptr, dArrived.as<uint32_t>());
+		launches += 2;
+	} else {
+		// PLOC: cluster lists (two, alternating) + partner positions + keep flags
+		DevBuf dClusters[2], dNN, dKeep;
+		LRB_CUDA(cudaMalloc(&dClusters[0].p, (size_t)n * 4));
+		LRB_CUDA(cudaMalloc(&dClusters[1].p, (size_t)n * 4));
+		LRB_CUDA(cudaMalloc(&dNN.p, (size_t)n * 4));
+		LRB_CUDA(cudaMalloc(&dKeep.p, (size_t)n));
+		IotaKernel<<<blocks, 256, 0, st>>>(dClusters[0].as<uint32_t>(), n);      // the leaves in Morton order: ids 0 .. n-1
+		++launches;
+		LRB_CUDA(cudaMemsetAsync(dCount, 0, 64, st));
+		LRB_CUDA(cudaMemsetAsync(dParent.p, 0xff, (size_t)nAll * 4, st));
+		uint32_t m = n;
+		int cur = 0;
+		const int radius = 16;
+		for (uint32_t iter = 0; m > 1; ++iter) {
+			if (iter > 4u * 64u + n)
+				return Fail(LRB_ERR_INTERNAL, "device builder: clustering does not converge");
+			const int mb = (int)((m + 255) / 256);
+			PlocNearestKernel<<<mb, 256, 0, st>>>(dClusters[cur].as<uint32_t>(), (int)m, dNodeBox.as<float>(), radius, dNN.as<int>());
+			PlocMergeKernel<<<mb, 256, 0, st>>>(dClusters[cur].as<uint32_t>(), (int)m, dNN.as<int>(), n, dNodeBox.as<float>(), dLeft.as<uint32_t>(),
+					dRight.as<uint32_t>(), dParent.as<uint32_t>(), dCount, dClusters[1 - cur].as<uint32_t>(), dKeep.as<uint8_t>());
+			// compaction in place of the NEXT list: select into the current one (free now), then swap roles
+			LRB_CUDA(cub::DeviceSelect::Flagged(dTemp.p, selectBytes, dClusters[1 - cur].as<uint32_t>(), dKeep.as<uint8_t>(), dClusters[cur].as<uint32_t>(),
+					dCount + 1, (int)m, st));
+			launches += 3;
+			uint32_t mNew = 0;
+			LRB_CUDA(cudaMemcpyAsync(&mNew, dCount + 1, 4, cudaMemcpyDeviceToHost, st));
+			LRB_CUDA(cudaStreamSynchronize(st));
+			if (mNew == 0 || mNew >= m)
+				return Fail(LRB_ERR_INTERNAL, "device builder: clustering made no progress");
+			m = mNew;
+		}
+		uint32_t created = 0;
+		LRB_CUDA(cudaMemcpyAsync(&created, dCount, 4, cudaMemcpyDeviceToHost, st));
+		LRB_CUDA(cudaMemcpyAsync(&root, dClusters[cur].p, 4, cudaMemcpyDeviceToHost, st));
+		LRB_CUDA(cudaStreamSynchronize(st));
+		if (created != nInner || root < n || root >= nAll)
+			return Fail(LRB_ERR_INTERNAL, "device builder: inconsistent cluster tree");
+	}
 	LRB_CUDA(cudaEventRecord(ev[3], st));
+
+	// 4: k-ary collapse over a frontier (two lists, alternating)
+	{
+		DevBuf dFrontier[2];
+		LRB_CUDA(cudaMalloc(&dFrontier[0].p, (size_t)nInner * 4));
+		LRB_CUDA(cudaMalloc(&dFrontier[1].p, (size_t)nInner * 4));
+		LRB_CUDA(cudaMemsetAsync(dKept.p, 0, (size_t)nInner, st));
+		LRB_CUDA(cudaMemcpyAsync(dFrontier[0].p, &root, 4, cudaMemcpyHostToDevice, st));
+		uint32_t count = 1;
+		int cur = 0;
+		for (uint32_t level = 0; count > 0; ++level) {
+			if (level > nInner)
+				return Fail(LRB_ERR_INTERNAL, "device builder: collapse does not terminate");
+			LRB_CUDA(cudaMemsetAsync(dCount, 0, 4, st));
+			CollapseKernel<<<(int)((count + 127) / 128), 128, 0, st>>>(dFrontier[cur].as<uint32_t>(), count, n, treeType, dLeft.as<uint32_t>(),
+					dRight.as<uint32_t>(), dNodeBox.as<float>(), dKept.as<uint8_t>(), dFrontier[1 - cur].as<uint32_t>(), dCount);
+			++launches;
+			LRB_CUDA(cudaMemcpyAsync(&count, dCount, 4, cudaMemcpyDeviceToHost, st));
+			LRB_CUDA(cudaStreamSynchronize(st));
+			cur = 1 - cur;
+		}
+	}
+
+	// 5: sizes of the collapsed subtrees
+	LRB_CUDA(cudaMemsetAsync(dArrived.p, 0, (size_t)nInner * 4, st));
+	BottomUpKernel<false, true><<<blocks, 256, 0, st>>>(n, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>(), dKept.as<uint8_t>(),
+			dNodeBox.as<float>(), dSize.as<uint32_t>(), dArrived.as<uint32_t>());
+	++launches;
 	uint32_t total = 0;
-	LRB_CUDA(cudaMemcpyAsync(&total, dSize.p, 4, cudaMemcpyDeviceToHost, st));      // size of the root's subtree = nodes in the array
+	LRB_CUDA(cudaMemcpyAsync(&total, dSize.as<uint32_t>() + (root - n), 4, cudaMemcpyDeviceToHost, st));      // size of the root's subtree = nodes in the array
 	LRB_CUDA(cudaStreamSynchronize(st));
-	if (total < nLeaves + 1 || total > 2u * nLeaves - 1u)
+	if (total < n + 1 || total > nAll)
 		return Fail(LRB_ERR_INTERNAL, "device builder: inconsistent tree size");
 	if (total > outCapacity)
 		return Fail(LRB_ERR_INVALID, "output array too small (2 * leaves - 1 nodes always suffice)");
 
 	// 6 + 7: array indices and emission
 	LRB_CUDA(cudaMalloc(&dOut.p, (size_t)total * sizeof(lrb_bvh_node)));
-	EmitInnerKernel<<<iblocks, 256, 0, st>>>(nInner, dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dDepth.as<uint32_t>(),
-			dSize.as<uint32_t>(), dBox.as<float>(), levelStep, dOut.as<lrb_bvh_node>());
-	EmitLeafKernel<<<blocks, 256, 0, st>>>(n, vals.Current(), dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParI.as<uint32_t>(), dParL.as<uint32_t>(),
-			dDepth.as<uint32_t>(), dSize.as<uint32_t>(), levelStep, dOut.as<lrb_bvh_node>());
+	EmitKernel<<<(int)((nAll + 255) / 256), 256, 0, st>>>(n, vals.Current(), dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>(),
+			dKept.as<uint8_t>(), dSize.as<uint32_t>(), dNodeBox.as<float>(), dOut.as<lrb_bvh_node>());
+	++launches;
 	LRB_CUDA(cudaEventRecord(ev[4], st));
 	LRB_CUDA(cudaMemcpyAsync(outNodes, dOut.p, (size_t)total * sizeof(lrb_bvh_node), cudaMemcpyDeviceToHost, st));
 	dev->counters.d2h_bytes += (uint64_t)total * sizeof(lrb_bvh_node);
@@ -1471,9 +1550,14 @@ int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, ui
 		cudaEventElapsedTime(&ms, ev[2], ev[3]); timings->tree_ms = ms;
 		cudaEventElapsedTime(&ms, ev[3], ev[4]); timings->emit_ms = ms;
 		cudaEventElapsedTime(&ms, ev[4], ev[5]); timings->d2h_ms = ms;
-		timings->kernels = 8;
+		timings->kernels = launches;
 	}
 	return LRB_OK;
+}
+
+int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, lrb_bvh_node *outNodes,
+		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
+	return lrb_build_bvh(dev, leafBoxes, nLeaves, treeType, 0u, outNodes, outCapacity, nNodes, timings);
 }
 
 int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {
@@ -1577,6 +1661,47 @@ int lrb_gather_wait(lrb_device *dev, void *cudaStream, int which) {
 				dev->gatherPending[slot] = false;
 		}
 	}
+	return LRB_OK;
+}
+
+// Completion signal of a gather WITHOUT a kernel: the value travels as a 4-byte copy-engine transfer on the push stream,
+// behind this rank's pushes, into a flag word on the gathering GPU (peer-mapped like the gather buffer itself).
+// (Round-2 timeline: the 4-byte ncclAllReduce used as the signal needs SMs; against a persistent trace kernel that
+// fills every SM it can only run between two trace kernels, and cost 0.25 ms of every 5 ms step at >= 4 GPUs.)
+int lrb_gather_signal(lrb_device *dev, void *flagDev, uint32_t value) {
+	if (!dev || !flagDev)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	LRB_SETDEV(dev);
+	if (!dev->signalValues) {
+		// a table of the values 0 .. 65535: the source of the 4-byte copies (the value must live in device memory)
+		std::vector<uint32_t> v(65536);
+		for (uint32_t i = 0; i < 65536u; ++i) v[i] = i;
+		LRB_CUDA(cudaMalloc((void **)&dev->signalValues, v.size() * 4));
+		LRB_CUDA(cudaMemcpy(dev->signalValues, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+	}
+	if (value >= 65536u)
+		return Fail(LRB_ERR_INVALID, "signal values are 16-bit step counters");
+	// ordered behind the pushes of every gather issued so far (they run on the same stream) and behind the queue itself
+	// (a gather without pushes -- the gathering rank's own -- still signals that its trace has been queued ... and run)
+	if (!dev->pipeJoin)
+		LRB_CUDA(cudaEventCreateWithFlags(&dev->pipeJoin, cudaEventDisableTiming));
+	LRB_CUDA(cudaEventRecord(dev->pipeJoin, dev->stream));
+	LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, dev->pipeJoin, 0));
+	LRB_CUDA(cudaMemcpyAsync(flagDev, dev->signalValues + value, 4, cudaMemcpyDefault, dev->copyOutStream));
+	return LRB_OK;
+}
+
+// Makes a stream (NULL = the device's queue) wait until the 32-bit word at flagDev (memory of THIS device) is >= value.
+int lrb_wait_value(lrb_device *dev, void *flagDev, uint32_t value, void *cudaStream) {
+	if (!dev || !flagDev)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	LRB_SETDEV(dev);
+	const int rc = ResolveDriverEntryPoints();
+	if (rc != LRB_OK)
+		return rc;
+	cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : dev->stream;
+	if (g_streamWaitValue32((CUstream)st, (CUdeviceptr)(uintptr_t)flagDev, value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+		return Fail(LRB_ERR_CUDA, "cuStreamWaitValue32 failed");
 	return LRB_OK;
 }
 

@@ -41,6 +41,8 @@ static ocl::BVHArrayNode *RunBuilder(const Context *ctx, const char *who, const 
 		return BuildEmbreeBVHBinnedSAH(params, nNodes, meshes, list);
 	if (builderType == "EMBREE_MORTON")
 		return BuildEmbreeBVHMorton(params, nNodes, meshes, list);
+	if (builderType == "B200_PLOC")
+		return BuildB200BVHPloc(params, nNodes, meshes, list);
 	throw std::runtime_error(std::string("Unknown BVH builder type in ") + who + ": " + builderType);
 }
 

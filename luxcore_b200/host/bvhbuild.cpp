@@ -736,11 +736,11 @@ static lrb_device *BuilderDevice() {
 	return dev;
 }
 
-Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
+static Node *BuildOnDevice(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList, const uint32_t quality) {
 	lrb_device *dev = leafList.empty() ? nullptr : BuilderDevice();
 	if (!dev) {
 		if (!leafList.empty())
-			fprintf(stderr, "luxrays_b200: EMBREE_MORTON: no CUDA device for the GPU builder, using the host SAH builder\n");
+			fprintf(stderr, "luxrays_b200: no CUDA device for the GPU BVH builder, using the host SAH builder\n");
 		return BuildEmbreeBVHBinnedSAH(params, nNodes, meshes, leafList);
 	}
 	const size_t n = leafList.size();
@@ -756,7 +756,7 @@ Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::de
 	uint32_t total = 0;
 	lrb_build_timings tm;
 	static_assert(sizeof(Node) == sizeof(lrb_bvh_node), "BVHArrayNode layout");
-	if (lrb_build_lbvh(dev, boxes.data(), (uint32_t)n, params.treeType, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, &tm) != LRB_OK) {
+	if (lrb_build_bvh(dev, boxes.data(), (uint32_t)n, params.treeType, quality, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, &tm) != LRB_OK) {
 		delete[] arr;
 		throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
 	}
@@ -785,6 +785,16 @@ Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::de
 	}
 	*nNodes = total;
 	return arr;
+}
+
+Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
+	return BuildOnDevice(params, nNodes, meshes, leafList, 0u);
+}
+
+// accelerator.bvh.builder.type = B200_PLOC (an extension of the reference's three names): the GPU builder with its
+// PLOC binary tree -- SAH-class quality at GPU build speed, for scenes whose host build would take seconds.
+Node *BuildB200BVHPloc(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
+	return BuildOnDevice(params, nNodes, meshes, leafList, 1u);
 }
 
 }   // namespace luxrays

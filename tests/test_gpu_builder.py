@@ -52,10 +52,12 @@ def check_array(nodes, boxes, tree_type):
     return max_kids
 
 
+@pytest.mark.parametrize("quality", [0, 1])
 @pytest.mark.parametrize("tree_type", [2, 4, 8])
 @pytest.mark.parametrize("n,kind", [(1, "uniform"), (2, "uniform"), (3, "uniform"), (7, "same"), (1000, "uniform"), (1000, "same"),
-                                    (50000, "uniform"), (50000, "line"), (200000, "clustered")])
-def test_lbvh_array_rules(dev, n, kind, tree_type):
+                                    (50000, "uniform"), (50000, "line"), (50000, "same"), (200000, "clustered")])
+def test_lbvh_array_rules(dev, n, kind, tree_type, quality):
+    """quality 0 = radix tree (lrb_build_lbvh), 1 = PLOC; (50000, "same"): identical boxes must not degrade into one merge per iteration."""
     rng = np.random.default_rng(n * 8 + tree_type)
     if kind == "uniform":
         c = rng.random((n, 3), dtype=np.float32) * 10 - 5
@@ -68,21 +70,26 @@ def test_lbvh_array_rules(dev, n, kind, tree_type):
         c = (rng.standard_normal((n, 3)) * 0.01 + rng.random((12, 3))[k] * 100).astype(np.float32)
     e = (rng.random((n, 3), dtype=np.float32) * 0.05).astype(np.float32)
     boxes = np.concatenate([c - e, c + e], axis=1).astype(np.float32)
-    nodes, tm = dev.build_lbvh(boxes, tree_type, node_dtype=O.NODE_DTYPE)
+    nodes, tm = dev.build_lbvh(boxes, tree_type, node_dtype=O.NODE_DTYPE, quality=quality)
     assert n <= nodes.shape[0] <= max(1, 2 * n - 1)
     kids = check_array(nodes, boxes, tree_type)
     if n >= 1000 and kind == "uniform":
         assert kids == tree_type            # the collapse really produces wide nodes
         assert nodes.shape[0] < (2 * n - 1 if tree_type > 2 else 2 * n)
+        if tree_type == 4:
+            assert nodes.shape[0] - n <= 0.6 * n        # greedy collapse: well under the n - 1 inner nodes of the binary tree
+    if quality == 1 and n >= 1000:
+        assert tm.kernels < 3 * 400 + 200, "PLOC needed %d launches" % tm.kernels
     assert H.Emu.lib().emu_validate_tree(nodes.ctypes.data, nodes.shape[0]) == 0        # the product's own upload check
 
 
+@pytest.mark.parametrize("builder", ["EMBREE_MORTON", "B200_PLOC"])
 @pytest.mark.parametrize("name,tree_type,n_rays", [("cornell", 4, 200000), ("kitchen", 4, 600000), ("kitchen", 8, 300000), ("bigmonkey", 2, 300000)])
-def test_embree_morton_through_the_host_layer(name, tree_type, n_rays):
-    """accelerator.bvh.builder.type = EMBREE_MORTON: BVHAccel::Init hands its leaf list to the GPU builder; tracing the
-    result on the GPU equals the oracle walking the same array."""
+def test_embree_morton_through_the_host_layer(name, tree_type, n_rays, builder):
+    """accelerator.bvh.builder.type = EMBREE_MORTON / B200_PLOC: BVHAccel::Init hands its leaf list to the GPU builder; tracing
+    the result on the GPU equals the oracle walking the same array."""
     desc = S.load_fixture(name)
-    s = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": "EMBREE_MORTON", "accelerator.bvh.treetype": tree_type}, desc)
+    s = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": builder, "accelerator.bvh.treetype": tree_type}, desc)
     s.start(0)
     nodes = s.bvh_nodes()
     n_tris = sum(t.shape[0] for _, t in desc.shapes) if all(m.kind == S.PLAIN for m in desc.meshes) else None
@@ -107,10 +114,11 @@ def test_embree_morton_through_the_host_layer(name, tree_type, n_rays):
     s.close()
 
 
-def test_embree_morton_mbvh_root_and_leaves():
+@pytest.mark.parametrize("builder", ["EMBREE_MORTON", "B200_PLOC"])
+def test_embree_morton_mbvh_root_and_leaves(builder):
     """Two-level scenes: the root tree over the instances and every leaf tree come from the GPU builder."""
     desc = Z.instances_scene(20)
-    s = hostapi.Session({"accelerator.bvh.builder.type": "EMBREE_MORTON"}, desc)
+    s = hostapi.Session({"accelerator.bvh.builder.type": builder}, desc)
     s.start(0)
     assert s.accelerator_type() == hostapi.ACCEL_MBVH
     lo, hi = desc.bbox()

@@ -11,16 +11,16 @@ from luxcore_b200 import capi, hostapi, rays as R, scenes as S
 
 rows = []
 dev = capi.Device(0)
-for n in (86032, 1000000, 10000000, 50000000):
+for n, quality in ((86032, 0), (86032, 1), (1000000, 0), (1000000, 1), (10000000, 0), (10000000, 1), (50000000, 0), (50000000, 1)):
     rng = np.random.default_rng(n)
     c = rng.random((n, 3), dtype=np.float32)
     e = np.float32(0.001)
     boxes = np.concatenate([c - e, c + e], axis=1)
-    dev.build_lbvh(boxes[:1000], 4)       # warm-up (context, CUB)
+    dev.build_lbvh(boxes[:1000], 4, quality=quality)       # warm-up (context, CUB)
     t0 = time.perf_counter()
-    nodes, tm = dev.build_lbvh(boxes, 4)
+    nodes, tm = dev.build_lbvh(boxes, 4, quality=quality)
     wall = time.perf_counter() - t0
-    row = {"leaves": n, "nodes": int(nodes.shape[0]), "wall_s": round(wall, 4), "h2d_ms": round(tm.h2d_ms, 3), "sort_ms": round(tm.sort_ms, 3),
+    row = {"leaves": n, "binary_tree": "PLOC" if quality else "radix", "launches": int(tm.kernels), "nodes": int(nodes.shape[0]), "wall_s": round(wall, 4), "h2d_ms": round(tm.h2d_ms, 3), "sort_ms": round(tm.sort_ms, 3),
            "tree_ms": round(tm.tree_ms, 3), "emit_ms": round(tm.emit_ms, 3), "d2h_ms": round(tm.d2h_ms, 3),
            "device_ms_without_copies": round(tm.sort_ms + tm.tree_ms + tm.emit_ms, 3),
            "mleaves_per_s_device": round(n / (tm.sort_ms + tm.tree_ms + tm.emit_ms) / 1e3, 1)}
@@ -31,7 +31,7 @@ dev.close()
 # the kitchen through the host layer: SAH (host) vs Morton (GPU) -- build time and what the tree costs to walk
 desc = S.load_fixture("kitchen")
 tdev = torch.device("cuda", 0)
-for builder in ("EMBREE_BINNED_SAH", "EMBREE_MORTON"):
+for builder in ("EMBREE_BINNED_SAH", "EMBREE_MORTON", "B200_PLOC"):
     t0 = time.perf_counter()
     s = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": builder, "accelerator.bvh.treetype": 4}, desc)
     s.build_accelerator("BVH")
