@@ -1,7 +1,7 @@
 """CPU-only issue-slot model of the persistent trace kernel.
 
-The kernel is issue-bound on L2-resident scenes (profiles/r01_f: issue-active 75 %, 306 warp
-instructions per ray at 16.9 active threads).  tests/cpp/wide_emulation.cpp::WarpSim replays the
+The kernel is issue-bound on L2-resident scenes (profiles/r02c6: issue-active 82 %, 276 warp
+instructions per ray at 17.9 active threads).  tests/cpp/wide_emulation.cpp::WarpSim replays the
 kernel's scheduling (bulk re-fill, Resolve, node / triangle phase vote) with the real traverse.h
 bodies and counts the phases a warp issues; this tool weights them with the SASS instruction counts
 of the sections of TracePersistent<0,1,0> (cuobjdump -sass) and prints warp instructions per ray --
@@ -23,18 +23,19 @@ import helpers as H
 import tree_stats as TS
 from luxcore_b200 import hostapi
 
-# Warp instructions per EXECUTED section: counted by hand along the common path through the SASS of
-# TracePersistent<0,1,0,0> (sm_100a).  tools/sass_costs.py attributes the same SASS to source functions
-# automatically (static counts: node phase 186 + 67 for the rarely taken spilling push, triangle phase
-# incl. gate 126, pop loop 31 over both its paths, re-fill 126) -- run it after touching the kernel.
-COST = {"inner_fixed": 30,      # Resolve entry test, __syncwarp, two ballots, vote, loop branch
-        "pop_trip": 16,         # one trip of the pop loop (longest lane decides)
-        "node_phase": 164,      # fetch + decode + 4 slab tests + network + predicated pushes
-        "tri_phase": 88,        # fetch + Moller-Trumbore + accept predicate
-        "gate": 40,             # accepted hit: gate fetch + box test + state update
-        "outer_fixed": 40,      # store / re-fill section when nothing to do
-        "store": 30,            # RayHit stores of the finished lanes
-        "refill": 120}          # atomic, ray fetch, 1/d, root box
+# Warp instructions per EXECUTED section, from the ncu SOURCE view of the benched kernel (round 2, commit c8a58a5,
+# profiles/r02c6_kitchen_ncu_summary.txt; per-SASS-instruction execution counts aggregated by section and divided by
+# the executions of the section -- DESIGN.md section 4, item 6): node phase 122.7 warp instructions per ray over 0.73
+# phases per ray, triangle phase + in-record gate 52.5 over 0.46, Resolve's loop 5 per trip, the rest per iteration.
+# tools/sass_costs.py attributes the static SASS to source functions automatically -- run it after touching the kernel.
+COST = {"inner_fixed": 55,      # Resolve entry / exit around the loop, __syncwarp, two ballots, vote, loop branch
+        "pop_trip": 5,          # one trip of Resolve's loop (longest lane decides): LDS, two address updates, compare, branch
+        "node_phase": 168,      # fetch + decode + 4 slab tests + network + predicated 64-bit pushes
+        "tri_phase": 114,       # fetch + Moller-Trumbore + the gate box from the same record + commit
+        "gate": 0,              # (round 1: a separate side path per accepted hit; now part of the triangle phase)
+        "outer_fixed": 10,      # store / re-fill section when nothing to do
+        "store": 40,            # RayHit stores of the finished lanes
+        "refill": 150}          # atomic, ray fetch, 1/d, root box
 
 
 def model(c):
