@@ -323,6 +323,34 @@ LRB_API int lrb_build_lbvh(lrb_device *dev, const float *leaf_boxes, uint32_t n_
 LRB_API int lrb_build_bvh(lrb_device *dev, const float *leaf_boxes, uint32_t n_leaves, uint32_t tree_type, uint32_t quality,
 		lrb_bvh_node *out_nodes, uint32_t out_capacity, uint32_t *n_nodes, lrb_build_timings *timings);
 
+/* Triangles in, traceable scene out -- everything on the device.  Replaces BVHAccel::Init + the builder + BVHKernel's
+ * upload (src/luxrays/accelerators/bvhaccel.cpp:72-168, src/luxrays/core/bvh/bvhembreebuild.cpp:218-336,
+ * src/luxrays/accelerators/bvhaccelhw.cpp:38-257) for trees that are built where the rays are traced: the triangles'
+ * build boxes (bvhaccel.cpp:116-122), the tree of lrb_build_bvh, the leaf payload (bvhclassicbuild.cpp:196-214) and the
+ * re-layout of lrb_bvh_upload all run as kernels; the BVHArrayNode array never visits the host unless it is asked for.
+ * The scene is byte-identical to lrb_bvh_upload of that array (same functions, compiled for both sides).
+ *   xyz / n_verts / mesh_vertex_offsets / n_meshes : as for lrb_bvh_upload (HOST memory);
+ *   mesh_triangle_offsets : n_meshes + 1 entries, first triangle of mesh m in `triangles`; the last entry is the total;
+ *   triangles             : 3 mesh-local vertex indices per triangle (luxrays::Triangle::v), all meshes back to back;
+ *   out_nodes (may be NULL): receives the reference array (what BVHAccel::bvhTree would hold), capacity in nodes;
+ *   n_nodes (may be NULL) : number of nodes of that array.
+ * Synchronous.  0 or 1 triangle: the (trivial) tree is made on the host and goes through lrb_bvh_upload. */
+typedef struct {
+	double h2d_ms;                      /* vertices + triangle indices to the device */
+	double leafbox_ms;                  /* build boxes of the triangles */
+	double sort_ms, tree_ms, emit_ms;   /* the builder's stages, as in lrb_build_timings */
+	double relayout_ms;                 /* leaf payload, wide nodes + triangle records, stack bound */
+	double d2h_ms;                      /* download of the reference array (0 when out_nodes == NULL) */
+	uint32_t kernels;                   /* own kernels launched (CUB's passes not counted) */
+} lrb_scene_build_timings;
+LRB_API int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t n_verts, const uint32_t *mesh_vertex_offsets,
+		const uint32_t *mesh_triangle_offsets, uint32_t n_meshes, const uint32_t *triangles, uint32_t tree_type, uint32_t quality,
+		lrb_scene **scene, lrb_bvh_node *out_nodes, uint32_t out_capacity, uint32_t *n_nodes, lrb_scene_build_timings *timings);
+/* Hands a scene to another lrb_device handle of the SAME CUDA device (the accelerator is built before the intersection
+ * device is started: Context::SetDataSet / Start, context.cpp:173-232): the scene's memory accounting moves to `dev`
+ * and its traces run on dev's queue from now on.  Fails, and changes nothing, when the CUDA ordinals differ. */
+LRB_API int lrb_scene_adopt(lrb_device *dev, lrb_scene *scene);
+
 /* ---- multi-GPU: film merge over NVLink -------------------------------------------------------- */
 /* The sum of per-GPU film planes that replaces the host-side merge of per-device films
  * (PathOCLRenderEngine::MergeThreadFilms -> Film::AddFilm, src/slg/engines/pathocl/pathocl.cpp:184-201,

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -26,6 +27,7 @@
 #include "trace_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "build_kernels.cuh"
+#include "relayout_kernels.cuh"
 
 using namespace lrb;
 
@@ -1372,42 +1374,25 @@ int lrb_film_reduce(lrb_device *dev, const float *const *tilesDev, uint32_t nTil
 
 // ---- BVH construction on the device (build_kernels.cuh) ---------------------------------------------------
 
-int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, uint32_t quality, lrb_bvh_node *outNodes,
-		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
-	if (!leafBoxes || !outNodes || !nNodes)
-		return Fail(LRB_ERR_INVALID, "null argument");
-	if (treeType != 2 && treeType != 4 && treeType != 8)
-		return Fail(LRB_ERR_INVALID, "tree type must be 2, 4 or 8 (bvhaccel.cpp:51)");
-	if (quality > 1)
-		return Fail(LRB_ERR_INVALID, "builder quality must be 0 (radix tree) or 1 (PLOC)");
-	if (nLeaves == 0 || nLeaves >= 0x3fffffffu)
-		return Fail(LRB_ERR_INVALID, "leaf count out of range");
-	LRB_SETDEV(dev);
-	{
-		const int rcJoin = JoinPending(dev);
-		if (rcJoin != LRB_OK) return rcJoin;
-	}
-	*nNodes = 0;
-	if (timings) memset(timings, 0, sizeof(*timings));
-	if (nLeaves == 1) {
-		// the tree is its only leaf (bvhclassicbuild.cpp: a leaf list of one)
-		if (outCapacity < 1)
-			return Fail(LRB_ERR_INVALID, "output array too small");
-		memset(outNodes, 0, sizeof(*outNodes));
-		outNodes[0].triangleLeaf.v[0] = 0;
-		outNodes[0].nodeData = 1u | 0x80000000u;
-		*nNodes = 1;
-		return LRB_OK;
-	}
-	const uint32_t n = nLeaves, nInner = n - 1, nAll = 2 * n - 1;
+// The tree of lrb_build_bvh from leaf boxes that are already on the device (n >= 2): steps 1 - 7 of build_kernels.cuh.
+// The array stays on the device (res->nodes); leaves carry their input index in triangleLeaf.v[0].
+struct DeviceTree {
+	DevBuf nodes;                   // lrb_bvh_node[total]
+	uint32_t total;
+	float sortMs, treeMs, emitMs;   // CUDA-event times of the stages
+	uint32_t launches;
+	DeviceTree() : total(0), sortMs(0.f), treeMs(0.f), emitMs(0.f), launches(0) {}
+};
+
+static int BuildTreeOnDevice(lrb_device *dev, const float *dLeafBoxes, const uint32_t n, const uint32_t treeType, const uint32_t quality, DeviceTree *res) {
+	const uint32_t nInner = n - 1, nAll = 2 * n - 1;
 	cudaStream_t st = dev->stream;
-	cudaEvent_t ev[6];
-	for (int i = 0; i < 6; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
-	BuildEvents evGuard = { ev, 6 };
+	cudaEvent_t ev[4];
+	for (int i = 0; i < 4; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
+	BuildEvents evGuard = { ev, 4 };
 	uint32_t launches = 0;
 
-	DevBuf dBoxes, dBounds, dKeys[2], dVals[2], dTemp, dLeft, dRight, dParent, dNodeBox, dSize, dArrived, dKept, dOut, dCounters;
-	LRB_CUDA(cudaMalloc(&dBoxes.p, (size_t)n * 24));
+	DevBuf dBounds, dKeys[2], dVals[2], dTemp, dLeft, dRight, dParent, dNodeBox, dSize, dArrived, dKept, dCounters;
 	LRB_CUDA(cudaMalloc(&dBounds.p, 32));
 	for (int k = 0; k < 2; ++k) {
 		LRB_CUDA(cudaMalloc(&dKeys[k].p, (size_t)n * 8));
@@ -1421,18 +1406,16 @@ int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uin
 	LRB_CUDA(cudaMalloc(&dArrived.p, (size_t)nInner * 4));
 	LRB_CUDA(cudaMalloc(&dKept.p, (size_t)nInner));
 	LRB_CUDA(cudaMalloc(&dCounters.p, 64));
+	const float *dBoxes = dLeafBoxes;
 
 	LRB_CUDA(cudaEventRecord(ev[0], st));
-	LRB_CUDA(cudaMemcpyAsync(dBoxes.p, leafBoxes, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-	dev->counters.h2d_bytes += (uint64_t)n * 24;
-	LRB_CUDA(cudaEventRecord(ev[1], st));
 
 	// 1 + 2: centroid bounds, Morton codes, sort
 	const uint32_t initBounds[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
 	LRB_CUDA(cudaMemcpyAsync(dBounds.p, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
 	const int blocks = (int)((n + 255) / 256);
-	CentroidBoundsKernel<<<std::min(blocks, dev->prop.multiProcessorCount * 8), 256, 0, st>>>(dBoxes.as<float>(), n, dBounds.as<uint32_t>());
-	MortonKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), n, dBounds.as<uint32_t>(), dKeys[0].as<uint64_t>(), dVals[0].as<uint32_t>());
+	CentroidBoundsKernel<<<std::min(blocks, dev->prop.multiProcessorCount * 8), 256, 0, st>>>(dBoxes, n, dBounds.as<uint32_t>());
+	MortonKernel<<<blocks, 256, 0, st>>>(dBoxes, n, dBounds.as<uint32_t>(), dKeys[0].as<uint64_t>(), dVals[0].as<uint32_t>());
 	launches += 2;
 	cub::DoubleBuffer<uint64_t> keys(dKeys[0].as<uint64_t>(), dKeys[1].as<uint64_t>());
 	cub::DoubleBuffer<uint32_t> vals(dVals[0].as<uint32_t>(), dVals[1].as<uint32_t>());
@@ -1442,9 +1425,9 @@ int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uin
 		LRB_CUDA(cub::DeviceSelect::Flagged(nullptr, selectBytes, (const uint32_t *)nullptr, (const uint8_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, st));
 	LRB_CUDA(cudaMalloc(&dTemp.p, std::max<size_t>(std::max(tempBytes, selectBytes), 16)));
 	LRB_CUDA(cub::DeviceRadixSort::SortPairs(dTemp.p, tempBytes, keys, vals, (int)n, 0, 63, st));
-	GatherLeafBoxesKernel<<<blocks, 256, 0, st>>>(dBoxes.as<float>(), vals.Current(), n, dNodeBox.as<float>());
+	GatherLeafBoxesKernel<<<blocks, 256, 0, st>>>(dBoxes, vals.Current(), n, dNodeBox.as<float>());
 	++launches;
-	LRB_CUDA(cudaEventRecord(ev[2], st));
+	LRB_CUDA(cudaEventRecord(ev[1], st));
 
 	// 3: the binary tree
 	uint32_t root = n;
@@ -1494,7 +1477,7 @@ int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uin
 		if (created != nInner || root < n || root >= nAll)
 			return Fail(LRB_ERR_INTERNAL, "device builder: inconsistent cluster tree");
 	}
-	LRB_CUDA(cudaEventRecord(ev[3], st));
+	LRB_CUDA(cudaEventRecord(ev[2], st));
 
 	// 4: k-ary collapse over a frontier (two lists, alternating)
 	{
@@ -1528,29 +1511,86 @@ int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uin
 	LRB_CUDA(cudaStreamSynchronize(st));
 	if (total < n + 1 || total > nAll)
 		return Fail(LRB_ERR_INTERNAL, "device builder: inconsistent tree size");
+
+	// 6 + 7: array indices and emission
+	LRB_CUDA(cudaMalloc(&res->nodes.p, (size_t)total * sizeof(lrb_bvh_node)));
+	EmitKernel<<<(int)((nAll + 255) / 256), 256, 0, st>>>(n, vals.Current(), dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>(),
+			dKept.as<uint8_t>(), dSize.as<uint32_t>(), dNodeBox.as<float>(), res->nodes.as<lrb_bvh_node>());
+	++launches;
+	LRB_CUDA(cudaEventRecord(ev[3], st));
+	LRB_CUDA(cudaStreamSynchronize(st));
+	LRB_CUDA(cudaGetLastError());
+	res->total = total;
+	cudaEventElapsedTime(&res->sortMs, ev[0], ev[1]);
+	cudaEventElapsedTime(&res->treeMs, ev[1], ev[2]);
+	cudaEventElapsedTime(&res->emitMs, ev[2], ev[3]);
+	res->launches = launches;
+	return LRB_OK;
+}
+
+int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, uint32_t quality, lrb_bvh_node *outNodes,
+		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
+	if (!leafBoxes || !outNodes || !nNodes)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	if (treeType != 2 && treeType != 4 && treeType != 8)
+		return Fail(LRB_ERR_INVALID, "tree type must be 2, 4 or 8 (bvhaccel.cpp:51)");
+	if (quality > 1)
+		return Fail(LRB_ERR_INVALID, "builder quality must be 0 (radix tree) or 1 (PLOC)");
+	if (nLeaves == 0 || nLeaves >= 0x3fffffffu)
+		return Fail(LRB_ERR_INVALID, "leaf count out of range");
+	LRB_SETDEV(dev);
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
+	*nNodes = 0;
+	if (timings) memset(timings, 0, sizeof(*timings));
+	if (nLeaves == 1) {
+		// the tree is its only leaf (bvhclassicbuild.cpp: a leaf list of one)
+		if (outCapacity < 1)
+			return Fail(LRB_ERR_INVALID, "output array too small");
+		memset(outNodes, 0, sizeof(*outNodes));
+		outNodes[0].triangleLeaf.v[0] = 0;
+		outNodes[0].nodeData = 1u | 0x80000000u;
+		*nNodes = 1;
+		return LRB_OK;
+	}
+	const uint32_t n = nLeaves;
+	cudaStream_t st = dev->stream;
+	cudaEvent_t ev[4];
+	for (int i = 0; i < 4; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
+	BuildEvents evGuard = { ev, 4 };
+
+	DevBuf dBoxes;
+	LRB_CUDA(cudaMalloc(&dBoxes.p, (size_t)n * 24));
+	LRB_CUDA(cudaEventRecord(ev[0], st));
+	LRB_CUDA(cudaMemcpyAsync(dBoxes.p, leafBoxes, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+	dev->counters.h2d_bytes += (uint64_t)n * 24;
+	LRB_CUDA(cudaEventRecord(ev[1], st));
+
+	DeviceTree tree;
+	const int rc = BuildTreeOnDevice(dev, dBoxes.as<float>(), n, treeType, quality, &tree);
+	if (rc != LRB_OK)
+		return rc;
+	const uint32_t total = tree.total;
 	if (total > outCapacity)
 		return Fail(LRB_ERR_INVALID, "output array too small (2 * leaves - 1 nodes always suffice)");
 
-	// 6 + 7: array indices and emission
-	LRB_CUDA(cudaMalloc(&dOut.p, (size_t)total * sizeof(lrb_bvh_node)));
-	EmitKernel<<<(int)((nAll + 255) / 256), 256, 0, st>>>(n, vals.Current(), dLeft.as<uint32_t>(), dRight.as<uint32_t>(), dParent.as<uint32_t>(),
-			dKept.as<uint8_t>(), dSize.as<uint32_t>(), dNodeBox.as<float>(), dOut.as<lrb_bvh_node>());
-	++launches;
-	LRB_CUDA(cudaEventRecord(ev[4], st));
-	LRB_CUDA(cudaMemcpyAsync(outNodes, dOut.p, (size_t)total * sizeof(lrb_bvh_node), cudaMemcpyDeviceToHost, st));
+	LRB_CUDA(cudaEventRecord(ev[2], st));
+	LRB_CUDA(cudaMemcpyAsync(outNodes, tree.nodes.p, (size_t)total * sizeof(lrb_bvh_node), cudaMemcpyDeviceToHost, st));
 	dev->counters.d2h_bytes += (uint64_t)total * sizeof(lrb_bvh_node);
-	LRB_CUDA(cudaEventRecord(ev[5], st));
+	LRB_CUDA(cudaEventRecord(ev[3], st));
 	LRB_CUDA(cudaStreamSynchronize(st));
 	LRB_CUDA(cudaGetLastError());
 	*nNodes = total;
 	if (timings) {
 		float ms;
 		cudaEventElapsedTime(&ms, ev[0], ev[1]); timings->h2d_ms = ms;
-		cudaEventElapsedTime(&ms, ev[1], ev[2]); timings->sort_ms = ms;
-		cudaEventElapsedTime(&ms, ev[2], ev[3]); timings->tree_ms = ms;
-		cudaEventElapsedTime(&ms, ev[3], ev[4]); timings->emit_ms = ms;
-		cudaEventElapsedTime(&ms, ev[4], ev[5]); timings->d2h_ms = ms;
-		timings->kernels = launches;
+		timings->sort_ms = tree.sortMs;
+		timings->tree_ms = tree.treeMs;
+		timings->emit_ms = tree.emitMs;
+		cudaEventElapsedTime(&ms, ev[2], ev[3]); timings->d2h_ms = ms;
+		timings->kernels = tree.launches;
 	}
 	return LRB_OK;
 }
@@ -1558,6 +1598,263 @@ int lrb_build_bvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uin
 int lrb_build_lbvh(lrb_device *dev, const float *leafBoxes, uint32_t nLeaves, uint32_t treeType, lrb_bvh_node *outNodes,
 		uint32_t outCapacity, uint32_t *nNodes, lrb_build_timings *timings) {
 	return lrb_build_bvh(dev, leafBoxes, nLeaves, treeType, 0u, outNodes, outCapacity, nNodes, timings);
+}
+
+int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t nVerts, const uint32_t *meshVertexOffsets, const uint32_t *meshTriangleOffsets,
+		uint32_t nMeshes, const uint32_t *triangles, uint32_t treeType, uint32_t quality, lrb_scene **out, lrb_bvh_node *outNodes, uint32_t outCapacity,
+		uint32_t *nNodes, lrb_scene_build_timings *timings) {
+	if (!out)
+		return Fail(LRB_ERR_INVALID, "null out pointer");
+	*out = nullptr;
+	if (nNodes) *nNodes = 0;
+	if (timings) memset(timings, 0, sizeof(*timings));
+	if (!xyz || !meshVertexOffsets || !meshTriangleOffsets || nMeshes == 0)
+		return Fail(LRB_ERR_INVALID, "scene build needs vertices, a mesh vertex-offset table and a mesh triangle-offset table");
+	if (treeType != 2 && treeType != 4 && treeType != 8)
+		return Fail(LRB_ERR_INVALID, "tree type must be 2, 4 or 8 (bvhaccel.cpp:51)");
+	if (quality > 1)
+		return Fail(LRB_ERR_INVALID, "builder quality must be 0 (radix tree) or 1 (PLOC)");
+	if (meshTriangleOffsets[0] != 0)
+		return Fail(LRB_ERR_INVALID, "mesh triangle offsets must start at 0");
+	for (uint32_t m = 0; m < nMeshes; ++m) {
+		if (meshTriangleOffsets[m + 1] < meshTriangleOffsets[m])
+			return Fail(LRB_ERR_INVALID, "mesh triangle offsets must not decrease");
+		if (meshVertexOffsets[m] > nVerts)
+			return Fail(LRB_ERR_INVALID, "mesh vertex offset outside the vertex buffer");
+	}
+	const uint32_t nTris = meshTriangleOffsets[nMeshes];
+	if (nTris >= 0x3fffffffu)
+		return Fail(LRB_ERR_INVALID, "triangle count out of range");
+	if (nTris && !triangles)
+		return Fail(LRB_ERR_INVALID, "null triangle index array");
+	LRB_SETDEV(dev);
+	if (nTris <= 1) {
+		// nothing to build: an empty array, or the tree that is its only leaf (bvhclassicbuild.cpp: a leaf list of one)
+		lrb_bvh_node leaf;
+		memset(&leaf, 0, sizeof(leaf));
+		if (nTris == 1) {
+			const uint32_t m = MeshOfTriangle(meshTriangleOffsets, nMeshes, 0u);
+			for (int j = 0; j < 3; ++j) leaf.triangleLeaf.v[j] = triangles[j];
+			leaf.triangleLeaf.meshIndex = m;
+			leaf.triangleLeaf.triangleIndex = 0u - meshTriangleOffsets[m];
+			leaf.nodeData = 1u | 0x80000000u;
+			if (outNodes) {
+				if (outCapacity < 1)
+					return Fail(LRB_ERR_INVALID, "output array too small");
+				outNodes[0] = leaf;
+			}
+		}
+		if (nNodes) *nNodes = nTris;
+		return lrb_bvh_upload(dev, &leaf, nTris, xyz, nVerts, meshVertexOffsets, nMeshes, out);
+	}
+	{
+		const int rcJoin = JoinPending(dev);
+		if (rcJoin != LRB_OK) return rcJoin;
+	}
+	cudaStream_t st = dev->stream;
+	cudaEvent_t ev[6];
+	for (int i = 0; i < 6; ++i) LRB_CUDA(cudaEventCreate(&ev[i]));
+	BuildEvents evGuard = { ev, 6 };
+	uint32_t launches = 0;
+
+	// inputs
+	DevBuf dXyz, dTriIdx, dMeshVertOff, dMeshTriOff, dBoxes, dErr;
+	LRB_CUDA(cudaMalloc(&dXyz.p, std::max<size_t>((size_t)nVerts * 12, 16)));
+	LRB_CUDA(cudaMalloc(&dTriIdx.p, (size_t)nTris * 12));
+	LRB_CUDA(cudaMalloc(&dMeshVertOff.p, (size_t)nMeshes * 4));
+	LRB_CUDA(cudaMalloc(&dMeshTriOff.p, ((size_t)nMeshes + 1) * 4));
+	LRB_CUDA(cudaMalloc(&dBoxes.p, (size_t)nTris * 24));
+	LRB_CUDA(cudaMalloc(&dErr.p, 64));       // [0] error code, [1] stack bound, [2..7] exact root box
+	LRB_CUDA(cudaEventRecord(ev[0], st));
+	LRB_CUDA(cudaMemcpyAsync(dXyz.p, xyz, (size_t)nVerts * 12, cudaMemcpyHostToDevice, st));
+	LRB_CUDA(cudaMemcpyAsync(dTriIdx.p, triangles, (size_t)nTris * 12, cudaMemcpyHostToDevice, st));
+	LRB_CUDA(cudaMemcpyAsync(dMeshVertOff.p, meshVertexOffsets, (size_t)nMeshes * 4, cudaMemcpyHostToDevice, st));
+	LRB_CUDA(cudaMemcpyAsync(dMeshTriOff.p, meshTriangleOffsets, ((size_t)nMeshes + 1) * 4, cudaMemcpyHostToDevice, st));
+	LRB_CUDA(cudaMemsetAsync(dErr.p, 0, 64, st));
+	dev->counters.h2d_bytes += (uint64_t)nVerts * 12 + (uint64_t)nTris * 12 + (uint64_t)nMeshes * 8 + 4;
+	LRB_CUDA(cudaEventRecord(ev[1], st));
+
+	// 0: the triangles' build boxes
+	const int triBlocks = (int)((nTris + 255) / 256);
+	LeafBoxKernel<<<triBlocks, 256, 0, st>>>(dXyz.as<float>(), nVerts, dMeshVertOff.as<uint32_t>(), dMeshTriOff.as<uint32_t>(), nMeshes, dTriIdx.as<uint32_t>(),
+			nTris, dBoxes.as<float>(), dErr.as<uint32_t>());
+	++launches;
+	LRB_CUDA(cudaEventRecord(ev[2], st));
+	uint32_t errCode = 0;
+	LRB_CUDA(cudaMemcpyAsync(&errCode, dErr.p, 4, cudaMemcpyDeviceToHost, st));
+	LRB_CUDA(cudaStreamSynchronize(st));
+	if (errCode != kRelayoutOk)
+		return Fail(LRB_ERR_INVALID, RelayoutErrorString((int)errCode));
+
+	// the tree
+	DeviceTree tree;
+	{
+		const int rc = BuildTreeOnDevice(dev, dBoxes.as<float>(), nTris, treeType, quality, &tree);
+		if (rc != LRB_OK)
+			return rc;
+	}
+	launches += tree.launches;
+	cudaFree(dBoxes.p);
+	dBoxes.p = nullptr;
+	const uint32_t total = tree.total;
+	if (outNodes && total > outCapacity)
+		return Fail(LRB_ERR_INVALID, "output array too small (2 * triangles - 1 nodes always suffice)");
+	lrb_bvh_node *dNodes = tree.nodes.as<lrb_bvh_node>();
+	const int nodeBlocks = (int)((total + 255) / 256);
+
+	LRB_CUDA(cudaEventRecord(ev[3], st));
+	// 1: leaf payload
+	LeafPayloadKernel<<<nodeBlocks, 256, 0, st>>>(dNodes, total, dMeshTriOff.as<uint32_t>(), nMeshes, dTriIdx.as<uint32_t>());
+	++launches;
+
+	// 2: indices of the wide nodes and of the triangle records
+	DevBuf dCounts, dScanned, dScanTemp, dWideOf;
+	LRB_CUDA(cudaMalloc(&dCounts.p, (size_t)total * 8));
+	LRB_CUDA(cudaMalloc(&dScanned.p, (size_t)total * 8));
+	LRB_CUDA(cudaMalloc(&dWideOf.p, (size_t)total * 4));
+	size_t scanBytes = 0;
+	LRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dCounts.as<unsigned long long>(), dScanned.as<unsigned long long>(), (int)total, st));
+	LRB_CUDA(cudaMalloc(&dScanTemp.p, std::max<size_t>(scanBytes, 16)));
+	RelayoutCountKernel<<<nodeBlocks, 256, 0, st>>>(dNodes, total, dCounts.as<unsigned long long>());
+	LRB_CUDA(cub::DeviceScan::ExclusiveSum(dScanTemp.p, scanBytes, dCounts.as<unsigned long long>(), dScanned.as<unsigned long long>(), (int)total, st));
+	RelayoutIndexKernel<<<nodeBlocks, 256, 0, st>>>(dNodes, total, dScanned.as<unsigned long long>(), dWideOf.as<uint32_t>());
+	launches += 2;
+	unsigned long long lastScan = 0, lastCount = 0;
+	LRB_CUDA(cudaMemcpyAsync(&lastScan, dScanned.as<unsigned long long>() + (total - 1), 8, cudaMemcpyDeviceToHost, st));
+	LRB_CUDA(cudaMemcpyAsync(&lastCount, dCounts.as<unsigned long long>() + (total - 1), 8, cudaMemcpyDeviceToHost, st));
+	LRB_CUDA(cudaStreamSynchronize(st));
+	const unsigned long long sums = lastScan + lastCount;
+	const uint64_t nLeafRecords = sums & 0xffffffffull, nWide64 = 1ull + (sums >> 32);
+	if (nLeafRecords != nTris)
+		return Fail(LRB_ERR_INTERNAL, "device re-layout: leaf count of the built tree differs from the triangle count");
+	if (nWide64 >= kMaxRefIndex || nLeafRecords >= kMaxRefIndex)
+		return Fail(LRB_ERR_INVALID, "too many wide nodes");
+	const uint32_t nWide = (uint32_t)nWide64;
+	cudaFree(dCounts.p); dCounts.p = nullptr;
+	cudaFree(dScanned.p); dScanned.p = nullptr;
+
+	// 3 + 4: the scene's arrays, written in place
+	lrb_scene *s = NewScene(dev);
+	const size_t nb = ((size_t)nWide * sizeof(WideNode) + 255) & ~(size_t)255;
+	const size_t tb = ((size_t)nTris * sizeof(TriRecord) + 255) & ~(size_t)255;
+	const size_t ib = ((size_t)nTris * sizeof(TriIds) + 255) & ~(size_t)255;
+	DevBuf dParentOf, dBelow, dArrived;
+	cudaError_t ce = cudaMalloc(&s->dSlab, nb + tb + ib);
+	if (ce == cudaSuccess) ce = cudaMalloc((void **)&s->dCounter, 256);
+	if (ce == cudaSuccess) ce = cudaMalloc((void **)&s->dStats, sizeof(TraceStats));
+	if (ce == cudaSuccess) ce = cudaMalloc(&dParentOf.p, (size_t)nWide * 4);
+	if (ce == cudaSuccess) ce = cudaMalloc(&dBelow.p, (size_t)nWide * 4);
+	if (ce == cudaSuccess) ce = cudaMalloc(&dArrived.p, (size_t)nWide * 4);
+	if (ce != cudaSuccess) {
+		cudaGetLastError();
+		lrb_scene_free(s);
+		return Fail(ce == cudaErrorMemoryAllocation ? LRB_ERR_OOM : LRB_ERR_CUDA, std::string("device re-layout: ") + cudaGetErrorString(ce));
+	}
+	s->slabBytes = nb + tb + ib;
+	s->dNodes = reinterpret_cast<WideNode *>(s->dSlab);
+	s->dTris = reinterpret_cast<TriRecord *>((char *)s->dSlab + nb);
+	s->dIds = reinterpret_cast<TriIds *>((char *)s->dSlab + nb + tb);
+	s->capNodes = nWide;
+	s->info.device_bytes = s->slabBytes + 256 + sizeof(TraceStats);
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		dev->counters.device_bytes_in_use += s->info.device_bytes;
+	}
+	TriTreeView tv;
+	tv.nodes = dNodes; tv.n = total; tv.xyz = dXyz.as<float>(); tv.nVerts = nVerts; tv.meshOff = dMeshVertOff.as<uint32_t>(); tv.nMeshes = nMeshes;
+	uint32_t *dStatus = dErr.as<uint32_t>();
+	cudaMemsetAsync(dBelow.p, 0, (size_t)nWide * 4, st);
+	cudaMemsetAsync(dArrived.p, 0, (size_t)nWide * 4, st);
+	RelayoutFillKernel<<<(int)((total + 127) / 128), 128, 0, st>>>(tv, dWideOf.as<uint32_t>(), s->dNodes, s->dTris, s->dIds, dParentOf.as<uint32_t>(),
+			reinterpret_cast<float *>(dStatus + 2), dStatus);
+	StackNeedKernel<<<(int)((nWide + 255) / 256), 256, 0, st>>>(s->dNodes, nWide, dParentOf.as<uint32_t>(), dBelow.as<uint32_t>(), dArrived.as<uint32_t>(), dStatus + 1);
+	launches += 2;
+	cudaEventRecord(ev[4], st);
+	uint32_t status[8];
+	memset(status, 0, sizeof(status));
+	cudaMemcpyAsync(status, dStatus, sizeof(status), cudaMemcpyDeviceToHost, st);
+	if (outNodes) {
+		cudaMemcpyAsync(outNodes, dNodes, (size_t)total * sizeof(lrb_bvh_node), cudaMemcpyDeviceToHost, st);
+		dev->counters.d2h_bytes += (uint64_t)total * sizeof(lrb_bvh_node);
+	}
+	cudaEventRecord(ev[5], st);
+	ce = cudaStreamSynchronize(st);
+	if (ce == cudaSuccess) ce = cudaGetLastError();
+	if (ce != cudaSuccess) {
+		lrb_scene_free(s);
+		return Fail(LRB_ERR_CUDA, std::string("device re-layout: ") + cudaGetErrorString(ce));
+	}
+	if (status[0] != kRelayoutOk) {
+		lrb_scene_free(s);
+		return Fail(LRB_ERR_INVALID, RelayoutErrorString((int)status[0]));
+	}
+	dev->counters.kernel_launches += launches;
+
+	// bookkeeping the host path takes from its WideScene (FillView / FillRootOfView)
+	s->host.twoLevel = false;
+	s->host.nRefNodes = total;
+	s->host.rootWide = 0;
+	s->host.stackNeed = status[1] + 1;
+	memcpy(s->host.entryBox, status + 2, 24);
+	SceneView &v = s->view;
+	v.nodes = s->dNodes;
+	v.tris = s->dTris;
+	v.ids = s->dIds;
+	v.nWide = nWide;
+	v.rootWide = 0;
+	v.twoLevel = 0;
+	v.rootHasBox = 1;
+	v.rootChild = 1;            // the root is the first inner node of the array: wide node 1, behind the entry node
+	memcpy(v.rootBox, status + 2, 24);
+	v.oneBits = 0x3f800000u;
+	s->info.n_ref_nodes = total;
+	s->info.n_wide_nodes = nWide;
+	s->info.n_triangles = nTris;
+	s->info.n_instances = 0;
+	s->info.stack_need = s->host.stackNeed;
+	s->info.two_level = 0;
+	if (nNodes) *nNodes = total;
+	if (timings) {
+		float ms;
+		cudaEventElapsedTime(&ms, ev[0], ev[1]); timings->h2d_ms = ms;
+		cudaEventElapsedTime(&ms, ev[1], ev[2]); timings->leafbox_ms = ms;
+		timings->sort_ms = tree.sortMs;
+		timings->tree_ms = tree.treeMs;
+		timings->emit_ms = tree.emitMs;
+		cudaEventElapsedTime(&ms, ev[3], ev[4]); timings->relayout_ms = ms;
+		cudaEventElapsedTime(&ms, ev[4], ev[5]); timings->d2h_ms = outNodes ? ms : 0.0;
+		timings->kernels = launches;
+	}
+	*out = s;
+	return LRB_OK;
+}
+
+int lrb_scene_adopt(lrb_device *dev, lrb_scene *s) {
+	if (!dev || !s)
+		return Fail(LRB_ERR_INVALID, "null argument");
+	lrb_device *old = s->dev;
+	if (old == dev)
+		return LRB_OK;
+	if (old->ordinal != dev->ordinal)
+		return Fail(LRB_ERR_INVALID, "a scene can only be handed to a device handle of the same CUDA device");
+	LRB_SETDEV(old);
+	{
+		const int rc = JoinPending(old);
+		if (rc != LRB_OK) return rc;
+	}
+	LRB_CUDA(cudaStreamSynchronize(old->stream));
+	if (old->l2WindowBase && old->l2WindowBase == s->dSlab)
+		ClearL2Window(old);
+	{
+		std::lock_guard<std::mutex> g(old->mtx);
+		old->counters.device_bytes_in_use -= std::min<uint64_t>(old->counters.device_bytes_in_use, s->info.device_bytes);
+	}
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);
+		dev->counters.device_bytes_in_use += s->info.device_bytes;
+	}
+	s->dev = dev;
+	return LRB_OK;
 }
 
 int lrb_trace_stats(lrb_scene *s, const void *rays, void *hits, uint32_t n, lrb_trace_stats_t *out) {

@@ -5,6 +5,7 @@
 // upload (bvhaccelhw.cpp:126-145, mbvhaccelhw.cpp:380-427).
 
 #include "relayout.h"
+#include "relayout_shared.h"  // the per-node functions shared with the device re-layout (relayout_kernels.cuh)
 #include "traverse.h"       // MotionSample: the kernels' own MotionSystem::Sample, compiled for the host
 
 #include <algorithm>
@@ -71,32 +72,19 @@ struct TreeInput {
 	const std::vector<DevInterp> *interps;
 };
 
+static inline TriTreeView TriViewOf(const TreeInput &in) {
+	TriTreeView v;
+	v.nodes = in.nodes; v.n = in.n; v.xyz = in.xyz; v.nVerts = in.nVerts; v.meshOff = in.meshOff; v.nMeshes = in.nMeshes;
+	return v;
+}
+
+static inline void ThrowIfRelayoutError(const int rc) {
+	if (rc != kRelayoutOk)
+		throw std::runtime_error(RelayoutErrorString(rc));
+}
+
 static void FillTri(const TreeInput &in, uint32_t c, TriRecord *tr, TriIds *ids = nullptr) {
-	const lrb_bvh_node &nd = in.nodes[c];
-	const uint32_t mesh = nd.triangleLeaf.meshIndex;
-	if (mesh >= in.nMeshes)
-		throw std::runtime_error("triangle leaf references a mesh outside the vertex-offset table");
-	const float *p[3];
-	for (int j = 0; j < 3; ++j) {
-		const uint64_t g = (uint64_t)nd.triangleLeaf.v[j] + in.meshOff[mesh];
-		if (g >= in.nVerts)
-			throw std::runtime_error("triangle leaf references a vertex outside the vertex buffer");
-		p[j] = in.xyz + 3 * g;
-	}
-	for (int k = 0; k < 3; ++k) {
-		tr->p0[k] = p[0][k];
-		tr->p1[k] = p[1][k];
-		tr->p2[k] = p[2][k];
-	}
-	for (int k = 0; k < 3; ++k) {
-		tr->gateLo[k] = -std::numeric_limits<float>::infinity();
-		tr->gateHi[k] = std::numeric_limits<float>::infinity();
-	}
-	tr->order = c;
-	if (ids) {
-		ids->meshIndex = mesh;
-		ids->triangleIndex = nd.triangleLeaf.triangleIndex;
-	}
+	ThrowIfRelayoutError(FillTriOf(TriViewOf(in), c, tr, ids));
 }
 
 static void FillInst(const TreeInput &in, uint32_t c, InstRecord *ir) {
@@ -116,137 +104,11 @@ static void FillInst(const TreeInput &in, uint32_t c, InstRecord *ir) {
 	ir->pad[0] = (*in.leafStackNeed)[nd.bvhLeaf.leafIndex];   // host-side bookkeeping only
 }
 
-// MachineEpsilon::E (include/luxrays/core/epsilon.h:48-86) with the default clamp 1e-5 .. 1e-1.
-static inline float EpsOf(float v) {
-	union { float f; uint32_t i; } mf;
-	mf.f = v;
-	mf.i += 0x80u;
-	const float e = fabsf(mf.f - v);
-	return e > 1e-5f ? (e < 1e-1f ? e : 1e-1f) : 1e-5f;
-}
-
 static const float kInfF = std::numeric_limits<float>::infinity();
 
-// Float boxes of the slots of one wide node, before they are put on the node's grid.
-struct SlotBoxes {
-	float lo[kWideSlots][3], hi[kWideSlots][3];
-	bool whole[kWideSlots];         // MBVH root leaf: the slot covers the whole grid
-	uint32_t child[kWideSlots];
-	uint32_t n;
-	bool hasOwn;                    // the node's own reference box (bounds every child, instances included)
-	float ownLo[3], ownHi[3];
-	SlotBoxes() : n(0), hasOwn(false) {}
-};
-
-static inline uint32_t NodeSlots(const WideNode &w) { return w.exps >> 24; }
-
-// Puts the slot boxes on the node's grid (layout.h): origin = min corner of everything the node
-// bounds, power-of-two step per axis, lower planes rounded down and upper planes rounded up with a
-// 1/64-step margin (the kernel's decode error is below 2^-9 step, traverse.h).
-static void QuantizeNode(const SlotBoxes &b, uint32_t next, uint32_t flags, WideNode *w) {
-	memset(w, 0, sizeof(*w));
-	w->next = next;
-	w->flags = flags;
-	for (uint32_t k = 0; k < kWideSlots; ++k)
-		w->child[k] = k < b.n ? b.child[k] : kNullIndex;
-	uint32_t exps = b.n << 24;
-	for (int a = 0; a < 3; ++a) {
-		double lo = std::numeric_limits<double>::infinity(), hi = -lo;
-		if (b.hasOwn) { lo = b.ownLo[a]; hi = b.ownHi[a]; }
-		for (uint32_t k = 0; k < b.n; ++k) {
-			if (b.whole[k]) continue;
-			lo = std::min(lo, (double)b.lo[k][a]);
-			hi = std::max(hi, (double)b.hi[k][a]);
-		}
-		int eb;             // biased exponent byte of step * 2^kGridShift
-		float org;
-		uint32_t qlo = 0, qhi = 0;
-		if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {
-			// nothing finite to bound (a lone MBVH root leaf, or non-finite input): the axis never rejects.
-			// Exponent byte 255 makes the decode scale +inf: A = +-inf, B = finite - A = -+inf, and every
-			// plane distance fma(q, A, B) is inf - inf = NaN, which the slab test ignores -- for every ray,
-			// with no overflow edge (a huge finite grid fails where A is finite but B overflows).
-			org = 0.f;
-			eb = 255;
-			for (uint32_t k = 0; k < kWideSlots; ++k) {
-				qlo |= (k < b.n ? 0u : 255u) << (8 * k);
-				qhi |= (k < b.n ? 255u : 0u) << (8 * k);
-			}
-		} else {
-			// smallest power-of-two step with 250 steps >= extent, but never finer than 4 ulp of the
-			// largest coordinate (the grid origin is a float)
-			const double ext = hi - lo;
-			int E = -140, e2;
-			if (ext > 0.0) {
-				const double m = frexp(ext / 250.0, &e2);      // ext / 250 = m * 2^e2, m in [0.5, 1)
-				E = (m == 0.5) ? e2 - 1 : e2;
-			}
-			const double mag = std::max(fabs(lo), fabs(hi));
-			if (mag > 0.0) {
-				frexp(mag, &e2);
-				E = std::max(E, e2 - 24 + 2);
-			}
-			E = std::max(E, 1 - kGridShift - 127);
-			for (;; ++E) {
-				eb = E + kGridShift + 127;
-				if (eb > 254)
-					throw std::runtime_error("BVH box coordinates are too large for the node grid");
-				const double step = ldexp(1.0, E);
-				// the origin sits 1.5 steps below the lowest plane: every plane keeps its outward margin
-				// (no plane is clamped at 0 or 255), whole-grid slots extend past the node's own box
-				org = (float)(lo - 1.5 * step);
-				bool ok = std::isfinite(org);
-				qlo = qhi = 0;
-				for (uint32_t k = 0; k < kWideSlots && ok; ++k) {
-					uint32_t l = 255, h = 0;        // unused slot: inverted
-					if (k < b.n) {
-						if (b.whole[k]) {
-							l = 0; h = 255;
-						} else {
-							const double xl = ((double)b.lo[k][a] - (double)org) / step, xh = ((double)b.hi[k][a] - (double)org) / step;
-							const double fl = floor(xl - 1.0 / 64.0), ch = ceil(xh + 1.0 / 64.0);
-							if (!(fl >= 0.0) || !(ch <= 255.0) || !(fl <= ch)) {
-								ok = false;     // needs a coarser grid (or the child box is not finite)
-								break;
-							}
-							l = (uint32_t)fl;
-							h = (uint32_t)ch;
-						}
-					}
-					qlo |= l << (8 * k);
-					qhi |= h << (8 * k);
-				}
-				if (ok)
-					break;
-				bool finite = true;
-				for (uint32_t k = 0; k < b.n; ++k)
-					if (!b.whole[k] && (!std::isfinite(b.lo[k][a]) || !std::isfinite(b.hi[k][a]) || !(b.lo[k][a] <= b.hi[k][a])))
-						finite = false;
-				if (!finite)
-					throw std::runtime_error("internal error: a non-finite slot box reached the node grid");
-			}
-		}
-		w->org[a] = org;
-		w->qlo[a] = qlo;
-		w->qhi[a] = qhi;
-		exps |= (uint32_t)eb << (8 * a);
-	}
-	w->exps = exps;
-}
-
-// The box BVHAccel::Init gives the builders for one triangle (bvhaccel.cpp:116-122): bounds of the
-// three vertices, grown by MachineEpsilon::E of the bounds.
-static void TriBuildBox(const TriRecord &tr, float lo[3], float hi[3]) {
-	float e = 0.f;
-	for (int k = 0; k < 3; ++k) {
-		lo[k] = std::min(std::min(tr.p0[k], tr.p1[k]), tr.p2[k]);
-		hi[k] = std::max(std::max(tr.p0[k], tr.p1[k]), tr.p2[k]);
-		e = std::max(e, std::max(EpsOf(lo[k]), EpsOf(hi[k])));
-	}
-	for (int k = 0; k < 3; ++k) {
-		lo[k] -= e;
-		hi[k] += e;
-	}
+// EpsOf, SlotBoxes, NodeSlots, QuantizeNode, TriBuildBox, SanitizeSlot: relayout_shared.h
+static void QuantizeNodeOrThrow(const SlotBoxes &b, uint32_t next, uint32_t flags, WideNode *w) {
+	ThrowIfRelayoutError(QuantizeNode(b, next, flags, w));
 }
 
 // 4x4 inverse in double precision (Gauss-Jordan with partial pivoting); false when singular.
@@ -437,21 +299,6 @@ static bool MotionWorldBox(const TreeInput &in, const lrb_bvh_node &nd, const fl
 	return true;
 }
 
-// Boxes the reference's builders never emit but its traversal tolerates: BBox::IntersectP swaps the two
-// slab distances when they come out of order, so a box with min > max behaves like the sorted box, and
-// every comparison with a NaN is false, so a NaN plane never rejects.  Same behaviour here: corners
-// are sorted per axis, a box with a non-finite corner covers the whole grid of its node.
-static void SanitizeSlot(SlotBoxes *b, uint32_t k) {
-	for (int a = 0; a < 3; ++a) {
-		if (!std::isfinite(b->lo[k][a]) || !std::isfinite(b->hi[k][a])) {
-			b->whole[k] = true;
-			return;
-		}
-		if (b->lo[k][a] > b->hi[k][a])
-			std::swap(b->lo[k][a], b->hi[k][a]);
-	}
-}
-
 // Half the surface area of the box slot `c` will get (+inf for a slot that covers the whole grid).
 static double SlotSizeKey(const TreeInput &in, uint32_t c) {
 	const lrb_bvh_node &ch = in.nodes[c];
@@ -532,7 +379,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		}
 		AddSlot(in, wideOf, 0, nullptr, &b, out);
 		WideNode w;
-		QuantizeNode(b, kNullIndex, 0, &w);
+		QuantizeNodeOrThrow(b, kNullIndex, 0, &w);
 		*stackNeed = kWideSlots - 1;        // the unused slots "pass" for a NaN ray (see the sweep at the end)
 		if (in.instLeaves)
 			*stackNeed += 1 + (*in.leafStackNeed)[nodes[0].bvhLeaf.leafIndex];
@@ -586,7 +433,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		for (int a = 0; a < 3; ++a) { b.lo[0][a] = nodes[0].bvhNode.bboxMin[a]; b.hi[0][a] = nodes[0].bvhNode.bboxMax[a]; }
 		b.child[0] = wideOf[0];
 		SanitizeSlot(&b, 0);
-		QuantizeNode(b, kNullIndex, kNodeEntry, &out->wide[wideStart]);
+		QuantizeNodeOrThrow(b, kNullIndex, kNodeEntry, &out->wide[wideStart]);
 		if (in.instLeaves || !out->twoLevel) {
 			for (int a = 0; a < 3; ++a) {
 				out->entryBox[a] = nodes[0].bvhNode.bboxMin[a];
@@ -600,12 +447,22 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	// Pass 2: fill, children in reference order.  Every inner node writes its own wide node(s) and its own
 	// triangle records (indices fixed in pass 1), so ranges of the array are filled concurrently for big triangle
 	// trees (a 50 M-triangle soup: 74 M reference nodes); instance trees append to `insts` and stay serial.
+	const TriTreeView triView = TriViewOf(in);
 	auto fillRange = [&](const uint32_t i0, const uint32_t i1) {
 		std::vector<uint32_t> kids;
 		std::vector<std::pair<double, uint32_t> > keyed;
 		for (uint32_t i = i0; i < i1; ++i) {
 			if (IsLeaf(nodes[i].nodeData))
 				continue;
+			if (!in.instLeaves) {
+				// triangle trees: the body shared with the device re-layout (relayout_shared.h); nodes of an arity
+				// above the builders' maximum of 8 (a foreign array) take the general path below
+				const int rc = ConvertInnerNodeTri(triView, i, wideOf.data(), out->wide.data(), out->tris.data(), out->ids.data(), nullptr);
+				if (rc == kRelayoutOk)
+					continue;
+				if (rc != kRelayoutTooManyKids)
+					ThrowIfRelayoutError(rc);
+			}
 			kids.clear();
 			const uint32_t end = Skip(nodes[i].nodeData);
 			for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData))
@@ -633,7 +490,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 				for (int a = 0; a < 3; ++a) { b.ownLo[a] = nodes[i].bvhNode.bboxMin[a]; b.ownHi[a] = nodes[i].bvhNode.bboxMax[a]; }
 				for (uint32_t k = 0; k < cnt; ++k)
 					AddSlot(in, wideOf, kids[first + k], &nodes[i], &b, out);
-				QuantizeNode(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
+				QuantizeNodeOrThrow(b, (j + 1 < nW) ? (wideOf[i] + j + 1) : kNullIndex, 0, &out->wide[wideOf[i] + j]);
 			}
 		}
 	};

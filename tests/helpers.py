@@ -275,6 +275,89 @@ class Emu:
         return hits
 
 
+def flattened_triangles(desc):
+    """Triangle index buffer + per-mesh triangle offsets (n_meshes + 1 entries) in dataset order: what
+    lrb_bvh_build_scene takes next to flattened_from_oracle's vertices (mesh-local indices, luxrays::Triangle::v)."""
+    tris, offs, total = [], [0], 0
+    for m in desc.meshes:
+        t = np.ascontiguousarray(desc.shapes[m.shape][1], dtype=np.uint32).reshape(-1, 3)
+        tris.append(t)
+        total += t.shape[0]
+        offs.append(total)
+    return (np.concatenate(tris) if tris else np.zeros((0, 3), np.uint32)), np.asarray(offs, dtype=np.uint32)
+
+
+def to_builder_format(nodes, mesh_tri_offsets):
+    """A reference array as the GPU builder kernels emit it BEFORE the leaf payload is written: leaves carry the number of
+    their triangle in the concatenated triangle buffer in the first word and zeros elsewhere (build_kernels.cuh EmitKernel)."""
+    out = np.array(nodes, copy=True)
+    leaf = (out["nodeData"] & 0x80000000) != 0
+    w = out["w"]
+    g = np.asarray(mesh_tri_offsets, dtype=np.uint32)[w[leaf, 3]] + w[leaf, 4]
+    w[leaf] = 0
+    w[leaf, 0] = g
+    out["pad0"] = 0
+    return out
+
+
+class RelayoutDev:
+    """The per-record bodies of the DEVICE re-layout (luxcore_b200/csrc/relayout_kernels.cuh, relayout_shared.h) compiled for
+    the host and driven in the device pipeline's order by tests/cpp/relayout_device_emulation.cpp."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            d = os.path.join(ROOT, "tests", "cpp")
+            csrc = os.path.join(ROOT, "luxcore_b200", "csrc")
+            so = os.path.join(d, "librelayout_device_emulation.so")
+            src = os.path.join(d, "relayout_device_emulation.cpp")
+            deps = [src] + [os.path.join(csrc, f) for f in ("relayout_kernels.cuh", "relayout_shared.h", "layout.h")]
+            if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-msse", "-msse2", "-mfma", "-ffp-contract=off",
+                                       "-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-o", so, src])
+            L = C.CDLL(so)
+            L.rde_last_error.restype = C.c_char_p
+            L.rde_run.restype = C.c_void_p
+            L.rde_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+            L.rde_free.argtypes = [C.c_void_p]
+            for f in (L.rde_info, L.rde_copy_nodes, L.rde_copy_tris, L.rde_copy_ids, L.rde_copy_ref_nodes, L.rde_copy_boxes, L.rde_copy_entry_box):
+                f.argtypes = [C.c_void_p, C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def run(cls, builder_nodes, verts, mesh_vert_offsets, tri_idx, mesh_tri_offsets):
+        """-> dict(wide, tris, ids, ref_nodes, boxes, stack_need, entry_box)"""
+        L = cls.lib()
+        nodes = np.ascontiguousarray(builder_nodes)
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        voff = np.ascontiguousarray(mesh_vert_offsets, dtype=np.uint32)
+        toff = np.ascontiguousarray(mesh_tri_offsets, dtype=np.uint32)
+        tri = np.ascontiguousarray(tri_idx, dtype=np.uint32).reshape(-1, 3)
+        h = L.rde_run(nodes.ctypes.data, nodes.shape[0], verts.ctypes.data, verts.shape[0], voff.ctypes.data, toff.ctypes.data, voff.shape[0], tri.ctypes.data)
+        if not h:
+            raise RuntimeError(L.rde_last_error().decode())
+        try:
+            info = np.zeros(3, dtype=np.uint32)
+            L.rde_info(h, info.ctypes.data)
+            wide = np.zeros(int(info[0]), dtype=Emu.WIDE_DTYPE)
+            tris = np.zeros(int(info[1]), dtype=Emu.TRI_DTYPE)
+            ids = np.zeros(int(info[1]), dtype=Emu.IDS_DTYPE)
+            ref = np.zeros(nodes.shape[0], dtype=nodes.dtype)
+            boxes = np.zeros((tri.shape[0], 6), dtype=np.float32)
+            entry = np.zeros(6, dtype=np.float32)
+            L.rde_copy_nodes(h, wide.ctypes.data)
+            L.rde_copy_tris(h, tris.ctypes.data)
+            L.rde_copy_ids(h, ids.ctypes.data)
+            L.rde_copy_ref_nodes(h, ref.ctypes.data)
+            L.rde_copy_boxes(h, boxes.ctypes.data)
+            L.rde_copy_entry_box(h, entry.ctypes.data)
+        finally:
+            L.rde_free(h)
+        return {"wide": wide, "tris": tris, "ids": ids, "ref_nodes": ref, "boxes": boxes, "stack_need": int(info[2]), "entry_box": entry}
+
+
 class Lockstep:
     """The product's REAL kernel source (luxcore_b200/csrc/trace_kernels.cuh) compiled for the host against a
     stand-in <cuda_runtime.h> and run with one OS thread per lane (tests/cpp/kernel_lockstep.cpp)."""

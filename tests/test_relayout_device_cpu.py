@@ -1,0 +1,86 @@
+"""The DEVICE re-layout's per-record code (luxcore_b200/csrc/relayout_kernels.cuh + relayout_shared.h: what the kernels of
+lrb_bvh_build_scene run, one thread per record) compiled for the host and driven in the device pipeline's order, held to the
+BYTES of the host re-layout (relayout.cpp BuildWideBVH, what lrb_bvh_upload runs) of the same reference array.  On the GPU
+box tests/test_gpu_builder.py repeats the comparison with the real kernels."""
+import numpy as np
+import pytest
+
+import helpers as H
+from luxcore_b200 import hostapi
+from luxcore_b200 import scenes as S
+from oracle import oracle as O
+
+
+def _arrays(desc):
+    osc = H.oracle_scene(desc)
+    verts, voff = H.flattened_from_oracle(desc, osc)
+    tri, toff = H.flattened_triangles(desc)
+    return osc, verts, voff, tri, toff
+
+
+def _check(nodes, verts, voff, tri, toff, what):
+    emu = H.Emu.bvh(nodes, verts, voff)
+    wide, tris, ids = emu.arrays()
+    dev = H.RelayoutDev.run(H.to_builder_format(nodes, toff), verts, voff, tri, toff)
+    # the leaf payload written on the device gives back the array a host builder would have made
+    assert dev["ref_nodes"].tobytes() == np.ascontiguousarray(nodes).tobytes(), what + ": reference array"
+    assert dev["wide"].shape == wide.shape and dev["wide"].tobytes() == wide.tobytes(), what + ": wide nodes"
+    assert dev["tris"].tobytes() == tris.tobytes(), what + ": triangle records"
+    assert dev["ids"].tobytes() == ids.tobytes(), what + ": triangle ids"
+    assert dev["stack_need"] == emu.info()["stack_need"], what + ": stack bound"
+    # exact root box = the reference's node 0
+    root = np.ascontiguousarray(nodes)[0]["w"].view(np.float32)
+    assert np.array_equal(dev["entry_box"], root), what + ": root box"
+    return dev
+
+
+@pytest.mark.parametrize("name", ["cornell", "bigmonkey", "kitchen", "luxball"])
+@pytest.mark.parametrize("tree_type", [2, 4, 8])
+def test_device_relayout_bodies_equal_the_host_relayout_classic_trees(name, tree_type):
+    desc = S.load_fixture(name)
+    osc, verts, voff, tri, toff = _arrays(desc)
+    nodes = O.BVH(osc, tree_type=tree_type).nodes()
+    _check(nodes, verts, voff, tri, toff, "%s CLASSIC k=%d" % (name, tree_type))
+
+
+@pytest.mark.parametrize("name,tree_type", [("kitchen", 4), ("kitchen", 8), ("classroom", 4)])
+def test_device_relayout_bodies_equal_the_host_relayout_sah_trees(name, tree_type):
+    desc = S.load_fixture(name)
+    osc, verts, voff, tri, toff = _arrays(desc)
+    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": tree_type}, desc)
+    sess.build_accelerator("BVH")
+    _check(sess.bvh_nodes(), verts, voff, tri, toff, "%s SAH k=%d" % (name, tree_type))
+
+
+def test_device_relayout_bodies_on_a_soup_and_its_build_boxes():
+    n = 200000
+    desc = S.random_soup(n, seed=4, size=0.002 * (50e6 / n) ** (1.0 / 3.0), name="soup")
+    osc, verts, voff, tri, toff = _arrays(desc)
+    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": 4}, desc)
+    sess.build_accelerator("BVH")
+    dev = _check(sess.bvh_nodes(), verts, voff, tri, toff, "soup")
+    # LeafBoxKernel's boxes: bounds of the three vertices grown by MachineEpsilon::E of the bounds (bvhaccel.cpp:116-122),
+    # recomputed here with numpy from the definition in epsilon.h:48-86
+    p = verts[tri.reshape(-1)].reshape(-1, 3, 3)
+    lo, hi = p.min(axis=1), p.max(axis=1)
+
+    def eps(v):
+        bumped = (v.view(np.uint32) + np.uint32(0x80)).view(np.float32)
+        return np.clip(np.abs(bumped - v), np.float32(1e-5), np.float32(1e-1)).astype(np.float32)
+    e = np.maximum(eps(lo).max(axis=1), eps(hi).max(axis=1))[:, None]
+    assert np.array_equal(dev["boxes"][:, :3], lo - e) and np.array_equal(dev["boxes"][:, 3:], hi + e)
+
+
+def test_mesh_lookup_skips_empty_meshes():
+    """Leaf payload with empty meshes in the table: triangle g belongs to the LAST mesh whose offset is <= g."""
+    desc = S.load_fixture("cornell")
+    osc, verts, voff, tri, toff = _arrays(desc)
+    nodes = O.BVH(osc, tree_type=4).nodes()
+    # insert an empty mesh after mesh 0: mesh indices >= 1 shift by one
+    voff2 = np.insert(voff, 1, voff[1]).astype(np.uint32)
+    toff2 = np.insert(toff, 1, toff[1]).astype(np.uint32)
+    shifted = np.array(nodes, copy=True)
+    leaf = (shifted["nodeData"] & 0x80000000) != 0
+    w = shifted["w"]
+    w[leaf, 3] = np.where(w[leaf, 3] >= 1, w[leaf, 3] + 1, w[leaf, 3])
+    _check(shifted, verts, voff2, tri, toff2, "cornell + empty mesh")
