@@ -284,6 +284,8 @@ def main():
     torch.cuda.set_stream(stream)
 
     desc = build_scene_arrays(args.scene)
+    # GPU builders (EMBREE_MORTON / B200_PLOC) build on the GPU the rank traces on, so that the scene stays where it was built
+    os.environ.setdefault("LRB_BUILDER_DEVICE", str(local_rank))
     t0 = time.perf_counter()
     sess = hostapi.Session(accel_config(args), desc)
     sess.build_accelerator(args.accel)

@@ -43,6 +43,12 @@ private:
 	std::deque<const Mesh *> meshes;
 	u_longlong totalVertexCount, totalTriangleCount;
 	bool initialized;
+
+	// B200 extension (builder types EMBREE_MORTON / B200_PLOC): the accelerator as the device built and laid it out, waiting
+	// for the BVHKernel of the same CUDA device to adopt it (then NULL again).  Leaf BVHs of an MBVH never have one.
+	bool allowResidentScene;
+	mutable void *residentScene;
+	mutable int residentOrdinal;
 };
 
 }   // namespace luxrays

@@ -71,6 +71,15 @@ extern ocl::BVHArrayNode *BuildEmbreeBVHMorton(const BVHParams &params, u_int *n
 extern ocl::BVHArrayNode *BuildB200BVHPloc(const BVHParams &params, u_int *nNodes,
 		const std::deque<const Mesh *> *meshes, std::vector<BVHTreeNode *> &leafList);
 
+// extension: the whole single-level accelerator made ON the device (C ABI lrb_bvh_build_scene: triangle boxes, tree, leaf
+// payload and the device lay-out, none of it on the host).  quality 0 = EMBREE_MORTON's radix tree, 1 = B200_PLOC.  Fills
+// *nodes / *nNodes with the reference array (downloaded once: BVHAccel::bvhTree stays what the reference's friends read) and
+// *scene with the resident scene (an lrb_scene of CUDA device *ordinal) that BVHKernel adopts instead of uploading.
+// Returns false, touching nothing, when there is no CUDA device (the caller then builds on the host).
+extern bool BuildB200SceneOnDevice(const BVHParams &params, const u_int quality, const std::deque<const Mesh *> &meshes,
+		ocl::BVHArrayNode **nodes, u_int *nNodes, void **scene, int *ordinal);
+extern void FreeB200ResidentScene(void *scene);
+
 }   // namespace luxrays
 
 #endif

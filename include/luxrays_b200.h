@@ -350,6 +350,10 @@ LRB_API int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t n_ve
  * device is started: Context::SetDataSet / Start, context.cpp:173-232): the scene's memory accounting moves to `dev`
  * and its traces run on dev's queue from now on.  Fails, and changes nothing, when the CUDA ordinals differ. */
 LRB_API int lrb_scene_adopt(lrb_device *dev, lrb_scene *scene);
+/* Diagnostics: copies the laid-out arrays of a single-level scene back to the host -- n_wide_nodes records of 64 B,
+ * n_triangles records of 64 B, n_triangles id pairs of 8 B (counts from lrb_scene_get_info; any pointer may be NULL).
+ * The tests compare a scene laid out on the device with the host's lay-out of the same array byte for byte. */
+LRB_API int lrb_scene_download(lrb_scene *scene, void *wide_nodes, void *tri_records, void *tri_ids);
 
 /* ---- multi-GPU: film merge over NVLink -------------------------------------------------------- */
 /* The sum of per-GPU film planes that replaces the host-side merge of per-device films

@@ -35,6 +35,7 @@ EXPORTS = [
     "lrb_measure_read_bandwidth",
     "lrb_ipc_get_handle", "lrb_ipc_open_handle", "lrb_ipc_close_handle", "lrb_trace_gather", "lrb_gather_wait", "lrb_film_reduce",
     "lrb_build_lbvh", "lrb_build_bvh", "lrb_gather_signal", "lrb_wait_value",
+    "lrb_bvh_build_scene", "lrb_scene_adopt", "lrb_scene_download",
 ]
 
 
@@ -71,6 +72,14 @@ class TraceStats(C.Structure):
 class BuildTimings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("sort_ms", C.c_double), ("tree_ms", C.c_double), ("emit_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("kernels", C.c_uint32)]
+
+
+class SceneBuildTimings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("leafbox_ms", C.c_double), ("sort_ms", C.c_double), ("tree_ms", C.c_double),
+                ("emit_ms", C.c_double), ("relayout_ms", C.c_double), ("d2h_ms", C.c_double), ("kernels", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class LrbError(RuntimeError):
@@ -134,6 +143,9 @@ def lib():
             "lrb_gather_signal": (i32, [vp, vp, u32]),
             "lrb_wait_value": (i32, [vp, vp, u32, vp]),
             "lrb_build_bvh": (i32, [vp, vp, u32, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(BuildTimings)]),
+            "lrb_bvh_build_scene": (i32, [vp, vp, u64, vp, vp, u32, vp, u32, u32, pvp, vp, u32, C.POINTER(u32), C.POINTER(SceneBuildTimings)]),
+            "lrb_scene_adopt": (i32, [vp, vp]),
+            "lrb_scene_download": (i32, [vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -290,6 +302,24 @@ class Device:
         _check(lib().lrb_build_bvh(self.h, _ptr(boxes), n, tree_type, quality, _ptr(out), out.shape[0], C.byref(total), C.byref(tm)))
         return out[:total.value].copy(), tm
 
+    def build_scene(self, verts, mesh_vertex_offsets, triangles, mesh_triangle_offsets, tree_type=4, quality=1, want_nodes=False, node_dtype=None):
+        """lrb_bvh_build_scene: triangles in, traceable scene out, everything on the device (leaf boxes, tree, leaf payload,
+        re-layout).  verts [n, 3] float32 + first vertex per mesh, triangles [t, 3] uint32 (mesh-local indices) + first
+        triangle per mesh (n_meshes + 1 entries).  -> (Scene, SceneBuildTimings, reference array or None)."""
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        voff = np.ascontiguousarray(mesh_vertex_offsets, dtype=np.uint32)
+        tri = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        toff = np.ascontiguousarray(mesh_triangle_offsets, dtype=np.uint32)
+        assert toff.shape[0] == voff.shape[0] + 1 and int(toff[-1]) == tri.shape[0]
+        dt = node_dtype or np.dtype([("w", "<u4", 6), ("nodeData", "<u4"), ("pad0", "<i4")])
+        out = np.zeros(max(1, 2 * tri.shape[0]), dtype=dt) if want_nodes else None
+        total = C.c_uint32()
+        tm = SceneBuildTimings()
+        s = C.c_void_p()
+        _check(lib().lrb_bvh_build_scene(self.h, _ptr(verts), verts.shape[0], _ptr(voff), _ptr(toff), voff.shape[0], _ptr(tri), tree_type, quality,
+                                         C.byref(s), _ptr(out) if want_nodes else None, out.shape[0] if want_nodes else 0, C.byref(total), C.byref(tm)))
+        return Scene(self, s), tm, (out[:total.value].copy() if want_nodes else None)
+
     # ---- scenes ----
     def upload_bvh(self, nodes, verts, mesh_vertex_offsets):
         nodes = np.ascontiguousarray(nodes)
@@ -364,6 +394,20 @@ class Scene:
         i = SceneInfo()
         _check(lib().lrb_scene_get_info(self.h, C.byref(i)))
         return i
+
+    def adopt(self, dev):
+        """lrb_scene_adopt: hand the scene to another Device handle of the same CUDA device."""
+        _check(lib().lrb_scene_adopt(dev.h, self.h))
+        self.dev = dev
+
+    def download(self):
+        """lrb_scene_download -> (wide nodes [n, 64] uint8, triangle records [t, 64] uint8, triangle ids [t, 2] uint32)."""
+        i = self.info()
+        wide = np.zeros((i.n_wide_nodes, 64), dtype=np.uint8)
+        tris = np.zeros((i.n_triangles, 64), dtype=np.uint8)
+        ids = np.zeros((i.n_triangles, 2), dtype=np.uint32)
+        _check(lib().lrb_scene_download(self.h, _ptr(wide) if wide.size else None, _ptr(tris) if tris.size else None, _ptr(ids) if ids.size else None))
+        return wide, tris, ids
 
     def update(self, root_nodes, transforms_minv):
         root_nodes = np.ascontiguousarray(root_nodes)

@@ -923,6 +923,10 @@ static int EnsureSpill(lrb_scene *s, uint32_t residentDepth, int totalThreads) {
 	LRB_CUDA(cudaMalloc((void **)&s->dSpillNode, entries * sizeof(uint32_t)));
 	LRB_CUDA(cudaMalloc((void **)&s->dSpillT, entries * sizeof(float)));
 	s->info.device_bytes += (entries - s->spillEntries) * 8;
+	{
+		std::lock_guard<std::mutex> g(dev->mtx);        // lrb_scene_free takes the scene's whole device_bytes off again
+		dev->counters.device_bytes_in_use += (entries - s->spillEntries) * 8;
+	}
 	s->spillEntries = entries;
 	return LRB_OK;
 }
@@ -1765,6 +1769,7 @@ int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t nVerts, cons
 	uint32_t *dStatus = dErr.as<uint32_t>();
 	cudaMemsetAsync(dBelow.p, 0, (size_t)nWide * 4, st);
 	cudaMemsetAsync(dArrived.p, 0, (size_t)nWide * 4, st);
+	cudaMemsetAsync(dParentOf.p, 0xff, (size_t)nWide * 4, st);
 	RelayoutFillKernel<<<(int)((total + 127) / 128), 128, 0, st>>>(tv, dWideOf.as<uint32_t>(), s->dNodes, s->dTris, s->dIds, dParentOf.as<uint32_t>(),
 			reinterpret_cast<float *>(dStatus + 2), dStatus);
 	StackNeedKernel<<<(int)((nWide + 255) / 256), 256, 0, st>>>(s->dNodes, nWide, dParentOf.as<uint32_t>(), dBelow.as<uint32_t>(), dArrived.as<uint32_t>(), dStatus + 1);
@@ -1787,6 +1792,10 @@ int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t nVerts, cons
 	if (status[0] != kRelayoutOk) {
 		lrb_scene_free(s);
 		return Fail(LRB_ERR_INVALID, RelayoutErrorString((int)status[0]));
+	}
+	if (status[1] < 2 * (kWideSlots - 1)) {     // entry node + root: the smallest tree already needs this much
+		lrb_scene_free(s);
+		return Fail(LRB_ERR_INTERNAL, "device re-layout: the stack bound was not computed");
 	}
 	dev->counters.kernel_launches += launches;
 
@@ -1826,6 +1835,27 @@ int lrb_bvh_build_scene(lrb_device *dev, const float *xyz, uint64_t nVerts, cons
 		timings->kernels = launches;
 	}
 	*out = s;
+	return LRB_OK;
+}
+
+int lrb_scene_download(lrb_scene *s, void *wide, void *tris, void *ids) {
+	if (!s)
+		return Fail(LRB_ERR_INVALID, "null scene");
+	if (s->view.twoLevel)
+		return Fail(LRB_ERR_INVALID, "lrb_scene_download serves single-level scenes");
+	lrb_device *dev = s->dev;
+	LRB_SETDEV(dev);
+	{
+		const int rc = JoinPending(dev);
+		if (rc != LRB_OK) return rc;
+	}
+	if (wide && s->info.n_wide_nodes)
+		LRB_CUDA(cudaMemcpyAsync(wide, s->dNodes, (size_t)s->info.n_wide_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost, dev->stream));
+	if (tris && s->info.n_triangles)
+		LRB_CUDA(cudaMemcpyAsync(tris, s->dTris, (size_t)s->info.n_triangles * sizeof(TriRecord), cudaMemcpyDeviceToHost, dev->stream));
+	if (ids && s->info.n_triangles)
+		LRB_CUDA(cudaMemcpyAsync(ids, s->dIds, (size_t)s->info.n_triangles * sizeof(TriIds), cudaMemcpyDeviceToHost, dev->stream));
+	LRB_CUDA(cudaStreamSynchronize(dev->stream));
 	return LRB_OK;
 }
 

@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(256) StackNeedKernel(const WideNode *__restric
 		return;
 	uint32_t cur = w;
 	uint32_t D = StackNeedOfNode(wide[cur], 0u);
-	for (;;) {
+	for (uint32_t hops = 0; hops <= nWide; ++hops) {    // a walk up is shorter than the node count (bound against corrupt links)
 		const uint32_t p = parentOf[cur];
-		if (p == kNullIndex) {
-			*result = D;
+		if (p >= nWide) {
+			if (cur == 0u)
+				*result = D;        // the entry node has no parent
 			return;
 		}
 		atomicMax(below + p, D);

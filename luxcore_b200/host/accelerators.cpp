@@ -51,12 +51,15 @@ static ocl::BVHArrayNode *RunBuilder(const Context *ctx, const char *who, const 
 //------------------------------------------------------------------------------
 
 BVHAccel::BVHAccel(const Context *context) : nNodes(0), bvhTree(nullptr), ctx(context),
-		totalVertexCount(0), totalTriangleCount(0), initialized(false) {
+		totalVertexCount(0), totalTriangleCount(0), initialized(false),
+		allowResidentScene(true), residentScene(nullptr), residentOrdinal(-1) {
 	params = ToBVHParams(ctx->GetConfig());
 }
 
 BVHAccel::~BVHAccel() {
 	delete[] bvhTree;
+	if (residentScene)
+		FreeB200ResidentScene(residentScene);
 }
 
 BVHParams BVHAccel::ToBVHParams(const Properties &props) {
@@ -80,6 +83,25 @@ void BVHAccel::Init(const std::deque<const Mesh *> &ms, const u_longlong totVert
 		bvhTree = nullptr;
 		initialized = true;
 		return;
+	}
+
+	// GPU builders: boxes, tree, leaf payload and the device lay-out are all made on the device (no BVHTreeNode list, no
+	// host re-layout at upload); the reference array is downloaded once for bvhTree.  "accelerator.b200.resident" = false
+	// keeps the two-step path (lrb_build_bvh from host boxes, lrb_bvh_upload of the array).
+	{
+		const std::string builderType = ctx->GetConfig().Get(Property("accelerator.bvh.builder.type")("EMBREE_BINNED_SAH")).Get<std::string>();
+		const bool gpuBuilder = builderType == "EMBREE_MORTON" || builderType == "B200_PLOC";
+		if (gpuBuilder && allowResidentScene && totalTriangleCount > 1 &&
+				ctx->GetConfig().Get(Property("accelerator.b200.resident")(true)).Get<bool>()) {
+			const double tb = WallClockTime();
+			if (BuildB200SceneOnDevice(params, builderType == "B200_PLOC" ? 1u : 0u, meshes, &bvhTree, &nNodes, &residentScene, &residentOrdinal)) {
+				LR_LOG(ctx, "BVH builder: " << builderType << " (scene resident on CUDA device " << residentOrdinal << ")");
+				LR_LOG(ctx, "BVH build hierarchy time: " << int((WallClockTime() - tb) * 1000) << "ms");
+				LR_LOG(ctx, "Total BVH memory usage: " << nNodes * sizeof(ocl::BVHArrayNode) / 1024 << "Kbytes");
+				initialized = true;
+				return;
+			}
+		}
 	}
 
 	const double t0 = WallClockTime();
@@ -190,6 +212,7 @@ void MBVHAccel::Init(const std::deque<const Mesh *> &ms, const u_longlong, const
 		std::map<const Mesh *, u_int>::iterator it = leafOfBase.find(base);
 		if (!share || it == leafOfBase.end()) {
 			BVHAccel *leaf = new BVHAccel(ctx);
+			leaf->allowResidentScene = false;       // leaf trees travel as arrays (lrb_mbvh_upload)
 			const std::deque<const Mesh *> one(1, base);
 			leaf->Init(one, base->GetTotalVertexCount(), base->GetTotalTriangleCount());
 			leafIndex = (u_int)uniqueLeafs.size();

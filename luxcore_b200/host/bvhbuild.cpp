@@ -787,6 +787,83 @@ static Node *BuildOnDevice(const BVHParams &params, u_int *nNodes, const std::de
 	return arr;
 }
 
+// All meshes' vertices back to back in dataset order (world-space positions for instances when the BVH was built with
+// instance support disabled), first vertex of every mesh: what BVHKernel hands lrb_bvh_upload (bvhaccelhw.cpp:68-92).
+void GatherSceneVertices(const std::deque<const Mesh *> &meshes, std::vector<float> &xyz, std::vector<uint32_t> &offsets) {
+	size_t total = 0;
+	for (size_t m = 0; m < meshes.size(); ++m)
+		total += meshes[m]->GetTotalVertexCount();
+	xyz.clear();
+	offsets.clear();
+	xyz.reserve(3 * total);
+	for (size_t m = 0; m < meshes.size(); ++m) {
+		const Mesh *mesh = meshes[m];
+		offsets.push_back((uint32_t)(xyz.size() / 3));
+		const u_int n = mesh->GetTotalVertexCount();
+		if (mesh->GetType() == TYPE_TRIANGLE || mesh->GetType() == TYPE_EXT_TRIANGLE) {
+			const float *src = reinterpret_cast<const float *>(mesh->GetVertices());
+			xyz.insert(xyz.end(), src, src + 3 * (size_t)n);
+		} else {
+			for (u_int i = 0; i < n; ++i) {
+				const Point p = mesh->GetVertex(Transform::TRANS_IDENTITY, i);
+				xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z);
+			}
+		}
+	}
+}
+
+bool BuildB200SceneOnDevice(const BVHParams &params, const u_int quality, const std::deque<const Mesh *> &meshes,
+		Node **nodes, u_int *nNodes, void **scene, int *ordinal) {
+	lrb_device *dev = BuilderDevice();
+	if (!dev)
+		return false;
+	std::vector<float> xyz;
+	std::vector<uint32_t> vertOff, triOff;
+	GatherSceneVertices(meshes, xyz, vertOff);
+	// triangle indices: luxrays::Triangle is three u_int (include/luxrays/core/geometry/triangle.h:35-53)
+	static_assert(sizeof(Triangle) == 3 * sizeof(uint32_t), "Triangle layout");
+	size_t nTris = 0;
+	triOff.push_back(0u);
+	for (size_t m = 0; m < meshes.size(); ++m) {
+		nTris += meshes[m]->GetTotalTriangleCount();
+		triOff.push_back((uint32_t)nTris);
+	}
+	if (nTris >= 0x3fffffffu)
+		throw std::runtime_error("GPU BVH builder: too many triangles");
+	const uint32_t *tris;
+	std::vector<uint32_t> triBuf;
+	if (meshes.size() == 1)
+		tris = reinterpret_cast<const uint32_t *>(meshes[0]->GetTriangles());       // one mesh: its own array, no copy
+	else {
+		triBuf.reserve(3 * nTris);
+		for (size_t m = 0; m < meshes.size(); ++m) {
+			const uint32_t *src = reinterpret_cast<const uint32_t *>(meshes[m]->GetTriangles());
+			triBuf.insert(triBuf.end(), src, src + 3 * (size_t)meshes[m]->GetTotalTriangleCount());
+		}
+		tris = triBuf.data();
+	}
+	const size_t cap = 2 * nTris;
+	Node *arr = new Node[cap];
+	uint32_t total = 0;
+	lrb_scene *sc = nullptr;
+	static_assert(sizeof(Node) == sizeof(lrb_bvh_node), "BVHArrayNode layout");
+	if (lrb_bvh_build_scene(dev, xyz.data(), xyz.size() / 3, vertOff.data(), triOff.data(), (uint32_t)meshes.size(), tris, params.treeType, quality,
+			&sc, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, nullptr) != LRB_OK) {
+		delete[] arr;
+		throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+	}
+	lrb_device_props props;
+	*ordinal = lrb_device_get_props(dev, &props) == LRB_OK ? props.cuda_ordinal : -1;
+	*nodes = arr;
+	*nNodes = total;
+	*scene = sc;
+	return true;
+}
+
+void FreeB200ResidentScene(void *scene) {
+	lrb_scene_free(static_cast<lrb_scene *>(scene));
+}
+
 Node *BuildEmbreeBVHMorton(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList) {
 	return BuildOnDevice(params, nNodes, meshes, leafList, 0u);
 }

@@ -12,6 +12,8 @@
 
 namespace luxrays {
 
+void GatherSceneVertices(const std::deque<const Mesh *> &meshes, std::vector<float> &xyz, std::vector<uint32_t> &offsets);    // bvhbuild.cpp
+
 static void Check(const int rc, const char *what) {
 	if (rc != LRB_OK)
 		throw std::runtime_error(std::string(what) + ": " + lrb_last_error_string());
@@ -51,25 +53,20 @@ class BVHKernel : public HardwareIntersectionKernel, public B200SceneOwner {
 public:
 	BVHKernel(HardwareIntersectionDevice &dev, const BVHAccel &bvh) : HardwareIntersectionKernel(dev), scene(nullptr) {
 		lrb_device *nd = NativeOf(dev);
-		// All meshes' vertices back to back, in dataset order; GetVertex() yields world-space
-		// positions for instances when the BVH was built with instance support disabled.
-		std::vector<float> xyz;
-		std::vector<uint32_t> offsets;
-		xyz.reserve(3 * (size_t)bvh.totalVertexCount);
-		for (size_t m = 0; m < bvh.meshes.size(); ++m) {
-			const Mesh *mesh = bvh.meshes[m];
-			offsets.push_back((uint32_t)(xyz.size() / 3));
-			const u_int n = mesh->GetTotalVertexCount();
-			if (mesh->GetType() == TYPE_TRIANGLE || mesh->GetType() == TYPE_EXT_TRIANGLE) {
-				const float *src = reinterpret_cast<const float *>(mesh->GetVertices());
-				xyz.insert(xyz.end(), src, src + 3 * (size_t)n);
-			} else {
-				for (u_int i = 0; i < n; ++i) {
-					const Point p = mesh->GetVertex(Transform::TRANS_IDENTITY, i);
-					xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z);
-				}
+		// A GPU-built accelerator is already laid out on its device (BVHAccel::Init, lrb_bvh_build_scene): the kernel of that
+		// CUDA device takes the scene over; any other device gets the array like a host-built one.
+		if (bvh.residentScene) {
+			lrb_device_props props;
+			if (lrb_device_get_props(nd, &props) == LRB_OK && props.cuda_ordinal == bvh.residentOrdinal &&
+					lrb_scene_adopt(nd, static_cast<lrb_scene *>(bvh.residentScene)) == LRB_OK) {
+				scene = static_cast<lrb_scene *>(bvh.residentScene);
+				bvh.residentScene = nullptr;
+				return;
 			}
 		}
+		std::vector<float> xyz;
+		std::vector<uint32_t> offsets;
+		GatherSceneVertices(bvh.meshes, xyz, offsets);
 		Check(lrb_bvh_upload(nd, reinterpret_cast<const lrb_bvh_node *>(bvh.bvhTree), bvh.nNodes,
 				xyz.empty() ? nullptr : xyz.data(), xyz.size() / 3,
 				offsets.empty() ? nullptr : offsets.data(), (uint32_t)offsets.size(), &scene), "BVHKernel upload");
