@@ -556,6 +556,14 @@ def main():
     t0 = time.perf_counter()
     sess.trace_host_ptr(h_rays.data_ptr(), h_hits.data_ptr(), n)
     plugin_s = time.perf_counter() - t0
+    # (not timed) what came back through the host pipelines is, byte for byte, what a device-resident trace of the batch gives
+    h_hits2 = torch.empty_like(h_hits)
+    scene.trace_host_ptr(h_rays.data_ptr(), h_hits2.data_ptr(), n)
+    d_chk = torch.empty((n, 20), dtype=torch.uint8, device=device)
+    sess.trace_device(rays.data_ptr(), d_chk.data_ptr(), n)
+    torch.cuda.synchronize()
+    e2e_verified = bool(torch.equal(d_chk, h_hits.to(device))) and bool(torch.equal(d_chk, h_hits2.to(device)))
+    del d_chk, h_hits2
 
     # ---- what the implementation itself asks memory for (instrumented kernel) ----
     st = scene.trace_stats(rays.data_ptr(), 0, n)
@@ -608,6 +616,7 @@ def main():
                       "signal": (args.completion if pipeline else ("nccl" if gather_mode == "p2p" else None)), "verified": gather_ok,
                       "bytes_per_step_into_rank0": (total_rays - counts[0]) * 20 if world > 1 else 0},
            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 20,
+                   "verified_against_device_trace": e2e_verified,
                    "api": "lrb_trace_host (C ABI, pinned host buffers, chunked copy/trace overlap)",
                    "plugin_sequence_mrays_per_s": round(n / plugin_s / 1e6, 2)}}
     if parity:

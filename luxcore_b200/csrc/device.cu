@@ -24,6 +24,7 @@
 #include "luxrays_b200.h"
 #include "layout.h"
 #include "relayout.h"
+#include "host_chunks.h"
 #include "trace_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "build_kernels.cuh"
@@ -89,6 +90,8 @@ struct lrb_device {
 	void *sortTemp;
 	size_t sortCap, sortTempBytes;
 	int hostChunk;                  // rays per chunk in lrb_trace_host
+	int hostTaper;                  // 1: the last chunks shrink geometrically down to hostMinChunk rays (host_chunks.h), 0: uniform chunks
+	int hostMinChunk;
 	// The reference-facing call sequence (AllocBufferRW(src) / EnqueueTraceRayBuffer / EnqueueReadBuffer / FinishQueue =
 	// lrb_h2d / lrb_trace / lrb_d2h / lrb_sync) pipelined behind its own interface: a large asynchronous upload is cut
 	// into chunks on the copy-in stream, a trace whose ray buffer is exactly that upload follows it chunk by chunk, a
@@ -97,7 +100,8 @@ struct lrb_device {
 	int pipeline;                   // option "pipeline": 1 (default) = as described, 0 = every call on the queue as it is
 	struct Pending {
 		const char *base;           // device range [base, base + bytes)
-		size_t bytes, chunkBytes;
+		size_t bytes;
+		std::vector<uint64_t> ends;     // exclusive end of every chunk in BYTES of this range (host_chunks.h: the tail tapers)
 		std::vector<cudaEvent_t> ev;    // one per chunk (borrowed from pipeEvents)
 		bool active;
 	} pendUpload[2], pendTraced;
@@ -201,15 +205,24 @@ static int PipelinedUpload(lrb_device *dev, void *dst, const void *src, size_t b
 	if (rc != LRB_OK) return rc;
 	LRB_CUDA(cudaEventRecord(start, dev->stream));
 	LRB_CUDA(cudaStreamWaitEvent(dev->copyInStream, start, 0));
-	const size_t chunk = (size_t)dev->hostChunk * sizeof(lrb_ray);     // a whole number of rays AND of RayHits (48 = lcm-friendly: 12 x 4)
-	u.base = (const char *)dst; u.bytes = bytes; u.chunkBytes = chunk; u.ev.clear();
-	for (size_t off = 0; off < bytes; off += chunk) {
-		const size_t cnt = std::min(chunk, bytes - off);
+	// chunk boundaries in whole rays (48 B: a ray buffer cut this way is traced chunk by chunk, lrb_trace); a remainder
+	// that is not a whole ray -- some other kind of buffer -- travels with the last chunk
+	u.base = (const char *)dst; u.bytes = bytes; u.ev.clear();
+	ChunkEnds(bytes / sizeof(lrb_ray), (uint64_t)dev->hostChunk, (uint64_t)dev->hostMinChunk, dev->hostTaper != 0, &u.ends);
+	for (uint64_t &e : u.ends)
+		e *= sizeof(lrb_ray);
+	if (u.ends.empty())
+		u.ends.push_back(bytes);
+	u.ends.back() = bytes;
+	size_t off = 0;
+	for (size_t c = 0; c < u.ends.size(); ++c) {
+		const size_t cnt = (size_t)u.ends[c] - off;
 		LRB_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, cnt, cudaMemcpyHostToDevice, dev->copyInStream));
 		cudaEvent_t e;
 		if ((rc = PipeEvent(dev, &e)) != LRB_OK) return rc;
 		LRB_CUDA(cudaEventRecord(e, dev->copyInStream));
 		u.ev.push_back(e);
+		off = (size_t)u.ends[c];
 	}
 	u.active = true;
 	return LRB_OK;
@@ -291,6 +304,8 @@ int lrb_device_create(int ordinal, lrb_device **out) {
 	dev->sortTemp = nullptr;
 	dev->sortCap = dev->sortTempBytes = 0;
 	dev->hostChunk = 1 << 20;
+	dev->hostTaper = 1;
+	dev->hostMinChunk = 1 << 16;
 	dev->pipeline = 1;
 	dev->pendUpload[0].active = dev->pendUpload[1].active = dev->pendTraced.active = false;
 	dev->pipeEventNext = 0;
@@ -424,6 +439,12 @@ int lrb_device_set_option(lrb_device *dev, const char *key, const char *value) {
 	} else if (k == "host_chunk") {
 		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_chunk too small");
 		dev->hostChunk = iv;
+	} else if (k == "host_taper") {
+		if (iv < 0 || iv > 1) return Fail(LRB_ERR_INVALID, "host_taper must be 0 or 1");
+		dev->hostTaper = iv;
+	} else if (k == "host_min_chunk") {
+		if (iv < 1024) return Fail(LRB_ERR_INVALID, "host_min_chunk too small");
+		dev->hostMinChunk = iv;
 	} else
 		return Fail(LRB_ERR_INVALID, "unknown option: " + k);
 	return LRB_OK;
@@ -492,11 +513,12 @@ int lrb_d2h(lrb_device *dev, void *dst, const void *src, size_t bytes, int block
 	lrb_device::Pending &t = dev->pendTraced;
 	if (t.active && (const char *)src == t.base && bytes == t.bytes) {
 		// the RayHit buffer of the chunked trace: every chunk leaves as soon as it has been traced
-		size_t c = 0;
-		for (size_t off = 0; off < bytes; off += t.chunkBytes, ++c) {
-			const size_t cnt = std::min(t.chunkBytes, bytes - off);
+		size_t off = 0;
+		for (size_t c = 0; c < t.ends.size(); ++c) {
+			const size_t cnt = (size_t)t.ends[c] - off;
 			LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, t.ev[c], 0));
 			LRB_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, cnt, cudaMemcpyDeviceToHost, dev->copyOutStream));
+			off = (size_t)t.ends[c];
 		}
 		t.active = false;
 		dev->copyOutBusy = true;
@@ -1208,13 +1230,15 @@ int lrb_trace(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
 		if (o.active && !o.ev.empty())
 			LRB_CUDA(cudaStreamWaitEvent(dev->stream, o.ev.back(), 0));
 		o.active = false;
-		const uint32_t chunkRays = (uint32_t)(u.chunkBytes / sizeof(lrb_ray));
 		const std::vector<cudaEvent_t> landed = u.ev;
+		const std::vector<uint64_t> rayEnds = u.ends;       // bytes of the ray buffer; u.bytes == n * 48, so every end is a whole ray
 		u.active = false;       // (the launches below join whatever else is pending; the queue follows this upload chunk by chunk)
 		std::vector<cudaEvent_t> traced;
-		size_t c = 0;
-		for (uint32_t first = 0; first < n; first += chunkRays, ++c) {
-			const uint32_t cnt = std::min(chunkRays, n - first);
+		std::vector<uint64_t> hitEnds;
+		uint32_t first = 0;
+		for (size_t c = 0; c < rayEnds.size(); ++c) {
+			const uint32_t end = (uint32_t)(rayEnds[c] / sizeof(lrb_ray));
+			const uint32_t cnt = end - first;
 			LRB_CUDA(cudaStreamWaitEvent(dev->stream, landed[c], 0));
 			int rc = LaunchTrace(s, (const lrb_ray *)rays + first, (lrb_rayhit *)hits + first, cnt, false, dev->stream);
 			if (rc != LRB_OK) {
@@ -1226,9 +1250,12 @@ int lrb_trace(lrb_scene *s, const void *rays, void *hits, uint32_t n) {
 			if ((rc = PipeEvent(dev, &e)) != LRB_OK) return rc;
 			LRB_CUDA(cudaEventRecord(e, dev->stream));
 			traced.push_back(e);
+			hitEnds.push_back((uint64_t)end * sizeof(lrb_rayhit));
+			first = end;
 		}
 		lrb_device::Pending &t = dev->pendTraced;
-		t.base = (const char *)hits; t.bytes = (size_t)n * sizeof(lrb_rayhit); t.chunkBytes = (size_t)chunkRays * sizeof(lrb_rayhit);
+		t.base = (const char *)hits; t.bytes = (size_t)n * sizeof(lrb_rayhit);
+		t.ends.swap(hitEnds);
 		t.ev.swap(traced);
 		t.active = true;
 		return LRB_OK;
@@ -2155,8 +2182,9 @@ int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t
 	if (!anyMasked)     // masked rays leave their record untouched: make what is read back for them deterministic
 		LRB_CUDA(cudaMemsetAsync(dev->stageHits, 0, hb, dev->stream));
 
-	const uint32_t chunk = (uint32_t)dev->hostChunk;
-	const uint32_t nChunks = (n + chunk - 1) / chunk;
+	std::vector<uint64_t> ends;
+	ChunkEnds(n, (uint64_t)dev->hostChunk, (uint64_t)dev->hostMinChunk, dev->hostTaper != 0, &ends);
+	const uint32_t nChunks = (uint32_t)ends.size();
 	while (dev->events.size() < 3 * (size_t)nChunks + 1) {
 		cudaEvent_t e;
 		LRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2168,7 +2196,7 @@ int lrb_trace_host(lrb_scene *s, const lrb_ray *rays, lrb_rayhit *hits, uint32_t
 	LRB_CUDA(cudaStreamWaitEvent(dev->copyInStream, start, 0));
 	LRB_CUDA(cudaStreamWaitEvent(dev->copyOutStream, start, 0));
 	for (uint32_t c = 0; c < nChunks; ++c) {
-		const uint32_t first = c * chunk, cnt = std::min(chunk, n - first);
+		const uint32_t first = c ? (uint32_t)ends[c - 1] : 0u, cnt = (uint32_t)ends[c] - first;
 		lrb_ray *dR = (lrb_ray *)dev->stageRays + first;
 		lrb_rayhit *dH = (lrb_rayhit *)dev->stageHits + first;
 		cudaEvent_t in = dev->events[3 * c], done = dev->events[3 * c + 1];

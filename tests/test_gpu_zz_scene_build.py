@@ -188,3 +188,29 @@ def test_host_layer_resident_scene_equals_the_two_step_path(builder):
     for s in (a, b):
         s.stop()
         s.close()
+
+
+def test_resident_scene_of_a_flattened_instance_scene():
+    """accelerator.instances.enable = 0: the BVH is built over world-space copies of the instances (dataset.h:43); the device
+    build gets those vertices (Mesh::GetVertex) and the base meshes' triangle indices.  Same array and hits as the two-step
+    path, and the oracle's flattened BVH walking that array agrees bit for bit."""
+    import scene_zoo as Z
+    desc = Z.instances_scene(10)
+    cfg = {"accelerator.instances.enable": 0, "accelerator.bvh.builder.type": "B200_PLOC"}
+    a = hostapi.Session(dict(cfg), desc)
+    a.start(0)
+    b = hostapi.Session(dict(cfg, **{"accelerator.b200.resident": 0}), desc)
+    b.start(0)
+    assert a.accelerator_type() == hostapi.ACCEL_BVH and b.accelerator_type() == hostapi.ACCEL_BVH
+    assert a.bvh_nodes().tobytes() == b.bvh_nodes().tobytes()
+    lo, hi = desc.bbox()
+    pad = 0.1 * (hi - lo)
+    rays = R.to_numpy_rays(R.uniform_rays(lo - pad, hi + pad, 200000, seed=97))
+    ga, gb = a.trace_host(rays), b.trace_host(rays)
+    assert ga.tobytes() == gb.tobytes()
+    ref = O.BVH(H.oracle_scene(desc), nodes=a.bvh_nodes()).intersect(rays)
+    rep = H.compare_hits(ga, ref, rays, what="resident/flattened")
+    assert rep["bit_exact_hits"] == rep["hits"] and rep["hits"] > 0
+    for s in (a, b):
+        s.stop()
+        s.close()
