@@ -275,6 +275,26 @@ class Emu:
         return hits
 
 
+def chunk_ends(n, chunk=1 << 20, min_chunk=1 << 16, taper=True):
+    """Python restatement of luxcore_b200/csrc/host_chunks.h ChunkEnds (held to it by tests/test_host_chunks_cpu.py): the
+    pieces a batch from host memory is cut into by lrb_trace_host and by the pipelined plugin sequence."""
+    chunk = max(1, chunk)
+    min_chunk = min(max(1, min_chunk), chunk)
+    ends, pos = [], 0
+    while pos < n:
+        rem = n - pos
+        c = chunk
+        if taper and n > chunk and rem <= 2 * chunk:
+            c = (rem // 2 + 1023) & ~1023
+            c = min(max(c, min_chunk), chunk)
+            if rem <= min_chunk:
+                c = rem
+        c = min(c, rem)
+        pos += c
+        ends.append(pos)
+    return ends
+
+
 def flattened_triangles(desc):
     """Triangle index buffer + per-mesh triangle offsets (n_meshes + 1 entries) in dataset order: what
     lrb_bvh_build_scene takes next to flattened_from_oracle's vertices (mesh-local indices, luxrays::Triangle::v)."""

@@ -53,7 +53,7 @@ def test_pipelined_sequence_equals_the_plain_one(world):
     dev.set_option("pipeline", 1)
     c0 = dev.counters().trace_launches
     piped = _sequence(dev, scene, rays)
-    assert dev.counters().trace_launches - c0 == 4          # really chunked: 3 full chunks + the tail
+    assert dev.counters().trace_launches - c0 == len(H.chunk_ends(rays.shape[0])) == 7      # really chunked: 2 full chunks, then the tail halves down to 64 Ki rays (host_chunks.h)
     assert piped.tobytes() == plain.tobytes()
     assert _sequence(dev, scene, rays, blocking_read=True).tobytes() == plain.tobytes()
     # and both are the reference's answer
@@ -128,7 +128,7 @@ def test_host_layer_sequence_uses_the_pipeline():
     rays = R.to_numpy_rays(R.uniform_rays(lo, hi, 2 << 20, seed=72))
     c0 = s.counters().trace_launches
     got = s.trace_host(rays)
-    assert s.counters().trace_launches - c0 == 2
+    assert s.counters().trace_launches - c0 == len(H.chunk_ends(rays.shape[0])) == 6
     sel = np.random.default_rng(3).choice(rays.shape[0], 60000, replace=False)
     ref = O.BVH(H.oracle_scene(desc), nodes=s.bvh_nodes()).intersect(rays[sel])
     rep = H.compare_hits(got[sel], ref, rays[sel], what="host layer, pipelined")

@@ -8,6 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import helpers as H
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -52,6 +54,7 @@ def test_pieces_tile_the_batch(ends, taper):
             if n // int(chunk) > 100000:
                 continue
             e = ends(n, int(chunk), int(mn), taper)
+            assert e == H.chunk_ends(n, int(chunk), int(mn), taper)     # the restatement the GPU tests count launches with
             s = sizes(e)
             assert (n == 0 and e == []) or (e[-1] == n and all(x > 0 for x in s)), (n, chunk, mn)
             assert all(x <= chunk for x in s)
