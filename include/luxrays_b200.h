@@ -157,7 +157,7 @@ LRB_API int lrb_device_get_props(lrb_device *dev, lrb_device_props *out);
 LRB_API int lrb_device_set_stream(lrb_device *dev, void *cuda_stream);
 LRB_API int lrb_device_get_stream(lrb_device *dev, void **cuda_stream);
 /* Tunables (strings): "kernel" = "persistent"|"simple", "blocks_per_sm", "smem_depth",
- * "refill_below", "tri_bias", "inst_bias", "host_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
+ * "refill_below", "tri_bias", "inst_bias", "host_chunk", "host_taper", "host_min_chunk", "sort_rays" (0 never | 1 always | 2 = default: scenes larger than L2),
  * "sort_bits", "sort_min_rays", "gather_stores", "gather_chunk_shift", "gather_defer", "wide_stores",
  * "prefetch" (L2 prefetch of pushed children: 0 never = default | 1 always | 2 scenes larger than L2),
  * "compact" (0 = default: masked rays are skipped inside the kernel | 1 = lrb_trace compacts the live rays first |
@@ -173,7 +173,8 @@ LRB_API int lrb_free(lrb_device *dev, void *devptr);
 /* One in-order queue, as in the reference.  Behind that contract the reference-facing sequence
  *     AllocBufferRW(&rays, hostRays) -> EnqueueTraceRayBuffer(rays, hits, n) -> EnqueueReadBuffer(hits, hostHits) -> FinishQueue
  *   = lrb_h2d(rays_dev, ..., blocking = 0) -> lrb_trace(scene, rays_dev, hits_dev, n) -> lrb_d2h(hostHits, hits_dev, ...) -> lrb_sync
- * is pipelined: a non-blocking upload of >= 32 MB travels in chunks of "host_chunk" rays on a copy stream, a trace
+ * is pipelined: a non-blocking upload of >= 32 MB travels in chunks of "host_chunk" rays on a copy stream (the last
+ * chunks halve down to "host_min_chunk" rays unless "host_taper" is 0: the pipeline's drain is one small piece), a trace
  * whose ray buffer is exactly that upload follows it chunk by chunk, and a read of exactly that trace's RayHit buffer
  * follows the trace chunk by chunk on a second copy stream (PCIe is full duplex).  Any other call first joins the
  * queue with whatever is pending, so results and ordering are those of the plain sequence; as with the reference's
