@@ -176,6 +176,33 @@ def make_bounce_batch(trace_fn, desc, n_rays, seed, device, depth=2):
     return rays
 
 
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: keep this rank's host threads -- and, by first touch, its pinned Ray / RayHit buffers -- on the
+    NUMA node its GPU hangs off, so that eight ranks streaming 70 GB/s each do not all go through one socket's memory
+    controllers and the inter-socket link (the host-buffer `e2e` of round 1 scaled 2.15x at 8 GPUs).  Reads the GPU's node
+    from sysfs; a no-op (reported as such) when the platform does not tell.  -> dict for the JSON line."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"bound": False, "gpu": bdf, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = set()
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            for part in f.read().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"bound": False, "gpu": bdf, "node": node, "why": "none of the node's CPUs is available to this process"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "gpu": bdf, "node": node, "cpus": len(allowed)}
+    except Exception as e:      # no sysfs, no permission, ...: run unbound
+        return {"bound": False, "why": ("%s: %s" % (type(e).__name__, e))[:120]}
+
+
 def oracle_for(desc, nodes, accel="BVH"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
@@ -249,6 +276,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="device option key=value")
+    ap.add_argument("--numa", default="auto", choices=["auto", "on", "off"], help="bind the rank's host threads (and so its pinned buffers) to the NUMA node "
+                    "of its GPU: auto = when there is more than one rank (at N = 1 the CPU baseline keeps every host core)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,6 +311,7 @@ def main():
     device = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(stream)
+    numa = bind_to_gpu_numa_node(local_rank) if (args.numa == "on" or (args.numa == "auto" and world > 1)) else {"bound": False, "why": "one rank: not requested"}
 
     desc = build_scene_arrays(args.scene)
     # GPU builders (EMBREE_MORTON / B200_PLOC) build on the GPU the rank traces on, so that the scene stays where it was built
@@ -619,6 +649,7 @@ def main():
                    "verified_against_device_trace": e2e_verified,
                    "api": "lrb_trace_host (C ABI, pinned host buffers, chunked copy/trace overlap)",
                    "plugin_sequence_mrays_per_s": round(n / plugin_s / 1e6, 2)}}
+    out["numa"] = numa
     if parity:
         out["parity_check"] = parity
     if timeline:
