@@ -3,10 +3,13 @@
 //
 // Builders emit the reference's depth-first skip-list array of 32-byte BVHArrayNode records:
 //   CLASSIC            restated from src/luxrays/core/bvh/bvhclassicbuild.cpp (bit-identical arrays)
-//   EMBREE_BINNED_SAH  the reference calls Embree's rtcBuildBVH (bvhembreebuild.cpp:218-280), a
-//   EMBREE_MORTON      third-party library; here both names select this tree's own from-scratch
-//                      binned-SAH k-ary builder (same array format, same "one triangle per leaf,
-//                      <= treeType children per node" contract; topology is ours).
+//   EMBREE_BINNED_SAH  the reference calls Embree's rtcBuildBVH (bvhembreebuild.cpp:218-280), a third-party
+//                      library; here this tree's own from-scratch binned-SAH builder with insertion-based
+//                      optimisation and optimal k-ary collapse (luxcore_b200/host/bvhbuild.cpp);
+//   EMBREE_MORTON      the fast builder (rtcBVHBuilderMorton there): here a radix tree built ON THE GPU
+//   B200_PLOC          (extension) the GPU builder with a PLOC binary tree (luxcore_b200/csrc/build_kernels.cuh).
+//   All emit the same array format under the same contract: one triangle per leaf, <= treeType children
+//   per node; topology is ours and never changes a closest hit.
 #ifndef _LUXRAYS_B200_BVHBUILD_H
 #define _LUXRAYS_B200_BVHBUILD_H
 
