@@ -139,6 +139,15 @@ def one_level(rng, it):
     osc = H.oracle_scene(desc)
     verts, offs = H.flattened_from_oracle(desc, osc)
     emu = H.Emu.bvh(nodes, verts, offs)
+    if nodes.shape[0] > 1:
+        # the DEVICE re-layout's per-record code (relayout_kernels.cuh, driven in the device pipeline's order on the host):
+        # leaf payload, indices by exclusive sum, fill, bottom-up stack bound -- the bytes of the host re-layout
+        tri, toff = H.flattened_triangles(desc)
+        dv = H.RelayoutDev.run(H.to_builder_format(nodes, toff), verts, offs, tri, toff)
+        w, t, i = emu.arrays()
+        assert dv["ref_nodes"].tobytes() == nodes.tobytes(), ("device leaf payload", it)
+        assert dv["wide"].tobytes() == w.tobytes() and dv["tris"].tobytes() == t.tobytes() and dv["ids"].tobytes() == i.tobytes(), ("device re-layout", it)
+        assert dv["stack_need"] == emu.info()["stack_need"], ("device stack bound", it, dv["stack_need"], emu.info())
     rays = random_rays(rng, desc, 3000, int(rng.integers(1, 1 << 30)))
     ref = O.BVH(osc, nodes=nodes).intersect(rays)
     if REFERENCE and SKIP_BELOW <= CURRENT[0]:
