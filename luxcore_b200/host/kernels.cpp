@@ -55,13 +55,19 @@ public:
 		lrb_device *nd = NativeOf(dev);
 		// A GPU-built accelerator is already laid out on its device (BVHAccel::Init, lrb_bvh_build_scene): the kernel of that
 		// CUDA device takes the scene over; any other device gets the array like a host-built one.
+		// (One DataSet may serve several devices, each started from its own host thread -- the reference's model: exactly
+		// one kernel takes the scene, atomically.)
 		if (bvh.residentScene) {
 			lrb_device_props props;
-			if (lrb_device_get_props(nd, &props) == LRB_OK && props.cuda_ordinal == bvh.residentOrdinal &&
-					lrb_scene_adopt(nd, static_cast<lrb_scene *>(bvh.residentScene)) == LRB_OK) {
-				scene = static_cast<lrb_scene *>(bvh.residentScene);
-				bvh.residentScene = nullptr;
-				return;
+			if (lrb_device_get_props(nd, &props) == LRB_OK && props.cuda_ordinal == bvh.residentOrdinal) {
+				void *taken = __atomic_exchange_n(&bvh.residentScene, (void *)nullptr, __ATOMIC_ACQ_REL);
+				if (taken) {
+					if (lrb_scene_adopt(nd, static_cast<lrb_scene *>(taken)) == LRB_OK) {
+						scene = static_cast<lrb_scene *>(taken);
+						return;
+					}
+					lrb_scene_free(static_cast<lrb_scene *>(taken));     // could not be handed over: upload the array instead
+				}
 			}
 		}
 		std::vector<float> xyz;
