@@ -691,7 +691,7 @@ static int SetL2Window(lrb_device *dev, const void *base, size_t bytes) {
 	return LRB_OK;
 }
 
-template <class T> static int UploadArray(lrb_device *dev, const std::vector<T> &src, T **dst, size_t *cap, uint64_t *bytes) {
+template <class V, class T = typename V::value_type> static int UploadArray(lrb_device *dev, const V &src, T **dst, size_t *cap, uint64_t *bytes) {
 	const size_t n = src.size();
 	if (cap && *dst && *cap >= n) {
 		// re-use the allocation (Update path)
@@ -846,9 +846,9 @@ int lrb_bvh_upload(lrb_device *dev, const lrb_bvh_node *nodes, uint32_t nNodes, 
 		return rc;
 	}
 	// single-level scenes never change: drop the host copy (the view / info keep the bookkeeping)
-	std::vector<WideNode>().swap(s->host.wide);
-	std::vector<TriRecord>().swap(s->host.tris);
-	std::vector<TriIds>().swap(s->host.ids);
+	RawVector<WideNode>().swap(s->host.wide);
+	RawVector<TriRecord>().swap(s->host.tris);
+	RawVector<TriIds>().swap(s->host.ids);
 	*out = s;
 	return LRB_OK;
 }
@@ -874,8 +874,8 @@ int lrb_mbvh_upload(lrb_device *dev, const lrb_mbvh_desc *desc, lrb_scene **out)
 		return rc;
 	}
 	// triangles are immutable under Update; the wide nodes / instances stay on the host
-	std::vector<TriRecord>().swap(s->host.tris);
-	std::vector<TriIds>().swap(s->host.ids);
+	RawVector<TriRecord>().swap(s->host.tris);
+	RawVector<TriIds>().swap(s->host.ids);
 	s->host.tris.resize(0);
 	*out = s;
 	return LRB_OK;

@@ -9,11 +9,14 @@
 #include "traverse.h"       // MotionSample: the kernels' own MotionSystem::Sample, compiled for the host
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <cstdlib>
 #include <exception>
+#include <functional>
 #include <stdexcept>
 #include <thread>
 
@@ -357,14 +360,29 @@ static void AddSlot(const TreeInput &in, const std::vector<uint32_t> &wideOf, ui
 
 // Appends the wide form of one reference tree to `out`.  Returns the wide index of its root
 // (kNullIndex for an empty tree) and the tree's worst-case stack need.
+// development switch LRB_RELAYOUT_VERBOSE=1: wall time of the phases of a conversion on stderr
+struct PhaseTimer {
+	bool on;
+	std::chrono::steady_clock::time_point t;
+	PhaseTimer() : on(getenv("LRB_RELAYOUT_VERBOSE") != nullptr), t(std::chrono::steady_clock::now()) {}
+	void operator()(const char *what) {
+		if (!on) return;
+		const std::chrono::steady_clock::time_point n = std::chrono::steady_clock::now();
+		fprintf(stderr, "luxrays_b200 re-layout: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+		t = n;
+	}
+};
+
 static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stackNeed) {
 	*stackNeed = 0;
 	if (in.n == 0)
 		return kNullIndex;
+	PhaseTimer phase;
 	std::string err;
 	if (!ValidateTree(in.nodes, in.n, &err))
 		throw std::runtime_error("malformed BVHArrayNode array: " + err);
 
+	phase("validate");
 	const uint32_t wideStart = (uint32_t)out->wide.size();
 	const lrb_bvh_node *nodes = in.nodes;
 	std::vector<uint32_t> wideOf(in.n, kNullIndex);
@@ -394,30 +412,107 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 	uint32_t nWide = 1;
 	uint64_t nLeafTotal = 0;
 	const size_t triStart = out->tris.size();
-	if (!in.instLeaves) {
-		uint64_t nTriLeaves = 0;
-		for (uint32_t i = 0; i < in.n; ++i)
-			if (IsLeaf(nodes[i].nodeData))
-				wideOf[i] = (uint32_t)(triStart + nTriLeaves++);
-		if (triStart + nTriLeaves >= kMaxRefIndex)
-			throw std::runtime_error("too many leaves");
+	// Big triangle trees (a 50 M-triangle soup: 74 M reference nodes) run both passes on several threads: ranges of the
+	// array are independent once every node knows its indices.  Instance trees append to `insts` and stay serial.
+	unsigned nThreads = 1;
+	if (!in.instLeaves && in.n >= 400000u) {
+		nThreads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+		if (const char *env = getenv("LRB_RELAYOUT_THREADS"))
+			nThreads = (unsigned)std::max(1, atoi(env));
 	}
-	for (uint32_t i = 0; i < in.n; ++i) {
-		if (IsLeaf(nodes[i].nodeData))
-			continue;
-		const uint32_t end = Skip(nodes[i].nodeData);
-		uint32_t nKids = 0;
-		for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData)) {
-			if (IsLeaf(nodes[c].nodeData)) ++nLeafTotal;
-			++nKids;
+	// fn(first node, end node, thread number) over nThreads contiguous ranges of the array
+	auto inRanges = [&](const std::function<void(uint32_t, uint32_t, unsigned)> &fn) {
+		if (nThreads <= 1) {
+			fn(0, in.n, 0);
+			return;
 		}
-		wideOf[i] = wideStart + nWide;
-		nWide += std::max<uint32_t>(1u, (nKids + kWideSlots - 1) / kWideSlots);
+		std::vector<std::thread> pool;
+		std::vector<std::exception_ptr> errors(nThreads);
+		const uint64_t per = ((uint64_t)in.n + nThreads - 1) / nThreads;
+		for (unsigned t = 0; t < nThreads; ++t) {
+			const uint32_t i0 = (uint32_t)std::min<uint64_t>(in.n, per * t), i1 = (uint32_t)std::min<uint64_t>(in.n, per * (t + 1));
+			pool.emplace_back([&, t, i0, i1]() {
+				try {
+					fn(i0, i1, t);
+				} catch (...) {
+					errors[t] = std::current_exception();
+				}
+			});
+		}
+		for (std::thread &th : pool)
+			th.join();
+		for (unsigned t = 0; t < nThreads; ++t)
+			if (errors[t])
+				std::rethrow_exception(errors[t]);
+	};
+	if (nThreads > 1) {
+		// counts per range, exclusive prefix over the ranges, indices: the same numbers the serial loops below give
+		std::vector<uint64_t> leaves(nThreads, 0), wides(nThreads, 0);
+		inRanges([&](const uint32_t i0, const uint32_t i1, const unsigned t) {
+			uint64_t nl = 0, nw = 0;
+			for (uint32_t i = i0; i < i1; ++i) {
+				if (IsLeaf(nodes[i].nodeData)) {
+					++nl;
+					continue;
+				}
+				const uint32_t w = WideNodesFor(CountKids(nodes, i));
+				wideOf[i] = w;
+				nw += w;
+			}
+			leaves[t] = nl;
+			wides[t] = nw;
+		});
+		std::vector<uint64_t> leafBase(nThreads), wideBase(nThreads);
+		uint64_t l = triStart, w = (uint64_t)wideStart + 1;
+		for (unsigned t = 0; t < nThreads; ++t) {
+			leafBase[t] = l; wideBase[t] = w;
+			l += leaves[t]; w += wides[t];
+		}
+		nLeafTotal = l - triStart;
+		if (l >= kMaxRefIndex)
+			throw std::runtime_error("too many leaves");
+		if (w >= kMaxRefIndex)
+			throw std::runtime_error("too many wide nodes");
+		nWide = (uint32_t)(w - wideStart);
+		inRanges([&](const uint32_t i0, const uint32_t i1, const unsigned t) {
+			uint64_t li = leafBase[t], wi = wideBase[t];
+			for (uint32_t i = i0; i < i1; ++i) {
+				if (IsLeaf(nodes[i].nodeData))
+					wideOf[i] = (uint32_t)li++;
+				else {
+					const uint32_t cnt = wideOf[i];
+					wideOf[i] = (uint32_t)wi;
+					wi += cnt;
+				}
+			}
+		});
+	} else {
+		if (!in.instLeaves) {
+			uint64_t nTriLeaves = 0;
+			for (uint32_t i = 0; i < in.n; ++i)
+				if (IsLeaf(nodes[i].nodeData))
+					wideOf[i] = (uint32_t)(triStart + nTriLeaves++);
+			if (triStart + nTriLeaves >= kMaxRefIndex)
+				throw std::runtime_error("too many leaves");
+		}
+		for (uint32_t i = 0; i < in.n; ++i) {
+			if (IsLeaf(nodes[i].nodeData))
+				continue;
+			const uint32_t end = Skip(nodes[i].nodeData);
+			uint32_t nKids = 0;
+			for (uint32_t c = i + 1; c < end; c = Skip(nodes[c].nodeData)) {
+				if (IsLeaf(nodes[c].nodeData)) ++nLeafTotal;
+				++nKids;
+			}
+			wideOf[i] = wideStart + nWide;
+			nWide += std::max<uint32_t>(1u, (nKids + kWideSlots - 1) / kWideSlots);
+		}
 	}
 	if ((uint64_t)wideStart + nWide >= kMaxRefIndex)
 		throw std::runtime_error("too many wide nodes");
 	if ((in.instLeaves ? out->insts.size() : out->tris.size()) + nLeafTotal >= kMaxRefIndex)
 		throw std::runtime_error("too many leaves");
+	phase("pass 1 (indices)");
 	out->wide.resize((size_t)wideStart + nWide);
 	if (in.instLeaves)
 		out->insts.reserve(out->insts.size() + nLeafTotal);
@@ -444,6 +539,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		}
 	}
 
+	phase("allocate");
 	// Pass 2: fill, children in reference order.  Every inner node writes its own wide node(s) and its own
 	// triangle records (indices fixed in pass 1), so ranges of the array are filled concurrently for big triangle
 	// trees (a 50 M-triangle soup: 74 M reference nodes); instance trees append to `insts` and stay serial.
@@ -494,35 +590,9 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 			}
 		}
 	};
-	unsigned nThreads = 1;
-	if (!in.instLeaves && in.n >= 400000u) {
-		nThreads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-		if (const char *env = getenv("LRB_RELAYOUT_THREADS"))
-			nThreads = (unsigned)std::max(1, atoi(env));
-	}
-	if (nThreads <= 1)
-		fillRange(0, in.n);
-	else {
-		std::vector<std::thread> pool;
-		std::vector<std::exception_ptr> errors(nThreads);
-		const uint64_t per = ((uint64_t)in.n + nThreads - 1) / nThreads;
-		for (unsigned t = 0; t < nThreads; ++t) {
-			const uint32_t i0 = (uint32_t)std::min<uint64_t>(in.n, per * t), i1 = (uint32_t)std::min<uint64_t>(in.n, per * (t + 1));
-			pool.emplace_back([&, t, i0, i1]() {
-				try {
-					fillRange(i0, i1);
-				} catch (...) {
-					errors[t] = std::current_exception();
-				}
-			});
-		}
-		for (std::thread &th : pool)
-			th.join();
-		for (unsigned t = 0; t < nThreads; ++t)
-			if (errors[t])
-				std::rethrow_exception(errors[t]);
-	}
+	inRanges([&](const uint32_t i0, const uint32_t i1, unsigned) { fillRange(i0, i1); });
 
+	phase("pass 2 (fill)");
 	// Worst-case live stack entries.  Children always have larger wide indices than their parent
 	// (depth-first pre-order), so one reverse sweep suffices.  Visiting w pushes every entry but the
 	// one it continues with:  D[w] = (slots of w) - 1 + max over entries D[entry];  entering an
@@ -551,6 +621,7 @@ static uint32_t ConvertTree(const TreeInput &in, WideScene *out, uint32_t *stack
 		D[r] = (k > 0 ? k - 1 : 0) + below;
 	}
 	*stackNeed = D[0];
+	phase("stack bound");
 	return wideStart;
 }
 

@@ -5,7 +5,9 @@
 #define LRB_RELAYOUT_H
 
 #include <stdint.h>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "luxrays_b200.h"
@@ -13,10 +15,25 @@
 
 namespace lrb {
 
+// std::vector whose resize() leaves new elements of a trivial type UNINITIALISED instead of zero-filling them: the big
+// arrays of a scene (50 M triangles: 5 GB) are written exactly once, by the threads of the re-layout's fill pass, and a
+// serial zero-fill in front of that pass cost as much as the pass itself (and put every page on the resizing thread's
+// NUMA node).  Every element must be written before it is read: the fill pass writes every wide node and record.
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+	template <class U> struct rebind { typedef DefaultInitAllocator<U> other; };
+	DefaultInitAllocator() {}
+	template <class U> DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
+	template <class U> void construct(U *p) { ::new ((void *)p) U; }
+	template <class U, class A0, class... Args> void construct(U *p, A0 &&a0, Args &&... args) {
+		::new ((void *)p) U(std::forward<A0>(a0), std::forward<Args>(args)...);
+	}
+};
+template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T> >;
+
 struct WideScene {
-	std::vector<WideNode> wide;
-	std::vector<TriRecord> tris;
-	std::vector<TriIds> ids;
+	RawVector<WideNode> wide;
+	RawVector<TriRecord> tris;
+	RawVector<TriIds> ids;
 	std::vector<InstRecord> insts;
 	std::vector<DevInterp> interps;
 	std::vector<uint32_t> motionFirst, motionLast;

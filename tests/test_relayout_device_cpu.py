@@ -84,3 +84,27 @@ def test_mesh_lookup_skips_empty_meshes():
     w = shifted["w"]
     w[leaf, 3] = np.where(w[leaf, 3] >= 1, w[leaf, 3] + 1, w[leaf, 3])
     _check(shifted, verts, voff2, tri, toff2, "cornell + empty mesh")
+
+
+def test_threaded_host_relayout_is_the_serial_one(monkeypatch):
+    """Arrays of 400 000 nodes and more are laid out on several threads (index pass: counts per range + exclusive prefix;
+    fill pass: ranges of the array) into buffers that are not zero-filled first (relayout.h RawVector): the bytes must not
+    depend on the thread count, and equal the device re-layout's."""
+    import hashlib
+    n = 300000
+    desc = S.random_soup(n, seed=11, size=0.002 * (50e6 / n) ** (1.0 / 3.0), name="soup")
+    osc, verts, voff, tri, toff = _arrays(desc)
+    monkeypatch.setenv("LRB_BVH_OPT", "0")          # the plain top-down builder: any tree will do, this one is quick
+    sess = hostapi.Session({"accelerator.type": "BVH", "accelerator.bvh.builder.type": "EMBREE_BINNED_SAH", "accelerator.bvh.treetype": 4}, desc)
+    sess.build_accelerator("BVH")
+    nodes = sess.bvh_nodes()
+    assert nodes.shape[0] >= 400000
+    digests = set()
+    for threads in ("1", "2", "5", "16"):
+        monkeypatch.setenv("LRB_RELAYOUT_THREADS", threads)
+        emu = H.Emu.bvh(nodes, verts, voff)
+        w, t, i = emu.arrays()
+        digests.add((hashlib.sha256(w.tobytes() + t.tobytes() + i.tobytes()).hexdigest(), emu.info()["stack_need"]))
+    assert len(digests) == 1
+    monkeypatch.setenv("LRB_RELAYOUT_THREADS", "7")
+    _check(nodes, verts, voff, tri, toff, "soup 300k, 7 threads")
