@@ -736,6 +736,13 @@ static lrb_device *BuilderDevice() {
 	return dev;
 }
 
+// The builder device is one in-order queue shared by the whole process: builds from several host threads (several
+// DataSets preprocessed at once) take turns.  (lrb_last_error_string is thread-local: read under the same lock.)
+static std::mutex &BuilderQueueMutex() {
+	static std::mutex m;
+	return m;
+}
+
 static Node *BuildOnDevice(const BVHParams &params, u_int *nNodes, const std::deque<const Mesh *> *meshes, LeafList &leafList, const uint32_t quality) {
 	lrb_device *dev = leafList.empty() ? nullptr : BuilderDevice();
 	if (!dev) {
@@ -756,9 +763,12 @@ static Node *BuildOnDevice(const BVHParams &params, u_int *nNodes, const std::de
 	uint32_t total = 0;
 	lrb_build_timings tm;
 	static_assert(sizeof(Node) == sizeof(lrb_bvh_node), "BVHArrayNode layout");
-	if (lrb_build_bvh(dev, boxes.data(), (uint32_t)n, params.treeType, quality, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, &tm) != LRB_OK) {
-		delete[] arr;
-		throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+	{
+		std::lock_guard<std::mutex> turn(BuilderQueueMutex());
+		if (lrb_build_bvh(dev, boxes.data(), (uint32_t)n, params.treeType, quality, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, &tm) != LRB_OK) {
+			delete[] arr;
+			throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+		}
 	}
 	// leaf payload (the device wrote the input index of every leaf into the first word)
 	for (uint32_t i = 0; i < total; ++i) {
@@ -847,10 +857,13 @@ bool BuildB200SceneOnDevice(const BVHParams &params, const u_int quality, const 
 	uint32_t total = 0;
 	lrb_scene *sc = nullptr;
 	static_assert(sizeof(Node) == sizeof(lrb_bvh_node), "BVHArrayNode layout");
-	if (lrb_bvh_build_scene(dev, xyz.data(), xyz.size() / 3, vertOff.data(), triOff.data(), (uint32_t)meshes.size(), tris, params.treeType, quality,
-			&sc, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, nullptr) != LRB_OK) {
-		delete[] arr;
-		throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+	{
+		std::lock_guard<std::mutex> turn(BuilderQueueMutex());
+		if (lrb_bvh_build_scene(dev, xyz.data(), xyz.size() / 3, vertOff.data(), triOff.data(), (uint32_t)meshes.size(), tris, params.treeType, quality,
+				&sc, reinterpret_cast<lrb_bvh_node *>(arr), (uint32_t)cap, &total, nullptr) != LRB_OK) {
+			delete[] arr;
+			throw std::runtime_error(std::string("GPU BVH builder failed: ") + lrb_last_error_string());
+		}
 	}
 	lrb_device_props props;
 	*ordinal = lrb_device_get_props(dev, &props) == LRB_OK ? props.cuda_ordinal : -1;
