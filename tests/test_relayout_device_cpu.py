@@ -108,3 +108,37 @@ def test_threaded_host_relayout_is_the_serial_one(monkeypatch):
     assert len(digests) == 1
     monkeypatch.setenv("LRB_RELAYOUT_THREADS", "7")
     _check(nodes, verts, voff, tri, toff, "soup 300k, 7 threads")
+
+
+@pytest.mark.parametrize("quality,tree_type", [(0, 4), (1, 4), (1, 8), (0, 2)])
+def test_whole_device_pipeline_restated_on_the_host(quality, tree_type):
+    """lrb_bvh_build_scene end to end without a GPU: LeafBoxBody's boxes -> the Python restatement of the builder kernels
+    (tests/builder_reference.py: leaves carry the input triangle number, as EmitKernel writes them) -> leaf payload, indices,
+    fill and stack bound by the device bodies.  The result must be the host re-layout of the payload-carrying array, and the
+    emulated traversal of it must give the oracle's closest hits."""
+    import builder_reference as BR
+    from luxcore_b200 import rays as R
+    desc = S.load_fixture("cornell")
+    rng = np.random.default_rng(5)
+    c = rng.random((700, 1, 3)) * 4 - 2
+    v = (c + rng.normal(scale=0.15, size=(700, 3, 3))).astype(np.float32).reshape(-1, 3)
+    desc.add_plain(desc.add_shape(v, np.arange(2100, dtype=np.uint32).reshape(-1, 3)))      # cornell + a 700-triangle cloud
+    osc, verts, voff, tri, toff = _arrays(desc)
+    # the boxes the device computes (compared with the definition in the soup test above)
+    probe = H.RelayoutDev.run(H.to_builder_format(O.BVH(osc, tree_type=4).nodes(), toff), verts, voff, tri, toff)
+    built = BR.build(probe["boxes"], tree_type, quality)        # builder output format
+    dev = H.RelayoutDev.run(built, verts, voff, tri, toff)
+    nodes = dev["ref_nodes"].astype(O.NODE_DTYPE)
+    # payload: every triangle once, with its own vertex indices
+    leaf = (nodes["nodeData"] >> 31) == 1
+    w = nodes["w"][leaf]
+    g = toff[w[:, 3]].astype(np.int64) + w[:, 4]
+    assert np.array_equal(np.sort(g), np.arange(tri.shape[0])) and np.array_equal(w[:, :3], tri[g])
+    emu = H.Emu.bvh(nodes, verts, voff)
+    wide, tris, ids = emu.arrays()
+    assert dev["wide"].tobytes() == wide.tobytes() and dev["tris"].tobytes() == tris.tobytes() and dev["ids"].tobytes() == ids.tobytes()
+    assert dev["stack_need"] == emu.info()["stack_need"]
+    lo, hi = desc.bbox()
+    rays = R.to_numpy_rays(R.uniform_rays(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), 20000, seed=3))
+    rep = H.compare_hits(emu.trace(rays), O.BVH(osc, nodes=nodes).intersect(rays), rays, what="device pipeline restated")
+    assert rep["bit_exact_hits"] == rep["hits"] and rep["hits"] > 0
