@@ -10,6 +10,14 @@
  *                                   :308-466 UpdateBVHNodes/Update, :468-507 launch)
  *   - bvh.cl / mbvh.cl             (include/luxrays/accelerators/bvh.cl:228-260, mbvh.cl:351-383:
  *                                   Accelerator_Intersect_RayBuffer)
+ * and, one step outwards, what it reaches through Embree and SLG's own loops:
+ *   - BuildEmbreeBVHMorton / BinnedSAH (src/luxrays/core/bvh/bvhembreebuild.cpp:218-336) and, for trees built on
+ *     the GPU, BVHAccel::Init itself (src/luxrays/accelerators/bvhaccel.cpp:72-168): lrb_build_bvh,
+ *     lrb_bvh_build_scene
+ *   - Scene::Intersect's pass-through loop and shadow rays (src/slg/scene/scene.cpp:556-690), the masked-ray
+ *     contract of the path tracer (pathoclbase_kernels_micro.cl:34-106,1029): lrb_trace_anyhit, lrb_compact_rays,
+ *     lrb_trace_indexed, lrb_advance_rays, lrb_trace_passthrough
+ *   - the film merge of PathOCLRenderEngine (src/slg/engines/pathocl/pathocl.cpp:184-201): lrb_film_reduce
  *
  * The C++ host layer in luxcore_b200/host (namespace luxrays, same class names as the reference)
  * sits on top of this ABI; INTEGRATION.md shows the binding a LuxCore maintainer would add.
